@@ -1,0 +1,150 @@
+// GEMM epilogue shared by the tcgen05 kernel (gemm_tc.cu) and the fp32 SIMT kernel (gemm_simt.cu).
+#pragma once
+
+#include "../../include/klab_b200.h"
+#include "common.cuh"
+
+namespace klab {
+
+struct EpiDropout {
+    uint32_t keep_threshold;
+    float inv_keep;
+    bool on;
+};
+
+__host__ __device__ inline EpiDropout make_dropout(float p) {
+    EpiDropout d;
+    d.on = p > 0.0f;
+    const double keep = 1.0 - static_cast<double>(p);
+    d.keep_threshold = d.on ? static_cast<uint32_t>(keep * 4294967295.0) : 0xFFFFFFFFu;
+    d.inv_keep = d.on ? static_cast<float>(1.0 / keep) : 1.0f;
+    return d;
+}
+
+// Load `CH` consecutive elements of a row into fp32 registers (vector path when aligned and full).
+template <int CH>
+__device__ __forceinline__ void load_chunk(const void* base, int dt, long long idx0, int nvalid, float (&out)[CH]) {
+    if (dt == KLAB_BF16) {
+        const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(base) + idx0;
+        if (nvalid == CH && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+            for (int i = 0; i < CH / 8; ++i) {
+                const uint4 q = reinterpret_cast<const uint4*>(p)[i];
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __bfloat1622float2(h[j]);
+                    out[i * 8 + 2 * j] = f.x;
+                    out[i * 8 + 2 * j + 1] = f.y;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) out[i] = i < nvalid ? __bfloat162float(p[i]) : 0.0f;
+        }
+    } else {
+        const float* p = reinterpret_cast<const float*>(base) + idx0;
+        if (nvalid == CH && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+            for (int i = 0; i < CH / 4; ++i) {
+                const float4 q = reinterpret_cast<const float4*>(p)[i];
+                out[i * 4] = q.x; out[i * 4 + 1] = q.y; out[i * 4 + 2] = q.z; out[i * 4 + 3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) out[i] = i < nvalid ? p[i] : 0.0f;
+        }
+    }
+}
+
+template <int CH>
+__device__ __forceinline__ void store_chunk(void* base, int dt, long long idx0, int nvalid, const float (&v)[CH]) {
+    if (dt == KLAB_BF16) {
+        __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(base) + idx0;
+        if (nvalid == CH && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+            for (int i = 0; i < CH / 8; ++i) {
+                uint4 q;
+                __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(v[i * 8 + 2 * j], v[i * 8 + 2 * j + 1]);
+                reinterpret_cast<uint4*>(p)[i] = q;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < CH; ++i)
+                if (i < nvalid) p[i] = __float2bfloat16_rn(v[i]);
+        }
+    } else {
+        float* p = reinterpret_cast<float*>(base) + idx0;
+        if (nvalid == CH && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+            for (int i = 0; i < CH / 4; ++i)
+                reinterpret_cast<float4*>(p)[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < CH; ++i)
+                if (i < nvalid) p[i] = v[i];
+        }
+    }
+}
+
+// Apply the epilogue to CH consecutive columns [col0, col0+nvalid) of output row `row` and store.
+template <int CH>
+__device__ __forceinline__ void epilogue_apply_store(const klab_gemm_epilogue& e, const EpiDropout& dr, float (&v)[CH],
+                                                     long long row, long long col0, int nvalid, int N,
+                                                     void* D, long long ldd) {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) v[i] *= e.alpha;
+    if (e.bias) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i)
+            if (i < nvalid) v[i] += __ldg(e.bias + col0 + i);
+    }
+    if (e.aux_out) store_chunk<CH>(e.aux_out, e.out_dtype, row * e.ld_aux_out + col0, nvalid, v);
+    if (e.act == KLAB_ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.0f);
+    } else if (e.act == KLAB_ACT_GELU) {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) v[i] = gelu_erf(v[i]);
+    } else if (e.act == KLAB_ACT_RELU_BWD || e.act == KLAB_ACT_GELU_BWD) {
+        float a[CH];
+        load_chunk<CH>(e.aux_in, e.aux_in_dtype, row * e.ld_aux_in + col0, nvalid, a);
+        if (e.act == KLAB_ACT_RELU_BWD) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] = a[i] > 0.0f ? v[i] : 0.0f;
+        } else {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] *= gelu_erf_grad(a[i]);
+        }
+    }
+    if (dr.on) {
+        const uint64_t base = static_cast<uint64_t>(row) * static_cast<uint64_t>(N) + static_cast<uint64_t>(col0);
+#pragma unroll
+        for (int i = 0; i < CH; ++i) v[i] *= dropout_scale(e.dropout_seed, base + i, dr.keep_threshold, dr.inv_keep);
+    }
+    if (e.residual) {
+        float r[CH];
+        load_chunk<CH>(e.residual, e.res_dtype, row * e.ldr + col0, nvalid, r);
+#pragma unroll
+        for (int i = 0; i < CH; ++i) v[i] += r[i];
+    }
+    if (e.accumulate) {
+        float r[CH];
+        load_chunk<CH>(D, e.out_dtype, row * ldd + col0, nvalid, r);
+#pragma unroll
+        for (int i = 0; i < CH; ++i) v[i] += r[i];
+    }
+    store_chunk<CH>(D, e.out_dtype, row * ldd + col0, nvalid, v);
+}
+
+// launchers (defined in gemm_tc.cu / gemm_simt.cu)
+int gemm_tc_launch(cudaStream_t stream, int M, int N, int K, const void* A, long long lda, int a_mn,
+                   const void* B, long long ldb, int b_mn, void* D, long long ldd, const klab_gemm_epilogue& epi);
+int gemm_simt_launch(cudaStream_t stream, int in_dtype, int M, int N, int K, const void* A, long long lda, int a_mn,
+                     const void* B, long long ldb, int b_mn, void* D, long long ldd, const klab_gemm_epilogue& epi);
+
+void count_launch(int n = 1);
+
+}  // namespace klab
