@@ -81,6 +81,98 @@ int klab_gemm_simt(void* stream, int in_dtype, int M, int N, int K,
                    const void* B, long long ldb, int b_mn_major,
                    void* D, long long ldd, const klab_gemm_epilogue* epi);
 
+/* ---- K8: T5 RMSNorm (HF/models/t5/modeling_t5.py:55-68) -------------------------------------
+ * y = x * rsqrt(mean(x^2) + eps) * gamma; fp32 statistics; gamma is fp32.  Output rows may be "grouped":
+ * row r is written at y + (r / y_rows_per_group) * y_group_stride + (r % y_rows_per_group) * ldy
+ * (y_rows_per_group = 0: plain r * ldy) so the frozen text encoder writes straight into the concatenated
+ * [image tokens; text tokens] buffer (/root/reference/models/model.py:23).  rstd_out (fp32 [rows]) may be NULL.
+ * bwd: dx = rstd * (dy*gamma - xhat * mean(dy*gamma*xhat)) + dres;  dgamma (+)= sum_rows dy * xhat. */
+int klab_rmsnorm_fwd(void* stream, int dtype, long long rows, int d, const void* x, long long ldx, const float* gamma, float eps,
+                     void* y, long long ldy, int y_rows_per_group, long long y_group_stride, float* rstd_out);
+int klab_rmsnorm_bwd(void* stream, int dtype, long long rows, int d, const void* dy, long long lddy, const void* x, long long ldx,
+                     const float* gamma, const float* rstd, const void* dres, long long lddres, void* dx, long long lddx,
+                     float* dgamma, int accumulate_dgamma, void* workspace);
+long long klab_norm_bwd_workspace_bytes(long long rows, int d);
+
+/* ---- K6: LayerNorm, Swin-V2 res-post-norm form (HF/models/swinv2/modeling_swinv2.py:273,386,707-712,969) ----
+ * y = LN(x) * gamma + beta (+ residual).  bwd: dx = LN'(dy) (+ dres); dgamma/dbeta (+)= column sums.
+ * The backward can read dy through the same grouped row map (gradient of the concat buffer). */
+int klab_layernorm_fwd(void* stream, int dtype, long long rows, int d, const void* x, long long ldx, const float* gamma,
+                       const float* beta, float eps, const void* residual, long long ldres, void* y, long long ldy,
+                       int y_rows_per_group, long long y_group_stride, float* mean_out, float* rstd_out);
+int klab_layernorm_bwd(void* stream, int dtype, long long rows, int d, const void* dy, long long lddy, int dy_rows_per_group,
+                       long long dy_group_stride, const void* x, long long ldx, const float* gamma, const float* mean,
+                       const float* rstd, const void* dres, long long lddres, void* dx, long long lddx, float* dgamma,
+                       float* dbeta, int accumulate_dparams, void* workspace);
+
+/* out[c] (+)= sum_r x[r,c]: bias gradients of the Swin linears. */
+int klab_colsum(void* stream, int dtype, long long rows, int d, const void* x, long long ldx, float* out, int accumulate,
+                void* workspace);
+long long klab_colsum_workspace_bytes(long long rows, int d);
+
+/* ---- K9: T5 attention (HF/models/t5/modeling_t5.py:253-344; bias :189-251; causal mask :704) ----
+ * q/k/v/out live in the [B*L, H*d_kv] layout of the projection GEMMs (row strides ld*); head h uses columns
+ * [h*d_kv, (h+1)*d_kv).  scores = q k^T (unscaled) + bias_table[rel_bucket[(j - i - q_offset) + rel_zero], h];
+ * causal: key j visible iff j <= i + q_offset.  bias_table NULL = cross-attention (zero bias).  rel_bucket is
+ * the int32 LUT of T5Attention._relative_position_bucket built by the host with the reference's own torch ops
+ * (bit-exact bucket edges).  lse fp32 [B,H,Lq] is saved for backward.  dropout_p > 0 drops probabilities with a
+ * counter-based RNG keyed by (seed, b, h, i, j) that backward regenerates.
+ * bwd: dq/dk/dv in the same layouts; dbias_table [num_buckets,H] is ACCUMULATED (the table of block 0 receives
+ * the gradient of every block, :758). */
+int klab_t5_attention_fwd(void* stream, int dtype, int B, int H, int Lq, int Lk, int d_kv, const void* q, long long ldq,
+                          const void* k, long long ldk, const void* v, long long ldv, void* out, long long ldo,
+                          const float* bias_table, const int* rel_bucket, int rel_zero, int num_buckets, int causal,
+                          int q_offset, float* lse, float dropout_p, unsigned long long seed);
+int klab_t5_attention_bwd(void* stream, int dtype, int B, int H, int Lq, int Lk, int d_kv, const void* q, long long ldq,
+                          const void* k, long long ldk, const void* v, long long ldv, const void* out, const void* dout,
+                          long long ldo, void* dq, void* dk, void* dv, const float* bias_table, const int* rel_bucket,
+                          int rel_zero, int num_buckets, int causal, int q_offset, const float* lse, float* dbias_table,
+                          float dropout_p, unsigned long long seed, void* workspace);
+long long klab_t5_attention_bwd_workspace_bytes(int B, int H, int Lq, int num_buckets);
+
+/* ---- K2+K3+K4: Swin-V2 shifted-window cosine attention (HF/models/swinv2/modeling_swinv2.py:421-487,
+ * window_partition/roll/reverse :146-166,:678,:698, shift mask :627-653) -------------------------------
+ * q/k/v (row stride ld; dq/dk/dv use the same) and ctx/dctx (row stride ldc) are [B*res*res, heads*head_dim] in natural token order; the window partition, the
+ * cyclic shift and the {0,-200} shift mask are computed from coordinates inside the kernel.
+ * bias = 16*sigmoid(CPB) [heads,N,N] from klab_swin_cpb_fwd; logit_scale is the raw parameter [heads].
+ * bwd OVERWRITES dbias [heads,N,N] and dlogit_scale [heads]. */
+int klab_swin_attention_fwd(void* stream, int dtype, int B, int res, int heads, int head_dim, int window, int shift,
+                            const void* q, const void* k, const void* v, long long ld, void* ctx, long long ldc,
+                            const float* logit_scale, const float* bias, float* lse);
+int klab_swin_attention_bwd(void* stream, int dtype, int B, int res, int heads, int head_dim, int window, int shift,
+                            const void* q, const void* k, const void* v, long long ld, const void* ctx, const void* dctx,
+                            long long ldc, void* dq, void* dk, void* dv, const float* logit_scale, const float* bias,
+                            const float* lse, float* dbias, float* dlogit_scale);
+/* Continuous position bias MLP (:408-410,:450-460; tables :489-524 are built by the host). */
+int klab_swin_cpb_fwd(void* stream, int table_rows, int hidden_units, int heads, int n_tokens, const float* coords,
+                      const int* index, const float* w1, const float* b1, const float* w2, float* hidden, float* tab, float* bias);
+int klab_swin_cpb_bwd(void* stream, int table_rows, int hidden_units, int heads, int n_tokens, const float* coords,
+                      const int* index, const float* w2, const float* hidden, const float* tab, const float* dbias, float* dtab,
+                      float* dw1, float* db1, float* dw2, int accumulate);
+
+/* ---- K11 + T8: embedding gather with _shift_right fused (HF/models/t5/modeling_t5.py:595-614,:682) and its
+ * scatter-add backward into the tied fp32 embedding gradient. ids are int64 [B,L]. */
+int klab_embedding_fwd(void* stream, int dtype, int B, int L, const long long* ids, int shift_right, int start_id, int pad_id,
+                       const void* table, long long vocab, int d, void* out, long long ldo, int* err_flag);
+int klab_embedding_bwd(void* stream, int dtype, int B, int L, const long long* ids, int shift_right, int start_id, int pad_id,
+                       const void* dout, long long ldo, int d, float* dtable, long long vocab);
+
+/* ---- K1 / K7 data movement: patch-embedding im2col (Conv2d k=s=P, :329) and patch-merging 2x2 gather (:374-383;
+ * scatter = 1 is the inverse permutation used by backward). */
+int klab_patchify(void* stream, int out_dtype, int B, int C, int H, int W, int P, const float* pixels, void* out, long long ldo);
+int klab_patch_merge(void* stream, int dtype, int B, int res, int C, const void* in, void* out, int scatter);
+
+/* ---- K10 (generic path): cross entropy with ignore_index = -100 over materialised logits
+ * (HF/models/t5/modeling_t5.py:1114-1117). stats = {mean loss, #non-ignored rows}.  bwd overwrites the logits
+ * with d loss / d logits scaled by *gscale (device scalar, may be NULL = 1). */
+int klab_ce_fwd(void* stream, int dtype, long long rows, int V, const void* logits, long long ld, const long long* labels,
+                float* lse, float* row_loss, float* stats, int* err_flag);
+int klab_ce_bwd(void* stream, int dtype, long long rows, int V, void* logits, long long ld, int ld_pad, const long long* labels,
+                const float* lse, const float* stats, const float* gscale);
+
+/* dtype conversion (fp32 master weights -> bf16 operand copies). */
+int klab_cast(void* stream, int src_dtype, int dst_dtype, long long n, const void* src, void* dst);
+
 #ifdef __cplusplus
 }
 #endif

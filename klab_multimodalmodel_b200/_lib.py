@@ -46,7 +46,7 @@ def check(rc: int) -> None:
         raise RuntimeError(f"libklab_b200: {lib().klab_last_error().decode()} (status {rc})")
 
 
-_vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+_vp, _i, _ll, _f, _ull = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulonglong
 
 # name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/klab_b200.h
 SIGNATURES = {
@@ -56,8 +56,32 @@ SIGNATURES = {
     "klab_launch_count": [],
     "klab_gemm": [_vp, _i, _i, _i, _i, _vp, _ll, _i, _vp, _ll, _i, _vp, _ll, C.POINTER(GemmEpilogue)],
     "klab_gemm_simt": [_vp, _i, _i, _i, _i, _vp, _ll, _i, _vp, _ll, _i, _vp, _ll, C.POINTER(GemmEpilogue)],
+    "klab_rmsnorm_fwd": [_vp, _i, _ll, _i, _vp, _ll, _vp, _f, _vp, _ll, _i, _ll, _vp],
+    "klab_rmsnorm_bwd": [_vp, _i, _ll, _i, _vp, _ll, _vp, _ll, _vp, _vp, _vp, _ll, _vp, _ll, _vp, _i, _vp],
+    "klab_norm_bwd_workspace_bytes": [_ll, _i],
+    "klab_layernorm_fwd": [_vp, _i, _ll, _i, _vp, _ll, _vp, _vp, _f, _vp, _ll, _vp, _ll, _i, _ll, _vp, _vp],
+    "klab_layernorm_bwd": [_vp, _i, _ll, _i, _vp, _ll, _i, _ll, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _vp, _ll, _vp, _vp, _i, _vp],
+    "klab_colsum": [_vp, _i, _ll, _i, _vp, _ll, _vp, _i, _vp],
+    "klab_colsum_workspace_bytes": [_ll, _i],
+    "klab_t5_attention_fwd": [_vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _vp, _f, _ull],
+    "klab_t5_attention_bwd": [_vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp,
+                              _i, _i, _i, _i, _vp, _vp, _f, _ull, _vp],
+    "klab_t5_attention_bwd_workspace_bytes": [_i, _i, _i, _i],
+    "klab_swin_attention_fwd": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _ll, _vp, _ll, _vp, _vp, _vp],
+    "klab_swin_attention_bwd": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "klab_swin_cpb_fwd": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "klab_swin_cpb_bwd": [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i],
+    "klab_embedding_fwd": [_vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _ll, _i, _vp, _ll, _vp],
+    "klab_embedding_bwd": [_vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _ll, _i, _vp, _ll],
+    "klab_patchify": [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _ll],
+    "klab_patch_merge": [_vp, _i, _i, _i, _i, _vp, _vp, _i],
+    "klab_ce_fwd": [_vp, _i, _ll, _i, _vp, _ll, _vp, _vp, _vp, _vp, _vp],
+    "klab_ce_bwd": [_vp, _i, _ll, _i, _vp, _ll, _i, _vp, _vp, _vp, _vp],
+    "klab_cast": [_vp, _i, _i, _ll, _vp, _vp],
 }
-_RESTYPES = {"klab_last_error": C.c_char_p, "klab_launch_count": C.c_longlong}
+_RESTYPES = {"klab_last_error": C.c_char_p, "klab_launch_count": C.c_longlong,
+             "klab_norm_bwd_workspace_bytes": C.c_longlong, "klab_colsum_workspace_bytes": C.c_longlong,
+             "klab_t5_attention_bwd_workspace_bytes": C.c_longlong}
 
 
 def _declare(l: C.CDLL) -> None:

@@ -87,6 +87,9 @@ __device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
     z = z ^ (z >> 31);
     return static_cast<uint32_t>(z >> 32);
 }
+__host__ __device__ inline uint32_t make_dropout_thr(float p) {
+    return p > 0.0f ? static_cast<uint32_t>((1.0 - static_cast<double>(p)) * 4294967295.0) : 0xFFFFFFFFu;
+}
 // returns the multiplier to apply: 0 or 1/(1-p)
 __device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t idx, uint32_t keep_threshold, float inv_keep) {
     return hash_u32(seed, idx) < keep_threshold ? inv_keep : 0.0f;

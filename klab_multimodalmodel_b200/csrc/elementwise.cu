@@ -1,0 +1,324 @@
+// Bandwidth-bound helpers around the GEMMs: dtype casts, embedding gather / scatter-add (K11 + T8),
+// patch-embedding im2col (K1), patch-merging gather / scatter (K7), cross-entropy over materialised logits
+// (K10, generic path) and small vector utilities.
+#include "common.cuh"
+
+namespace klab {
+void count_launch(int n = 1);
+namespace {
+
+template <typename TI, typename TO>
+__global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, long long n) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = from_f32<TO>(to_f32(in[i]));
+}
+
+// fp32 -> bf16, 8 elements per thread (weights: read 32 B, write 16 B)
+__global__ void cast_f32_bf16_vec_kernel(const float4* __restrict__ in, uint4* __restrict__ out, long long n8) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        const float4 a = in[2 * i], b = in[2 * i + 1];
+        uint4 o;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+        h[0] = __floats2bfloat162_rn(a.x, a.y);
+        h[1] = __floats2bfloat162_rn(a.z, a.w);
+        h[2] = __floats2bfloat162_rn(b.x, b.y);
+        h[3] = __floats2bfloat162_rn(b.z, b.w);
+        out[i] = o;
+    }
+}
+
+// T5 decoder input embedding with _shift_right fused (HF/models/t5/modeling_t5.py:595-614, :682):
+//   token(b,t) = t == 0 ? start_id : (labels[b,t-1] == -100 ? pad_id : labels[b,t-1]);  out[b,t,:] = table[token,:]
+// shift = 0 gives a plain embedding lookup of ids (frozen text encoder input, decode steps).
+template <typename T>
+__global__ void embedding_fwd_kernel(const long long* __restrict__ ids, int B, int L, int shift, int start_id, int pad_id,
+                                     const T* __restrict__ table, int d, T* __restrict__ out, long long ldo, long long vocab,
+                                     int* __restrict__ err) {
+    const int row = blockIdx.x;
+    const int b = row / L, t = row % L;
+    long long tok;
+    if (shift) {
+        tok = t == 0 ? start_id : ids[static_cast<long long>(b) * L + t - 1];
+        if (tok == -100) tok = pad_id;
+    } else {
+        tok = ids[static_cast<long long>(b) * L + t];
+    }
+    if (tok < 0 || tok >= vocab) {
+        if (threadIdx.x == 0) atomicExch(err, 1);
+        tok = 0;
+    }
+    const T* src = table + tok * d;
+    T* dst = out + static_cast<long long>(row) * ldo;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) dst[c] = src[c];
+}
+
+// dtable[token(b,t), :] += dout[b,t,:]   (fp32 atomics into the tied embedding gradient, K11)
+template <typename T>
+__global__ void embedding_bwd_kernel(const long long* __restrict__ ids, int B, int L, int shift, int start_id, int pad_id,
+                                     const T* __restrict__ dout, long long ldo, int d, float* __restrict__ dtable, long long vocab) {
+    const int row = blockIdx.x;
+    const int b = row / L, t = row % L;
+    long long tok;
+    if (shift) {
+        tok = t == 0 ? start_id : ids[static_cast<long long>(b) * L + t - 1];
+        if (tok == -100) tok = pad_id;
+    } else {
+        tok = ids[static_cast<long long>(b) * L + t];
+    }
+    if (tok < 0 || tok >= vocab) return;
+    const T* src = dout + static_cast<long long>(row) * ldo;
+    float* dst = dtable + tok * d;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) atomicAdd(&dst[c], to_f32(src[c]));
+}
+
+// Patch embedding im2col (Conv2d k = s = P, HF/models/swinv2/modeling_swinv2.py:329):
+//   out[(b*Hp + py)*Wp + px, (c*P + ky)*P + kx] = pix[b, c, py*P + ky, px*P + kx]
+template <typename T>
+__global__ void patchify_kernel(const float* __restrict__ pix, int B, int C, int H, int W, int P, T* __restrict__ out, long long ldo) {
+    const int Hp = H / P, Wp = W / P, Kp = C * P * P;
+    const long long total = static_cast<long long>(B) * Hp * Wp * Kp;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int kk = static_cast<int>(idx % Kp);
+        const long long row = idx / Kp;
+        const int px = static_cast<int>(row % Wp), py = static_cast<int>((row / Wp) % Hp), b = static_cast<int>(row / (static_cast<long long>(Wp) * Hp));
+        const int kx = kk % P, ky = (kk / P) % P, c = kk / (P * P);
+        out[row * ldo + kk] = from_f32<T>(pix[((static_cast<long long>(b) * C + c) * H + py * P + ky) * W + px * P + kx]);
+    }
+}
+
+// Patch merging gather (HF/models/swinv2/modeling_swinv2.py:374-383): 2x2 neighbourhood, concat order
+// (0,0),(1,0),(0,1),(1,1) -> out[(b, y2, x2), q*C + c] = x[(b, 2*y2 + (q & 1), 2*x2 + (q >> 1)), c].
+// `scatter` = 1 runs the inverse permutation (backward).
+template <typename T>
+__global__ void patch_merge_kernel(const T* __restrict__ in, T* __restrict__ out, int B, int res, int C, int scatter) {
+    const int r2 = res / 2;
+    const long long total = static_cast<long long>(B) * r2 * r2 * 4 * C;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        const int c = static_cast<int>(idx % C);
+        const int qd = static_cast<int>((idx / C) % 4);
+        const long long row = idx / (4ll * C);
+        const int x2 = static_cast<int>(row % r2), y2 = static_cast<int>((row / r2) % r2), b = static_cast<int>(row / (static_cast<long long>(r2) * r2));
+        const int y = 2 * y2 + (qd & 1), x = 2 * x2 + (qd >> 1);
+        const long long src = ((static_cast<long long>(b) * res + y) * res + x) * C + c;
+        if (scatter) out[src] = in[idx];
+        else out[idx] = in[src];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Cross entropy with ignore_index over materialised logits (generic path of K10;
+// HF/models/t5/modeling_t5.py:1114-1117): one CTA per row.
+//   fwd : lse[row] = logsumexp(logits[row,:]); row_loss = lse - logits[row,label] (0 if ignored)
+//   bwd : logits[row,:] <- (softmax - onehot) * (*gscale) / n_valid   (0 for ignored rows), in place
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) ce_fwd_kernel(const T* __restrict__ logits, long long ld, int V, const long long* __restrict__ labels,
+                                                     float* __restrict__ lse, float* __restrict__ row_loss, int* __restrict__ err) {
+    __shared__ float red[32];
+    const long long row = blockIdx.x;
+    const T* lr = logits + row * ld;
+    float mx = -INFINITY;
+    for (int c = threadIdx.x; c < V; c += blockDim.x) mx = fmaxf(mx, to_f32(lr[c]));
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < (blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+    float s = 0.0f;
+    for (int c = threadIdx.x; c < V; c += blockDim.x) s += __expf(to_f32(lr[c]) - mx);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+        const float l = mx + __logf(t);
+        lse[row] = l;
+        const long long lab = labels[row];
+        float loss = 0.0f;
+        if (lab != -100) {
+            if (lab < 0 || lab >= V) atomicExch(err, 2);
+            else loss = l - to_f32(lr[lab]);
+        }
+        row_loss[row] = loss;
+    }
+}
+
+// loss = sum(row_loss) / n_valid ; stats[0] = loss, stats[1] = n_valid   (single CTA, deterministic order)
+__global__ void __launch_bounds__(256) ce_reduce_kernel(const float* __restrict__ row_loss, const long long* __restrict__ labels,
+                                                        long long rows, float* __restrict__ stats) {
+    __shared__ float rs[256];
+    __shared__ float rc[256];
+    float s = 0.0f, c = 0.0f;
+    for (long long r = threadIdx.x; r < rows; r += blockDim.x) {
+        s += row_loss[r];
+        c += labels[r] != -100 ? 1.0f : 0.0f;
+    }
+    rs[threadIdx.x] = s;
+    rc[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            rs[threadIdx.x] += rs[threadIdx.x + o];
+            rc[threadIdx.x] += rc[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        stats[0] = rs[0] / rc[0];          // all-ignored batch -> nan, as torch
+        stats[1] = rc[0];
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) ce_bwd_kernel(T* __restrict__ logits, long long ld, int V, int ld_pad, const long long* __restrict__ labels,
+                                                     const float* __restrict__ lse, const float* __restrict__ stats,
+                                                     const float* __restrict__ gscale) {
+    const long long row = blockIdx.x;
+    T* lr = logits + row * ld;
+    const long long lab = labels[row];
+    const float g = lab == -100 ? 0.0f : (gscale ? *gscale : 1.0f) / stats[1];
+    const float l = lse[row];
+    for (int c = threadIdx.x; c < ld_pad; c += blockDim.x) {
+        float v = 0.0f;
+        if (c < V && lab != -100) v = (__expf(to_f32(lr[c]) - l) - (c == lab ? 1.0f : 0.0f)) * g;
+        lr[c] = from_f32<T>(v);
+    }
+}
+
+__global__ void scale_kernel(float* __restrict__ x, long long n, const float* __restrict__ s) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) x[i] *= *s;
+}
+
+inline unsigned grid_for(long long n, int block, int per_thread = 1) {
+    long long g = (n + static_cast<long long>(block) * per_thread - 1) / (static_cast<long long>(block) * per_thread);
+    const long long cap = 32ll * sm_count();
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return static_cast<unsigned>(g);
+}
+
+}  // namespace
+}  // namespace klab
+
+using namespace klab;
+
+extern "C" {
+
+int klab_cast(void* stream, int src_dtype, int dst_dtype, long long n, const void* src, void* dst) {
+    if (int rc = klab_check_device()) return rc;
+    if (n <= 0) return KLAB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (src_dtype == KLAB_F32 && dst_dtype == KLAB_BF16) {
+        if (n % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0)
+            cast_f32_bf16_vec_kernel<<<grid_for(n / 8, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint4*>(dst), n / 8);
+        else
+            cast_kernel<float, __nv_bfloat16><<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const float*>(src), reinterpret_cast<__nv_bfloat16*>(dst), n);
+    } else if (src_dtype == KLAB_BF16 && dst_dtype == KLAB_F32) {
+        cast_kernel<__nv_bfloat16, float><<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<float*>(dst), n);
+    } else if (src_dtype == KLAB_F32 && dst_dtype == KLAB_F32) {
+        cast_kernel<float, float><<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const float*>(src), reinterpret_cast<float*>(dst), n);
+    } else {
+        cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst), n);
+    }
+    KLAB_LAUNCH_CHECK();
+    count_launch();
+    return KLAB_OK;
+}
+
+// err_flag: device int, set non-zero if a token id is out of range (checked lazily by the host)
+int klab_embedding_fwd(void* stream, int dtype, int B, int L, const long long* ids, int shift_right, int start_id, int pad_id,
+                       const void* table, long long vocab, int d, void* out, long long ldo, int* err_flag) {
+    if (int rc = klab_check_device()) return rc;
+    KLAB_REQUIRE(B > 0 && L > 0, "embedding_fwd: empty input");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == KLAB_BF16)
+        embedding_fwd_kernel<__nv_bfloat16><<<B * L, 128, 0, st>>>(ids, B, L, shift_right, start_id, pad_id, reinterpret_cast<const __nv_bfloat16*>(table), d, reinterpret_cast<__nv_bfloat16*>(out), ldo, vocab, err_flag);
+    else
+        embedding_fwd_kernel<float><<<B * L, 128, 0, st>>>(ids, B, L, shift_right, start_id, pad_id, reinterpret_cast<const float*>(table), d, reinterpret_cast<float*>(out), ldo, vocab, err_flag);
+    KLAB_LAUNCH_CHECK();
+    count_launch();
+    return KLAB_OK;
+}
+
+int klab_embedding_bwd(void* stream, int dtype, int B, int L, const long long* ids, int shift_right, int start_id, int pad_id,
+                       const void* dout, long long ldo, int d, float* dtable, long long vocab) {
+    if (int rc = klab_check_device()) return rc;
+    KLAB_REQUIRE(B > 0 && L > 0, "embedding_bwd: empty input");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == KLAB_BF16)
+        embedding_bwd_kernel<__nv_bfloat16><<<B * L, 128, 0, st>>>(ids, B, L, shift_right, start_id, pad_id, reinterpret_cast<const __nv_bfloat16*>(dout), ldo, d, dtable, vocab);
+    else
+        embedding_bwd_kernel<float><<<B * L, 128, 0, st>>>(ids, B, L, shift_right, start_id, pad_id, reinterpret_cast<const float*>(dout), ldo, d, dtable, vocab);
+    KLAB_LAUNCH_CHECK();
+    count_launch();
+    return KLAB_OK;
+}
+
+int klab_patchify(void* stream, int out_dtype, int B, int C, int H, int W, int P, const float* pixels, void* out, long long ldo) {
+    if (int rc = klab_check_device()) return rc;
+    KLAB_REQUIRE(B > 0 && H % P == 0 && W % P == 0, "patchify: image %dx%d is not a multiple of patch %d", H, W, P);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long total = static_cast<long long>(B) * C * H * W;
+    if (out_dtype == KLAB_BF16)
+        patchify_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>(pixels, B, C, H, W, P, reinterpret_cast<__nv_bfloat16*>(out), ldo);
+    else
+        patchify_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(pixels, B, C, H, W, P, reinterpret_cast<float*>(out), ldo);
+    KLAB_LAUNCH_CHECK();
+    count_launch();
+    return KLAB_OK;
+}
+
+int klab_patch_merge(void* stream, int dtype, int B, int res, int C, const void* in, void* out, int scatter) {
+    if (int rc = klab_check_device()) return rc;
+    KLAB_REQUIRE(B > 0 && res % 2 == 0, "patch_merge: odd grid %d", res);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long total = static_cast<long long>(B) * res * res * C;
+    if (dtype == KLAB_BF16)
+        patch_merge_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), B, res, C, scatter);
+    else
+        patch_merge_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(out), B, res, C, scatter);
+    KLAB_LAUNCH_CHECK();
+    count_launch();
+    return KLAB_OK;
+}
+
+// stats: device float[2] = {mean loss over non-ignored rows, number of non-ignored rows}
+int klab_ce_fwd(void* stream, int dtype, long long rows, int V, const void* logits, long long ld, const long long* labels,
+                float* lse, float* row_loss, float* stats, int* err_flag) {
+    if (int rc = klab_check_device()) return rc;
+    KLAB_REQUIRE(rows > 0 && V > 0, "ce_fwd: empty input");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == KLAB_BF16)
+        ce_fwd_kernel<__nv_bfloat16><<<static_cast<unsigned>(rows), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(logits), ld, V, labels, lse, row_loss, err_flag);
+    else
+        ce_fwd_kernel<float><<<static_cast<unsigned>(rows), 256, 0, st>>>(reinterpret_cast<const float*>(logits), ld, V, labels, lse, row_loss, err_flag);
+    KLAB_LAUNCH_CHECK();
+    ce_reduce_kernel<<<1, 256, 0, st>>>(row_loss, labels, rows, stats);
+    KLAB_LAUNCH_CHECK();
+    count_launch(2);
+    return KLAB_OK;
+}
+
+// Overwrites logits[:, 0:ld_pad) with d(loss)/d(logits) * (*gscale); columns [V, ld_pad) are zeroed.
+int klab_ce_bwd(void* stream, int dtype, long long rows, int V, void* logits, long long ld, int ld_pad, const long long* labels,
+                const float* lse, const float* stats, const float* gscale) {
+    if (int rc = klab_check_device()) return rc;
+    KLAB_REQUIRE(rows > 0 && V > 0 && ld_pad >= V && ld_pad <= ld, "ce_bwd: bad shape rows=%lld V=%d ld=%lld ld_pad=%d", rows, V, ld, ld_pad);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == KLAB_BF16)
+        ce_bwd_kernel<__nv_bfloat16><<<static_cast<unsigned>(rows), 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(logits), ld, V, ld_pad, labels, lse, stats, gscale);
+    else
+        ce_bwd_kernel<float><<<static_cast<unsigned>(rows), 256, 0, st>>>(reinterpret_cast<float*>(logits), ld, V, ld_pad, labels, lse, stats, gscale);
+    KLAB_LAUNCH_CHECK();
+    count_launch();
+    return KLAB_OK;
+}
+
+}  // extern "C"

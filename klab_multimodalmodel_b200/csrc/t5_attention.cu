@@ -1,0 +1,383 @@
+// K9 (generic path): T5 attention forward / backward, CUDA-core fp32 arithmetic, whole K/V of one (batch, head)
+// resident in shared memory.  Follows T5Attention.forward, HF/models/t5/modeling_t5.py:253-344:
+//   scores = q k^T (NO 1/sqrt(d) scale, :308) + bias[bucket(j - i)] (:236-251, table of block 0 shared by all
+//   blocks, :758) [+ causal mask, :704]; softmax in fp32 (:331); dropout on the probabilities (:332); out = P v.
+// q/k/v/o are read and written in the [B*L, H*d_kv] layout the projection GEMMs produce (no transposes).
+// This kernel is exact-fp32 and serves the strict parity path for every shape; the bf16 hot path for
+// d_kv = 64 is the tcgen05 kernel in t5_attention_tc.cu.
+#include "common.cuh"
+
+namespace klab {
+void count_launch(int n = 1);
+namespace {
+
+constexpr int RPC = 16;     // rows per CTA
+constexpr int NW = 4;       // warps per CTA
+
+struct AttnArgs {
+    const void *q, *k, *v, *o, *dout;
+    void *out, *dq, *dk, *dv;
+    long long ldq, ldk, ldv, ldo;      // ldo also used for dout / dq (ldq), dk (ldk), dv (ldv)
+    int B, H, Lq, Lk, dk_;
+    const float* bias_table;   // [num_buckets, H] or null
+    const int* rel_bucket;     // bucket of relative position r = j - (i + q_offset); index r + rel_zero
+    int rel_zero;
+    int num_buckets;
+    int causal;
+    int q_offset;
+    float* lse;                // [B, H, Lq]
+    float* dvec;               // [B, H, Lq]  D_i = dO_i . O_i
+    float* dbias_partial;      // [B*H*chunks, num_buckets]
+    float dropout_p;
+    unsigned long long seed;
+};
+
+__device__ __forceinline__ float drop_mult(const AttnArgs& a, uint32_t thr, float inv_keep, int bh, int i, int j) {
+    if (a.dropout_p <= 0.0f) return 1.0f;
+    const uint64_t idx = (static_cast<uint64_t>(bh) * a.Lq + i) * a.Lk + j;
+    return dropout_scale(a.seed, idx, thr, inv_keep);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NW * 32) t5_attn_fwd_kernel(AttnArgs a) {
+    extern __shared__ float sm[];
+    const int dk = a.dk_, Lk = a.Lk, Lq = a.Lq, dp = dk + 1;
+    float* Ks = sm;
+    float* Vs = Ks + Lk * dp;
+    float* brel = Vs + Lk * dp;                 // [Lq + Lk]
+    float* pbuf = brel + (Lq + Lk);             // [NW][Lk]
+    float* qbuf = pbuf + NW * Lk;               // [NW][dk]
+    const int bh = blockIdx.x, b = bh / a.H, h = bh % a.H;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const T* kp = reinterpret_cast<const T*>(a.k) + static_cast<long long>(b) * Lk * a.ldk + h * dk;
+    const T* vp = reinterpret_cast<const T*>(a.v) + static_cast<long long>(b) * Lk * a.ldv + h * dk;
+    for (int idx = threadIdx.x; idx < Lk * dk; idx += blockDim.x) {
+        const int j = idx / dk, c = idx % dk;
+        Ks[j * dp + c] = to_f32(kp[j * a.ldk + c]);
+        Vs[j * dp + c] = to_f32(vp[j * a.ldv + c]);
+    }
+    if (a.bias_table)
+        for (int r = threadIdx.x; r < Lq + Lk - 1; r += blockDim.x) {
+            // r encodes (j - i) + (Lq - 1)
+            const int rel = r - (Lq - 1) - a.q_offset;
+            brel[r] = a.bias_table[a.rel_bucket[rel + a.rel_zero] * a.H + h];
+        }
+    __syncthreads();
+    const uint32_t thr = make_dropout_thr(a.dropout_p);
+    const float inv_keep = a.dropout_p > 0.0f ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
+    float* pw = pbuf + warp * Lk;
+    float* qw = qbuf + warp * dk;
+    const int i_end = min(Lq, (static_cast<int>(blockIdx.y) + 1) * RPC);
+    for (int i = blockIdx.y * RPC + warp; i < i_end; i += NW) {
+        const T* qp = reinterpret_cast<const T*>(a.q) + (static_cast<long long>(b) * Lq + i) * a.ldq + h * dk;
+        for (int c = lane; c < dk; c += 32) qw[c] = to_f32(qp[c]);
+        __syncwarp();
+        const int jmax = a.causal ? min(Lk, i + a.q_offset + 1) : Lk;     // keys [0, jmax) are visible
+        float mx = -INFINITY;
+        for (int j = lane; j < jmax; j += 32) {
+            float s = 0.0f;
+            const float* kr = Ks + j * dp;
+#pragma unroll 8
+            for (int c = 0; c < dk; ++c) s = fmaf(qw[c], kr[c], s);
+            if (a.bias_table) s += brel[j - i + Lq - 1];
+            pw[j] = s;
+            mx = fmaxf(mx, s);
+        }
+        mx = warp_max(mx);
+        float sum = 0.0f;
+        for (int j = lane; j < jmax; j += 32) {
+            const float e = __expf(pw[j] - mx);
+            pw[j] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        for (int j = lane; j < jmax; j += 32) pw[j] = pw[j] * inv * drop_mult(a, thr, inv_keep, bh, i, j);
+        __syncwarp();
+        if (lane == 0) a.lse[(static_cast<long long>(bh)) * Lq + i] = mx + __logf(sum);
+        T* op = reinterpret_cast<T*>(a.out) + (static_cast<long long>(b) * Lq + i) * a.ldo + h * dk;
+        for (int c = lane; c < dk; c += 32) {
+            float acc = 0.0f;
+            for (int j = 0; j < jmax; ++j) acc = fmaf(pw[j], Vs[j * dp + c], acc);
+            op[c] = from_f32<T>(acc);
+        }
+        __syncwarp();
+    }
+}
+
+// Pass A of the backward: per query row -> dq, D_i, and the per-bucket bias gradient partials.
+template <typename T>
+__global__ void __launch_bounds__(NW * 32) t5_attn_bwd_dq_kernel(AttnArgs a) {
+    extern __shared__ float sm[];
+    const int dk = a.dk_, Lk = a.Lk, Lq = a.Lq, dp = dk + 1;
+    float* Ks = sm;
+    float* Vs = Ks + Lk * dp;
+    float* brel = Vs + Lk * dp;                 // [Lq + Lk]
+    int* relb = reinterpret_cast<int*>(brel + (Lq + Lk));   // [Lq + Lk]
+    float* pbuf = reinterpret_cast<float*>(relb + (Lq + Lk));   // [NW][Lk]
+    float* qbuf = pbuf + NW * Lk;               // [NW][dk]
+    float* dobuf = qbuf + NW * dk;              // [NW][dk]
+    float* s_dbias = dobuf + NW * dk;           // [num_buckets]
+    const int bh = blockIdx.x, b = bh / a.H, h = bh % a.H;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const T* kp = reinterpret_cast<const T*>(a.k) + static_cast<long long>(b) * Lk * a.ldk + h * dk;
+    const T* vp = reinterpret_cast<const T*>(a.v) + static_cast<long long>(b) * Lk * a.ldv + h * dk;
+    for (int idx = threadIdx.x; idx < Lk * dk; idx += blockDim.x) {
+        const int j = idx / dk, c = idx % dk;
+        Ks[j * dp + c] = to_f32(kp[j * a.ldk + c]);
+        Vs[j * dp + c] = to_f32(vp[j * a.ldv + c]);
+    }
+    if (a.bias_table) {
+        for (int r = threadIdx.x; r < Lq + Lk - 1; r += blockDim.x) {
+            const int rel = r - (Lq - 1) - a.q_offset;
+            const int bk = a.rel_bucket[rel + a.rel_zero];
+            relb[r] = bk;
+            brel[r] = a.bias_table[bk * a.H + h];
+        }
+        for (int r = threadIdx.x; r < a.num_buckets; r += blockDim.x) s_dbias[r] = 0.0f;
+    }
+    __syncthreads();
+    const uint32_t thr = make_dropout_thr(a.dropout_p);
+    const float inv_keep = a.dropout_p > 0.0f ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
+    float* pw = pbuf + warp * Lk;
+    float* qw = qbuf + warp * dk;
+    float* dow = dobuf + warp * dk;
+    const int i_end = min(Lq, (static_cast<int>(blockIdx.y) + 1) * RPC);
+    for (int i = blockIdx.y * RPC + warp; i < i_end; i += NW) {
+        const long long row = static_cast<long long>(b) * Lq + i;
+        const T* qp = reinterpret_cast<const T*>(a.q) + row * a.ldq + h * dk;
+        const T* dop = reinterpret_cast<const T*>(a.dout) + row * a.ldo + h * dk;
+        const T* op = reinterpret_cast<const T*>(a.o) + row * a.ldo + h * dk;
+        float dsum = 0.0f;
+        for (int c = lane; c < dk; c += 32) {
+            qw[c] = to_f32(qp[c]);
+            const float g = to_f32(dop[c]);
+            dow[c] = g;
+            dsum += g * to_f32(op[c]);
+        }
+        const float Di = warp_sum(dsum);
+        __syncwarp();
+        const float lse = a.lse[static_cast<long long>(bh) * Lq + i];
+        const int jmax = a.causal ? min(Lk, i + a.q_offset + 1) : Lk;
+        for (int j = lane; j < jmax; j += 32) {
+            float s = 0.0f, dpv = 0.0f;
+            const float* kr = Ks + j * dp;
+            const float* vr = Vs + j * dp;
+#pragma unroll 8
+            for (int c = 0; c < dk; ++c) {
+                s = fmaf(qw[c], kr[c], s);
+                dpv = fmaf(dow[c], vr[c], dpv);
+            }
+            if (a.bias_table) s += brel[j - i + Lq - 1];
+            const float p = __expf(s - lse);
+            const float ds = p * (dpv * drop_mult(a, thr, inv_keep, bh, i, j) - Di);
+            pw[j] = ds;
+            if (a.bias_table) atomicAdd(&s_dbias[relb[j - i + Lq - 1]], ds);
+        }
+        __syncwarp();
+        if (lane == 0) a.dvec[static_cast<long long>(bh) * Lq + i] = Di;
+        T* dqp = reinterpret_cast<T*>(a.dq) + row * a.ldq + h * dk;
+        for (int c = lane; c < dk; c += 32) {
+            float acc = 0.0f;
+            for (int j = 0; j < jmax; ++j) acc = fmaf(pw[j], Ks[j * dp + c], acc);
+            dqp[c] = from_f32<T>(acc);
+        }
+        __syncwarp();
+    }
+    if (a.bias_table) {
+        __syncthreads();
+        float* part = a.dbias_partial + (static_cast<long long>(bh) * gridDim.y + blockIdx.y) * a.num_buckets;
+        for (int r = threadIdx.x; r < a.num_buckets; r += blockDim.x) part[r] = s_dbias[r];
+    }
+}
+
+// Pass B of the backward: per key row -> dk, dv (probabilities recomputed from lse).
+template <typename T>
+__global__ void __launch_bounds__(NW * 32) t5_attn_bwd_dkv_kernel(AttnArgs a) {
+    extern __shared__ float sm[];
+    const int dk = a.dk_, Lk = a.Lk, Lq = a.Lq, dp = dk + 1;
+    float* Qs = sm;
+    float* dOs = Qs + Lq * dp;
+    float* lse_s = dOs + Lq * dp;               // [Lq]
+    float* d_s = lse_s + Lq;                    // [Lq]
+    float* brel = d_s + Lq;                     // [Lq + Lk]
+    float* pbuf = brel + (Lq + Lk);             // [NW][Lq]
+    float* dsbuf = pbuf + NW * Lq;              // [NW][Lq]
+    float* kbuf = dsbuf + NW * Lq;              // [NW][dk]
+    float* vbuf = kbuf + NW * dk;               // [NW][dk]
+    const int bh = blockIdx.x, b = bh / a.H, h = bh % a.H;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const T* qp = reinterpret_cast<const T*>(a.q) + static_cast<long long>(b) * Lq * a.ldq + h * dk;
+    const T* dop = reinterpret_cast<const T*>(a.dout) + static_cast<long long>(b) * Lq * a.ldo + h * dk;
+    for (int idx = threadIdx.x; idx < Lq * dk; idx += blockDim.x) {
+        const int i = idx / dk, c = idx % dk;
+        Qs[i * dp + c] = to_f32(qp[i * a.ldq + c]);
+        dOs[i * dp + c] = to_f32(dop[i * a.ldo + c]);
+    }
+    for (int i = threadIdx.x; i < Lq; i += blockDim.x) {
+        lse_s[i] = a.lse[static_cast<long long>(bh) * Lq + i];
+        d_s[i] = a.dvec[static_cast<long long>(bh) * Lq + i];
+    }
+    if (a.bias_table)
+        for (int r = threadIdx.x; r < Lq + Lk - 1; r += blockDim.x) {
+            const int rel = r - (Lq - 1) - a.q_offset;
+            brel[r] = a.bias_table[a.rel_bucket[rel + a.rel_zero] * a.H + h];
+        }
+    __syncthreads();
+    const uint32_t thr = make_dropout_thr(a.dropout_p);
+    const float inv_keep = a.dropout_p > 0.0f ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
+    float* pw = pbuf + warp * Lq;
+    float* dsw = dsbuf + warp * Lq;
+    float* kw = kbuf + warp * dk;
+    float* vw = vbuf + warp * dk;
+    const int j_end = min(Lk, (static_cast<int>(blockIdx.y) + 1) * RPC);
+    for (int j = blockIdx.y * RPC + warp; j < j_end; j += NW) {
+        const long long krow = static_cast<long long>(b) * Lk + j;
+        const T* kp = reinterpret_cast<const T*>(a.k) + krow * a.ldk + h * dk;
+        const T* vp = reinterpret_cast<const T*>(a.v) + krow * a.ldv + h * dk;
+        for (int c = lane; c < dk; c += 32) {
+            kw[c] = to_f32(kp[c]);
+            vw[c] = to_f32(vp[c]);
+        }
+        __syncwarp();
+        const int imin = a.causal ? max(0, j - a.q_offset) : 0;      // queries [imin, Lq) see key j
+        for (int i = imin + lane; i < Lq; i += 32) {
+            float s = 0.0f, dpv = 0.0f;
+            const float* qr = Qs + i * dp;
+            const float* dor = dOs + i * dp;
+#pragma unroll 8
+            for (int c = 0; c < dk; ++c) {
+                s = fmaf(qr[c], kw[c], s);
+                dpv = fmaf(dor[c], vw[c], dpv);
+            }
+            if (a.bias_table) s += brel[j - i + Lq - 1];
+            const float p = __expf(s - lse_s[i]);
+            const float m = drop_mult(a, thr, inv_keep, bh, i, j);
+            pw[i] = p * m;
+            dsw[i] = p * (dpv * m - d_s[i]);
+        }
+        __syncwarp();
+        T* dkp = reinterpret_cast<T*>(a.dk) + krow * a.ldk + h * dk;
+        T* dvp = reinterpret_cast<T*>(a.dv) + krow * a.ldv + h * dk;
+        for (int c = lane; c < dk; c += 32) {
+            float accv = 0.0f, acck = 0.0f;
+            for (int i = imin; i < Lq; ++i) {
+                accv = fmaf(pw[i], dOs[i * dp + c], accv);
+                acck = fmaf(dsw[i], Qs[i * dp + c], acck);
+            }
+            dkp[c] = from_f32<T>(acck);
+            dvp[c] = from_f32<T>(accv);
+        }
+        __syncwarp();
+    }
+}
+
+// dtable[bucket, h] += sum over (b, chunk) of partial[(b*H + h)*chunks + chunk][bucket]
+__global__ void t5_dbias_reduce_kernel(const float* __restrict__ part, int B, int H, int chunks, int nb, float* __restrict__ dtable) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nb * H) return;
+    const int bucket = idx / H, h = idx % H;
+    float s = 0.0f;
+    for (int b = 0; b < B; ++b)
+        for (int c = 0; c < chunks; ++c) s += part[((static_cast<long long>(b) * H + h) * chunks + c) * nb + bucket];
+    dtable[idx] += s;
+}
+
+size_t fwd_smem(int Lq, int Lk, int dk) { return sizeof(float) * (2ll * Lk * (dk + 1) + (Lq + Lk) + NW * Lk + NW * dk); }
+size_t dq_smem(int Lq, int Lk, int dk, int nb) {
+    return sizeof(float) * (2ll * Lk * (dk + 1) + 2ll * (Lq + Lk) + NW * Lk + 2 * NW * dk + nb);
+}
+size_t dkv_smem(int Lq, int Lk, int dk) {
+    return sizeof(float) * (2ll * Lq * (dk + 1) + 2ll * Lq + (Lq + Lk) + 2ll * NW * Lq + 2 * NW * dk);
+}
+
+template <typename K>
+int set_smem(K kern, size_t bytes) {
+    KLAB_REQUIRE(bytes <= 227 * 1024, "t5_attention: sequence too long for the resident-K/V kernel (%zu bytes of shared memory)", bytes);
+    KLAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    return KLAB_OK;
+}
+
+}  // namespace
+}  // namespace klab
+
+using namespace klab;
+
+extern "C" {
+
+long long klab_t5_attention_bwd_workspace_bytes(int B, int H, int Lq, int num_buckets) {
+    const long long chunks = (Lq + RPC - 1) / RPC;
+    return static_cast<long long>(sizeof(float)) * (1ll * B * H * Lq + 1ll * B * H * chunks * num_buckets);
+}
+
+int klab_t5_attention_fwd(void* stream, int dtype, int B, int H, int Lq, int Lk, int d_kv, const void* q, long long ldq,
+                          const void* k, long long ldk, const void* v, long long ldv, void* out, long long ldo,
+                          const float* bias_table, const int* rel_bucket, int rel_zero, int num_buckets, int causal,
+                          int q_offset, float* lse, float dropout_p, unsigned long long seed) {
+    if (int rc = klab_check_device()) return rc;
+    KLAB_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0 && d_kv > 0, "t5_attention_fwd: empty problem");
+    AttnArgs a{};
+    a.q = q; a.k = k; a.v = v; a.out = out;
+    a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;
+    a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.dk_ = d_kv;
+    a.bias_table = bias_table; a.rel_bucket = rel_bucket; a.rel_zero = rel_zero; a.num_buckets = num_buckets;
+    a.causal = causal; a.q_offset = q_offset; a.lse = lse; a.dropout_p = dropout_p; a.seed = seed;
+    const size_t smem = fwd_smem(Lq, Lk, d_kv);
+    const dim3 grid(B * H, (Lq + RPC - 1) / RPC);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == KLAB_BF16) {
+        if (int rc = set_smem(t5_attn_fwd_kernel<__nv_bfloat16>, smem)) return rc;
+        t5_attn_fwd_kernel<__nv_bfloat16><<<grid, NW * 32, smem, st>>>(a);
+    } else {
+        if (int rc = set_smem(t5_attn_fwd_kernel<float>, smem)) return rc;
+        t5_attn_fwd_kernel<float><<<grid, NW * 32, smem, st>>>(a);
+    }
+    KLAB_LAUNCH_CHECK();
+    count_launch();
+    return KLAB_OK;
+}
+
+int klab_t5_attention_bwd(void* stream, int dtype, int B, int H, int Lq, int Lk, int d_kv, const void* q, long long ldq,
+                          const void* k, long long ldk, const void* v, long long ldv, const void* out, const void* dout,
+                          long long ldo, void* dq, void* dk, void* dv, const float* bias_table, const int* rel_bucket,
+                          int rel_zero, int num_buckets, int causal, int q_offset, const float* lse, float* dbias_table,
+                          float dropout_p, unsigned long long seed, void* workspace) {
+    if (int rc = klab_check_device()) return rc;
+    KLAB_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0 && d_kv > 0, "t5_attention_bwd: empty problem");
+    AttnArgs a{};
+    a.q = q; a.k = k; a.v = v; a.o = out; a.dout = dout; a.dq = dq; a.dk = dk; a.dv = dv;
+    a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;
+    a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.dk_ = d_kv;
+    a.bias_table = bias_table; a.rel_bucket = rel_bucket; a.rel_zero = rel_zero; a.num_buckets = num_buckets;
+    a.causal = causal; a.q_offset = q_offset; a.lse = const_cast<float*>(lse); a.dropout_p = dropout_p; a.seed = seed;
+    const int chunks = (Lq + RPC - 1) / RPC;
+    a.dvec = static_cast<float*>(workspace);
+    a.dbias_partial = a.dvec + 1ll * B * H * Lq;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t s1 = dq_smem(Lq, Lk, d_kv, num_buckets), s2 = dkv_smem(Lq, Lk, d_kv);
+    const dim3 g1(B * H, chunks), g2(B * H, (Lk + RPC - 1) / RPC);
+    if (dtype == KLAB_BF16) {
+        if (int rc = set_smem(t5_attn_bwd_dq_kernel<__nv_bfloat16>, s1)) return rc;
+        if (int rc = set_smem(t5_attn_bwd_dkv_kernel<__nv_bfloat16>, s2)) return rc;
+        t5_attn_bwd_dq_kernel<__nv_bfloat16><<<g1, NW * 32, s1, st>>>(a);
+        KLAB_LAUNCH_CHECK();
+        t5_attn_bwd_dkv_kernel<__nv_bfloat16><<<g2, NW * 32, s2, st>>>(a);
+    } else {
+        if (int rc = set_smem(t5_attn_bwd_dq_kernel<float>, s1)) return rc;
+        if (int rc = set_smem(t5_attn_bwd_dkv_kernel<float>, s2)) return rc;
+        t5_attn_bwd_dq_kernel<float><<<g1, NW * 32, s1, st>>>(a);
+        KLAB_LAUNCH_CHECK();
+        t5_attn_bwd_dkv_kernel<float><<<g2, NW * 32, s2, st>>>(a);
+    }
+    KLAB_LAUNCH_CHECK();
+    count_launch(2);
+    if (bias_table && dbias_table) {
+        const int n = num_buckets * H;
+        t5_dbias_reduce_kernel<<<(n + 127) / 128, 128, 0, st>>>(a.dbias_partial, B, H, chunks, num_buckets, dbias_table);
+        KLAB_LAUNCH_CHECK();
+        count_launch();
+    }
+    return KLAB_OK;
+}
+
+}  // extern "C"

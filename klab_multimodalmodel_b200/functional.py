@@ -1,0 +1,443 @@
+"""Block-level forward/backward schedules of the caption step, as torch.autograd.Functions over the C-ABI kernels.
+
+Granularity is one autograd node per transformer block (plus embed / merge / loss nodes) so that gradients of a block's
+parameters become ready as soon as its backward finishes: DistributedDataParallel's bucket all-reduce
+(/root/reference/train.py:26,62) then overlaps the rest of the backward pass.
+
+Every arithmetic step below is a kernel of libklab_b200.so (ops.py); torch supplies memory, streams and the
+autograd graph only.  Citations: HF/ = site-packages/transformers 5.5.0.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+from . import ops as O
+
+
+# ------------------------------------------------------------------------------------------------
+# operand cache: fp32 master weights -> (concatenated) operands in the compute dtype
+# ------------------------------------------------------------------------------------------------
+class OperandCache:
+    """Keeps, per group of parameters, one contiguous [sum(N_i), K] operand in the compute dtype (bf16 copies for the
+    tensor cores; q|k|v weights concatenated so one GEMM produces all three).  Entries are refreshed when a parameter's
+    in-place version counter changes (i.e. after optimizer.step()), so frozen sub-models are converted exactly once."""
+
+    def __init__(self):
+        self._store: dict = {}
+
+    def get(self, params, dtype: torch.dtype) -> torch.Tensor:
+        if len(params) == 1 and params[0].dtype == dtype and params[0].dim() == 2:
+            return params[0].detach()
+        key = tuple(id(p) for p in params) + (dtype,)
+        ver = tuple(p._version for p in params) + tuple(p.data_ptr() for p in params)
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        k = params[0][0].numel() if params[0].dim() > 1 else params[0].numel()
+        rows = [p.numel() // k for p in params]
+        buf = hit[1] if hit is not None else torch.empty(sum(rows), k, dtype=dtype, device=params[0].device)
+        r0 = 0
+        for p, r in zip(params, rows):
+            O.cast(p.detach().reshape(r, k), dtype, out=buf[r0:r0 + r])
+            r0 += r
+        self._store[key] = (ver, buf)
+        return buf
+
+    def clear(self):
+        self._store.clear()
+
+
+def cat_vec(vecs, device) -> torch.Tensor:
+    """Concatenate fp32 bias vectors (None -> zeros) with the copy kernel."""
+    n = sum(v[1] for v in vecs)
+    out = torch.zeros(n, dtype=torch.float32, device=device)
+    o = 0
+    for t, sz in vecs:
+        if t is not None:
+            O.cast(t.detach(), torch.float32, out=out[o:o + sz])
+        o += sz
+    return out
+
+
+class Ctx:
+    """Static description of one block call (shapes, mode, dropout)."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def _needs_grad(tensors) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+# ------------------------------------------------------------------------------------------------
+# T5 block  (HF/models/t5/modeling_t5.py: T5LayerSelfAttention :356-377, T5LayerCrossAttention :387-408,
+#            T5LayerFF :135-150, T5Attention :253-344)
+# ------------------------------------------------------------------------------------------------
+def _t5_attn_fwd(c, n, kv_src, wq_or_qkv, wkv, wo, resid, table, lut, rz, causal, Lq, Lk, seed):
+    """n: normed input [B*Lq, d]; returns (h_out, saved) with h_out = resid + dropout(attn(n) Wo^T)."""
+    H, dk = c.H, c.dk
+    inner = H * dk
+    if kv_src is None:                                   # self-attention: one GEMM for q|k|v
+        qkv = O.linear_fwd(n, wq_or_qkv)
+        q, k, v = qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:]
+        kvbuf = None
+    else:                                                # cross-attention: q from n, k|v from the encoder output
+        qkv = O.linear_fwd(n, wq_or_qkv)
+        q = qkv
+        kvbuf = O.linear_fwd(kv_src, wkv)
+        k, v = kvbuf[:, :inner], kvbuf[:, inner:]
+    ctxt, lse = O.t5_attention_fwd(q, k, v, c.B, H, Lq, Lk, dk, bias_table=table, lut=lut, rel_zero=rz,
+                                   num_buckets=c.num_buckets, causal=causal, dropout_p=c.p, seed=seed)
+    h = O.linear_fwd(ctxt, wo, residual=resid, dropout_p=c.p, seed=seed + 1)
+    return h, (qkv, kvbuf, ctxt, lse)
+
+
+def _t5_attn_bwd(c, dh, n, kv_src, wq_or_qkv, wkv, wo, saved, table, lut, rz, causal, Lq, Lk, seed, dtable):
+    """dh: gradient of the attention layer's output (residual part handled by the caller).
+    Returns dn, dkv_src (or None), dWq(kv), dWkv (or None), dWo."""
+    H, dk = c.H, c.dk
+    inner = H * dk
+    qkv, kvbuf, ctxt, lse = saved
+    if c.p > 0.0:                                        # dropout on the o-projection output (:375 / :406)
+        dh = O.dropout_apply(dh, c.p, seed + 1)
+    dctx = O.linear_dgrad(dh, wo)
+    dwo = O.linear_wgrad(dh, ctxt)
+    dqkv = torch.empty_like(qkv)
+    if kv_src is None:
+        q, k, v = qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:]
+        dq, dk_, dv = dqkv[:, :inner], dqkv[:, inner:2 * inner], dqkv[:, 2 * inner:]
+        dkvbuf = None
+    else:
+        q, k, v = qkv, kvbuf[:, :inner], kvbuf[:, inner:]
+        dkvbuf = torch.empty_like(kvbuf)
+        dq, dk_, dv = dqkv, dkvbuf[:, :inner], dkvbuf[:, inner:]
+    O.t5_attention_bwd(q, k, v, ctxt, dctx, lse, dq, dk_, dv, c.B, H, Lq, Lk, dk, bias_table=table, lut=lut, rel_zero=rz,
+                       num_buckets=c.num_buckets, causal=causal, dbias_table=dtable, dropout_p=c.p, seed=seed)
+    dn = O.linear_dgrad(dqkv, wq_or_qkv)
+    dwq = O.linear_wgrad(dqkv, n)
+    if kv_src is None:
+        return dn, None, dwq, None, dwo
+    dkv_src = O.linear_dgrad(dkvbuf, wkv)
+    dwkv = O.linear_wgrad(dkvbuf, kv_src)
+    return dn, dkv_src, dwq, dwkv, dwo
+
+
+def _t5_ff_fwd(c, x, ln_w, wi, wo, seed):
+    n, rstd = O.rmsnorm_fwd(x, ln_w, c.eps)
+    f = O.linear_fwd(n, wi, act=L.ACT_RELU, dropout_p=c.p, seed=seed)
+    out = O.linear_fwd(f, wo, residual=x, dropout_p=c.p, seed=seed + 1)
+    return out, (n, rstd, f)
+
+
+def _t5_ff_bwd(c, dout, x, ln_w, wi, wo, saved, seed):
+    n, rstd, f = saved
+    dy = O.dropout_apply(dout, c.p, seed + 1) if c.p > 0.0 else dout
+    df = O.linear_dgrad(dy, wo, act=L.ACT_RELU_BWD, aux_in=f, dropout_p=c.p, seed=seed)
+    dwo = O.linear_wgrad(dy, f)
+    dn = O.linear_dgrad(df, wi)
+    dwi = O.linear_wgrad(df, n)
+    dx, dln = O.rmsnorm_bwd(dn, x, ln_w, rstd, dres=dout)
+    return dx, dln, dwi, dwo
+
+
+class T5BlockFn(torch.autograd.Function):
+    """One T5Block.  inputs: (c, x, enc_out | None, bias_table | None, *params)
+    params (encoder): ln0, q, k, v, o, ln1, wi, wo
+    params (decoder): ln0, q, k, v, o, ln1, cq, ck, cv, co, ln2, wi, wo"""
+
+    @staticmethod
+    def forward(ctx, c, x, enc_out, table, *params):
+        cd = x.dtype
+        cache = c.cache
+        dec = c.is_decoder
+        if dec:
+            ln0, q, k, v, o, ln1, cq, ck, cv, co, ln2, wi, wo = params
+        else:
+            ln0, q, k, v, o, ln1, wi, wo = params
+        wqkv = cache.get([q, k, v], cd)
+        w_o = cache.get([o], cd)
+        w_i = cache.get([wi], cd)
+        w_ff = cache.get([wo], cd)
+        seed = c.seed
+        n0, rstd0 = O.rmsnorm_fwd(x, ln0, c.eps)
+        h1, s_self = _t5_attn_fwd(c, n0, None, wqkv, None, w_o, x, table, c.lut, c.rz, dec, c.L, c.L, seed)
+        if dec:
+            w_cq, w_ckv, w_co = cache.get([cq], cd), cache.get([ck, cv], cd), cache.get([co], cd)
+            n1, rstd1 = O.rmsnorm_fwd(h1, ln1, c.eps)
+            h2, s_cross = _t5_attn_fwd(c, n1, enc_out, w_cq, w_ckv, w_co, h1, None, None, 0, False, c.L, c.Le, seed + 2)
+            out, s_ff = _t5_ff_fwd(c, h2, ln2, w_i, w_ff, seed + 4)
+        else:
+            out, s_ff = _t5_ff_fwd(c, h1, ln1, w_i, w_ff, seed + 4)
+        if _needs_grad((x, enc_out, table) + tuple(params)):
+            ctx.c = c
+            ctx.nparams = len(params)
+            ctx.save_for_backward(x, enc_out, table, *params)
+            ctx.acts = (n0, rstd0, s_self, h1, (n1, rstd1, s_cross, h2) if dec else None, s_ff)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        c = ctx.c
+        x, enc_out, table, *params = ctx.saved_tensors
+        n0, rstd0, s_self, h1, cross, s_ff = ctx.acts
+        ctx.acts = None
+        cd = x.dtype
+        cache = c.cache
+        dec = c.is_decoder
+        dout = dout.contiguous()
+        if dec:
+            ln0, q, k, v, o, ln1, cq, ck, cv, co, ln2, wi, wo = params
+        else:
+            ln0, q, k, v, o, ln1, wi, wo = params
+        wqkv, w_o, w_i, w_ff = cache.get([q, k, v], cd), cache.get([o], cd), cache.get([wi], cd), cache.get([wo], cd)
+        seed = c.seed
+        inner = c.H * c.dk
+        dtable = torch.zeros_like(table) if table is not None else None
+        denc = None
+        if dec:
+            n1, rstd1, s_cross, h2 = cross
+            w_cq, w_ckv, w_co = cache.get([cq], cd), cache.get([ck, cv], cd), cache.get([co], cd)
+            dh2, dln2, dwi, dwo_ff = _t5_ff_bwd(c, dout, h2, ln2, w_i, w_ff, s_ff, seed + 4)
+            dn1, denc, dwcq, dwckv, dwco = _t5_attn_bwd(c, dh2, n1, enc_out, w_cq, w_ckv, w_co, s_cross, None, None, 0, False,
+                                                        c.L, c.Le, seed + 2, None)
+            dh1, dln1 = O.rmsnorm_bwd(dn1, h1, ln1, rstd1, dres=dh2)
+        else:
+            dh1, dln1, dwi, dwo_ff = _t5_ff_bwd(c, dout, h1, ln1, w_i, w_ff, s_ff, seed + 4)
+        dn0, _, dwqkv, _, dwo = _t5_attn_bwd(c, dh1, n0, None, wqkv, None, w_o, s_self, table, c.lut, c.rz, dec, c.L, c.L, seed, dtable)
+        dx, dln0 = O.rmsnorm_bwd(dn0, x, ln0, rstd0, dres=dh1)
+        gq, gk, gv = dwqkv[:inner], dwqkv[inner:2 * inner], dwqkv[2 * inner:]
+        if dec:
+            grads = (dln0, gq, gk, gv, dwo, dln1, dwcq, dwckv[:inner], dwckv[inner:], dwco, dln2, dwi, dwo_ff)
+        else:
+            grads = (dln0, gq, gk, gv, dwo, dln1, dwi, dwo_ff)
+        return (None, dx, denc, dtable) + grads
+
+
+# ------------------------------------------------------------------------------------------------
+# stand-alone norms (stack outputs) and the concat of [image tokens; text tokens]
+# ------------------------------------------------------------------------------------------------
+class RMSNormFn(torch.autograd.Function):
+    """T5Stack.final_layer_norm (HF/models/t5/modeling_t5.py:767)."""
+
+    @staticmethod
+    def forward(ctx, x, w, eps):
+        y, rstd = O.rmsnorm_fwd(x, w, eps)
+        if _needs_grad((x, w)):
+            ctx.save_for_backward(x, w, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, rstd = ctx.saved_tensors
+        dx, dw = O.rmsnorm_bwd(dy.contiguous(), x, w, rstd)
+        return dx, dw, None
+
+
+class ConcatEmbeddingsFn(torch.autograd.Function):
+    """/root/reference/models/model.py:20-23: final LayerNorm of Swin (HF/models/swinv2/modeling_swinv2.py:969) and final
+    RMSNorm of the frozen text encoder (HF/models/t5/modeling_t5.py:767) written straight into one [B, N_img + L_src, d] buffer
+    (torch.cat costs no copy).  Gradient flows to the image branch only (the text encoder is frozen, model.py:14,20)."""
+
+    @staticmethod
+    def forward(ctx, img, ln_w, ln_b, ln_eps, lang, rms_w, rms_eps, B):
+        n_img, d = img.shape[0] // B, img.shape[1]
+        l_src = lang.shape[0] // B
+        le = n_img + l_src
+        buf = torch.empty(B, le, d, dtype=img.dtype, device=img.device)
+        save = _needs_grad((img, ln_w, ln_b))
+        _, mean, rstd = O.layernorm_fwd(img, ln_w, ln_b, ln_eps, out=buf, out_rows_per_group=n_img, out_group_stride=le * d,
+                                        save_stats=save)
+        O.rmsnorm_fwd(lang, rms_w, rms_eps, out=buf[:, n_img:], out_rows_per_group=l_src, out_group_stride=le * d, save_stats=False)
+        if save:
+            ctx.save_for_backward(img, ln_w, mean, rstd)
+            ctx.geom = (n_img, le, d)
+        return buf.view(B * le, d)
+
+    @staticmethod
+    def backward(ctx, dbuf):
+        img, ln_w, mean, rstd = ctx.saved_tensors
+        n_img, le, d = ctx.geom
+        dbuf = dbuf.contiguous()
+        dimg, dg, db = O.layernorm_bwd(dbuf, img, ln_w, mean, rstd, dy_ld=d, dy_rows_per_group=n_img, dy_group_stride=le * d)
+        return dimg, dg, db, None, None, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# decoder input embedding and LM head + loss
+# ------------------------------------------------------------------------------------------------
+class DecoderEmbedFn(torch.autograd.Function):
+    """embed_tokens(_shift_right(labels)), HF/models/t5/modeling_t5.py:595-614,:682,:1089."""
+
+    @staticmethod
+    def forward(ctx, labels, table, cache, cd, start_id, pad_id):
+        tab = cache.get([table], cd)
+        y = O.embedding_fwd(labels, tab, shift_right=True, start_id=start_id, pad_id=pad_id)
+        if _needs_grad((table,)):
+            ctx.save_for_backward(labels)
+            ctx.meta = (table.shape, start_id, pad_id)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (labels,) = ctx.saved_tensors
+        shape, start_id, pad_id = ctx.meta
+        dtab = torch.zeros(shape, dtype=torch.float32, device=dy.device)
+        O.embedding_bwd(labels, dy.contiguous(), dtab, shift_right=True, start_id=start_id, pad_id=pad_id)
+        return None, dtab, None, None, None, None
+
+
+class LMHeadLossFn(torch.autograd.Function):
+    """final RMSNorm -> * d_model**-0.5 -> tied LM head -> CrossEntropyLoss(ignore_index=-100),
+    HF/models/t5/modeling_t5.py:767,1105-1117."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, table, labels, cache, eps):
+        cd = x.dtype
+        V, d = table.shape
+        tab = cache.get([table], cd)
+        n, rstd = O.rmsnorm_fwd(x, ln_w, eps)
+        vpad = (V + 7) // 8 * 8
+        logits = O.linear_fwd(n, tab, alpha=d ** -0.5, ldd_pad=vpad)
+        lab = labels.reshape(-1).contiguous()
+        lse, stats = O.ce_fwd(logits, V, lab)
+        if _needs_grad((x, ln_w, table)):
+            ctx.save_for_backward(x, ln_w, table, lab, rstd, n, logits, lse, stats)
+            ctx.cache, ctx.eps, ctx.vpad = cache, eps, vpad
+        return stats[0].clone()
+
+    @staticmethod
+    def backward(ctx, gloss):
+        x, ln_w, table, lab, rstd, n, logits, lse, stats = ctx.saved_tensors
+        V, d = table.shape
+        tab = ctx.cache.get([table], x.dtype)
+        g = gloss.reshape(1).to(torch.float32).contiguous()
+        O.ce_bwd(logits, V, ctx.vpad, lab, lse, stats, g)            # logits now hold d loss / d logits
+        dn = O.linear_dgrad(logits, tab, alpha=d ** -0.5)
+        dtab = O.linear_wgrad(logits, n, alpha=d ** -0.5)
+        dx, dln = O.rmsnorm_bwd(dn, x, ln_w, rstd)
+        return dx, dln, dtab, None, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# Swin-V2  (HF/models/swinv2/modeling_swinv2.py)
+# ------------------------------------------------------------------------------------------------
+class PatchEmbedFn(torch.autograd.Function):
+    """Swinv2Embeddings: Conv2d(k = s = patch) as im2col + GEMM (+bias), then LayerNorm (:265-334)."""
+
+    @staticmethod
+    def forward(ctx, pixels, conv_w, conv_b, ln_w, ln_b, cache, cd, patch, eps):
+        pm = O.patchify(pixels.contiguous().float(), patch, cd)
+        w = cache.get([conv_w], cd)
+        e = O.linear_fwd(pm, w, bias=conv_b)
+        save = _needs_grad((conv_w, conv_b, ln_w, ln_b))
+        y, mean, rstd = O.layernorm_fwd(e, ln_w, ln_b, eps, save_stats=save)
+        if save:
+            ctx.save_for_backward(pm, e, ln_w, mean, rstd)
+            ctx.wshape = conv_w.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        pm, e, ln_w, mean, rstd = ctx.saved_tensors
+        de, dg, db = O.layernorm_bwd(dy.contiguous(), e, ln_w, mean, rstd)
+        dw = O.linear_wgrad(de, pm).view(ctx.wshape)
+        dbias = O.colsum(de)
+        return None, dw, dbias, dg, db, None, None, None, None
+
+
+class PatchMergeFn(torch.autograd.Function):
+    """Swinv2PatchMerging (:365-388): 2x2 gather -> Linear(4C, 2C, no bias) -> LayerNorm."""
+
+    @staticmethod
+    def forward(ctx, x, red_w, ln_w, ln_b, cache, B, res, eps):
+        C_ = x.shape[1]
+        g = O.patch_merge(x.contiguous(), B, res, C_)
+        w = cache.get([red_w], x.dtype)
+        r = O.linear_fwd(g, w)
+        save = _needs_grad((x, red_w, ln_w, ln_b))
+        y, mean, rstd = O.layernorm_fwd(r, ln_w, ln_b, eps, save_stats=save)
+        if save:
+            ctx.save_for_backward(g, r, red_w, ln_w, mean, rstd)
+            ctx.meta = (cache, B, res, C_)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        g, r, red_w, ln_w, mean, rstd = ctx.saved_tensors
+        cache, B, res, C_ = ctx.meta
+        w = cache.get([red_w], g.dtype)
+        dr, dg_, db_ = O.layernorm_bwd(dy.contiguous(), r, ln_w, mean, rstd)
+        dgath = O.linear_dgrad(dr, w)
+        dw = O.linear_wgrad(dr, g)
+        dx = O.patch_merge(dgath, B, res, C_, scatter=True)
+        return dx, dw, dg_, db_, None, None, None, None
+
+
+class SwinBlockFn(torch.autograd.Function):
+    """One Swinv2Layer (:662-715) with Swinv2SelfAttention (:421-487) inlined.
+    params: logit_scale, cpb_w1, cpb_b1, cpb_w2, q_w, q_b, k_w, v_w, v_b, proj_w, proj_b, ln1_w, ln1_b, fc1_w, fc1_b, fc2_w, fc2_b,
+            ln2_w, ln2_b"""
+
+    @staticmethod
+    def forward(ctx, c, x, *params):
+        (ls, w1, b1, w2, qw, qb, kw, vw, vb, pw, pb, g1, be1, f1w, f1b, f2w, f2b, g2, be2) = params
+        cd = x.dtype
+        cache = c.cache
+        C_ = x.shape[1]
+        wqkv = cache.get([qw, kw, vw], cd)
+        bqkv = cat_vec([(qb, C_), (None, C_), (vb, C_)], x.device)            # key has no bias (:417)
+        qkv = O.linear_fwd(x, wqkv, bias=bqkv)
+        bias16, hidden, tab = O.swin_cpb_fwd(c.coords, c.index, w1.detach(), b1.detach(), w2.detach(), c.heads, c.N)
+        lsv = ls.detach().reshape(-1)
+        q, k, v = qkv[:, :C_], qkv[:, C_:2 * C_], qkv[:, 2 * C_:]
+        ctxt, lse = O.swin_attention_fwd(q, k, v, c.B, c.res, c.heads, c.hd, c.w, c.shift, lsv, bias16)
+        a = O.linear_fwd(ctxt, cache.get([pw], cd), bias=pb)
+        save = _needs_grad((x,) + tuple(params))
+        h, mean1, rstd1 = O.layernorm_fwd(a, g1, be1, c.eps, residual=x, save_stats=save)       # res-post-norm (:707-708)
+        m_pre = torch.empty(x.shape[0], 4 * C_, dtype=cd, device=x.device) if save else None
+        m_act = O.linear_fwd(h, cache.get([f1w], cd), bias=f1b, act=L.ACT_GELU, aux_out=m_pre)
+        m2 = O.linear_fwd(m_act, cache.get([f2w], cd), bias=f2b)
+        out, mean2, rstd2 = O.layernorm_fwd(m2, g2, be2, c.eps, residual=h, save_stats=save)      # :712
+        if save:
+            ctx.c = c
+            ctx.save_for_backward(x, *params)
+            ctx.acts = (qkv, bias16, hidden, tab, ctxt, lse, a, mean1, rstd1, h, m_pre, m_act, m2, mean2, rstd2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        c = ctx.c
+        x, *params = ctx.saved_tensors
+        (ls, w1, b1, w2, qw, qb, kw, vw, vb, pw, pb, g1, be1, f1w, f1b, f2w, f2b, g2, be2) = params
+        qkv, bias16, hidden, tab, ctxt, lse, a, mean1, rstd1, h, m_pre, m_act, m2, mean2, rstd2 = ctx.acts
+        ctx.acts = None
+        cd = x.dtype
+        cache = c.cache
+        C_ = x.shape[1]
+        dout = dout.contiguous()
+        dm2, dg2, dbe2 = O.layernorm_bwd(dout, m2, g2, mean2, rstd2)
+        w_f2, w_f1, w_p, wqkv = cache.get([f2w], cd), cache.get([f1w], cd), cache.get([pw], cd), cache.get([qw, kw, vw], cd)
+        dm_pre = O.linear_dgrad(dm2, w_f2, act=L.ACT_GELU_BWD, aux_in=m_pre)
+        df2w = O.linear_wgrad(dm2, m_act)
+        df2b = O.colsum(dm2)
+        dh = O.linear_dgrad(dm_pre, w_f1, residual=dout)                     # + residual path of the second norm
+        df1w = O.linear_wgrad(dm_pre, h)
+        df1b = O.colsum(dm_pre)
+        da, dg1, dbe1 = O.layernorm_bwd(dh, a, g1, mean1, rstd1)
+        dctx = O.linear_dgrad(da, w_p)
+        dpw = O.linear_wgrad(da, ctxt)
+        dpb = O.colsum(da)
+        dqkv = torch.empty_like(qkv)
+        q, k, v = qkv[:, :C_], qkv[:, C_:2 * C_], qkv[:, 2 * C_:]
+        lsv = ls.detach().reshape(-1)
+        dbias, dls = O.swin_attention_bwd(q, k, v, ctxt, dctx, dqkv[:, :C_], dqkv[:, C_:2 * C_], dqkv[:, 2 * C_:], c.B, c.res,
+                                          c.heads, c.hd, c.w, c.shift, lsv, bias16, lse)
+        dw1, db1, dw2 = O.swin_cpb_bwd(c.coords, c.index, w2.detach(), hidden, tab, dbias, c.heads, c.N)
+        dx = O.linear_dgrad(dqkv, wqkv, residual=dh)                          # + residual path of the first norm
+        dwqkv = O.linear_wgrad(dqkv, x)
+        dbqkv = O.colsum(dqkv)
+        grads = (dls.view(ls.shape), dw1, db1, dw2, dwqkv[:C_], dbqkv[:C_], dwqkv[C_:2 * C_], dwqkv[2 * C_:], dbqkv[2 * C_:],
+                 dpw, dpb, dg1, dbe1, df1w, df1b, df2w, df2b, dg2, dbe2)
+        return (None, dx) + grads

@@ -1,0 +1,328 @@
+"""Kernel-level parity (B200 only): every C-ABI kernel family against the oracle / plain torch fp32 on the CPU,
+on the same seeded inputs.  Tolerances: fp32 path 1e-4 of the tensor's scale, bf16 path 2e-2."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import swinv2 as osw  # noqa: E402
+from oracle import t5 as ot5  # noqa: E402
+
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+def ops():
+    from klab_multimodalmodel_b200 import ops as o
+    return o
+
+
+def L():
+    from klab_multimodalmodel_b200 import _lib
+    return _lib
+
+
+def tol(dtype):
+    return 1e-4 if dtype == torch.float32 else 2e-2
+
+
+def close(got, ref, dtype, what="", scale=None):
+    got = got.detach().float().cpu()
+    ref = ref.detach().float().cpu()
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    s = ref.abs().max().item() if scale is None else scale
+    err = (got - ref).abs().max().item()
+    assert err <= tol(dtype) * max(s, 1e-6) + 1e-7, f"{what}: max err {err:.3e} vs scale {s:.3e} ({dtype})"
+
+
+def rnd(*shape, dtype, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.randn(*shape, generator=g) * scale)
+    xq = x.to(dtype)
+    return xq.cuda(), xq.float()          # device tensor, exact fp32 copy of what the device sees
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (200, 136, 96), (520, 1032, 264), (96, 40, 48)])
+def test_gemm_layouts(dtype, a_mn, b_mn, M, N, K):
+    o = ops()
+    A, Ar = rnd(M, K, dtype=dtype, seed=1)
+    B, Br = rnd(N, K, dtype=dtype, seed=2)
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    d = o.gemm(a, b, M, N, K, a_mn=bool(a_mn), b_mn=bool(b_mn), out_dtype=torch.float32)
+    close(d, Ar @ Br.t(), torch.float32 if dtype == torch.float32 else dtype, "gemm")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_gemm_epilogues(dtype):
+    o, lib = ops(), L()
+    M, N, K = 300, 200, 104
+    A, Ar = rnd(M, K, dtype=dtype, seed=1)
+    B, Br = rnd(N, K, dtype=dtype, seed=2, scale=0.2)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(3))
+    R, Rr = rnd(M, N, dtype=dtype, seed=4)
+    base = Ar @ Br.t()
+    # bias + gelu with pre-activation copy + residual
+    pre = torch.empty(M, N, dtype=dtype, device="cuda")
+    d = o.gemm(A, B, M, N, K, bias=bias.cuda(), act=lib.ACT_GELU, aux_out=pre, residual=R)
+    close(pre, base + bias, dtype, "aux_out")
+    close(d, F.gelu(base + bias) + Rr, dtype, "gelu+res")
+    # relu, alpha, fp32 output, accumulate
+    acc0 = torch.randn(M, N, generator=torch.Generator().manual_seed(5))
+    d2 = acc0.clone().cuda()
+    o.gemm(A, B, M, N, K, act=lib.ACT_RELU, alpha=0.5, out=d2, accumulate=True)
+    close(d2, torch.relu(0.5 * base) + acc0, dtype, "relu+acc")
+    # activation backward epilogues
+    H, Hr = rnd(M, N, dtype=dtype, seed=6)
+    d3 = o.gemm(A, B, M, N, K, act=lib.ACT_RELU_BWD, aux_in=H)
+    close(d3, base * (Hr > 0), dtype, "relu_bwd")
+    d4 = o.gemm(A, B, M, N, K, act=lib.ACT_GELU_BWD, aux_in=H)
+    x = Hr.clone().requires_grad_(True)
+    F.gelu(x).backward(base)
+    close(d4, x.grad, dtype, "gelu_bwd")
+    # padded leading dimension (vocab not a multiple of 8)
+    d5 = o.gemm(A, B, M, N - 3, K, ldd_pad=N)
+    close(d5, base[:, :N - 3], dtype, "ldd_pad")
+
+
+def test_gemm_dropout_consistency():
+    """The epilogue dropout mask depends only on (seed, element index): the bf16 tcgen05 kernel and the fp32 SIMT kernel
+    drop the same elements, and about p of them."""
+    o = ops()
+    M, N, K = 256, 192, 64
+    A, Ar = rnd(M, K, dtype=torch.bfloat16, seed=1)
+    B, Br = rnd(N, K, dtype=torch.bfloat16, seed=2)
+    d = o.gemm(A, B, M, N, K, out_dtype=torch.float32, dropout_p=0.25, seed=77).cpu()
+    d32 = o.gemm(A.float(), B.float(), M, N, K, dropout_p=0.25, seed=77).cpu()
+    base = Ar @ Br.t()
+    dropped = (d == 0) & (base.abs() > 1e-3)
+    assert torch.equal(dropped, (d32 == 0) & (base.abs() > 1e-3))
+    frac = dropped.float().mean().item()
+    assert 0.22 < frac < 0.28, frac
+    keep = ~dropped
+    assert torch.allclose(d[keep], base[keep] / 0.75, rtol=1e-2, atol=1e-2)
+
+
+# ------------------------------------------------------------------------------------------------ norms
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("rows,d", [(37, 64), (260, 768), (5, 1000)])
+def test_rmsnorm(dtype, rows, d):
+    o = ops()
+    X, Xr = rnd(rows, d, dtype=dtype, seed=1)
+    DY, DYr = rnd(rows, d, dtype=dtype, seed=2)
+    DR, DRr = rnd(rows, d, dtype=dtype, seed=3)
+    g = 1 + 0.1 * torch.randn(d, generator=torch.Generator().manual_seed(4))
+    y, rstd = o.rmsnorm_fwd(X, g.cuda(), 1e-6)
+    xr = Xr.clone().requires_grad_(True)
+    gr = g.clone().requires_grad_(True)
+    yr = ot5.rms_norm(xr, gr, 1e-6)
+    close(y, yr, dtype, "rms fwd")
+    yr.backward(DYr)
+    dx, dg = o.rmsnorm_bwd(DY, X, g.cuda(), rstd, dres=DR)
+    close(dx, xr.grad + DRr, dtype, "rms dx")
+    close(dg, gr.grad, dtype, "rms dgamma")
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("rows,d", [(37, 32), (300, 128), (6, 1024)])
+def test_layernorm(dtype, rows, d):
+    o = ops()
+    X, Xr = rnd(rows, d, dtype=dtype, seed=1)
+    R, Rr = rnd(rows, d, dtype=dtype, seed=5)
+    DY, DYr = rnd(rows, d, dtype=dtype, seed=2)
+    gen = torch.Generator().manual_seed(4)
+    g = 1 + 0.1 * torch.randn(d, generator=gen)
+    b = 0.1 * torch.randn(d, generator=gen)
+    y, mean, rstd = o.layernorm_fwd(X, g.cuda(), b.cuda(), 1e-5, residual=R)
+    xr, gr, br = Xr.clone().requires_grad_(True), g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.layer_norm(xr, (d,), gr, br, 1e-5) + Rr
+    close(y, yr, dtype, "ln fwd")
+    yr.backward(DYr)
+    dx, dg, db = o.layernorm_bwd(DY, X, g.cuda(), mean, rstd)
+    close(dx, xr.grad, dtype, "ln dx")
+    close(dg, gr.grad, dtype, "ln dgamma")
+    close(db, br.grad, dtype, "ln dbeta")
+    close(o.colsum(DY), DYr.sum(0), dtype, "colsum")
+
+
+def test_norm_grouped_output():
+    """Writing the two halves of the concat buffer [image tokens; text tokens] (models/model.py:23) in place."""
+    o = ops()
+    B, n_img, l_src, d = 3, 4, 5, 64
+    buf = torch.zeros(B, n_img + l_src, d, device="cuda")
+    X, Xr = rnd(B * n_img, d, dtype=torch.float32, seed=1)
+    Z, Zr = rnd(B * l_src, d, dtype=torch.float32, seed=2)
+    g = torch.ones(d)
+    o.layernorm_fwd(X, g.cuda(), torch.zeros(d).cuda(), 1e-5, out=buf, out_rows_per_group=n_img,
+                    out_group_stride=(n_img + l_src) * d, save_stats=False)
+    o.rmsnorm_fwd(Z, g.cuda(), 1e-6, out=buf[:, n_img:], out_rows_per_group=l_src, out_group_stride=(n_img + l_src) * d,
+                  save_stats=False)
+    ref = torch.cat([F.layer_norm(Xr, (d,)).view(B, n_img, d), ot5.rms_norm(Zr, g, 1e-6).view(B, l_src, d)], 1)
+    close(buf, ref, torch.float32, "concat")
+
+
+# ------------------------------------------------------------------------------------------------ T5 attention
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("mode,B,H,Lq,Lk,dk", [("enc", 2, 3, 13, 13, 64), ("dec", 2, 2, 9, 9, 64), ("cross", 2, 2, 7, 13, 64),
+                                               ("enc", 1, 2, 81, 81, 16), ("dec", 1, 1, 40, 40, 32)])
+def test_t5_attention(dtype, mode, B, H, Lq, Lk, dk):
+    o = ops()
+    dims = ot5.T5Dims(num_heads=H, d_kv=dk)
+    inner = H * dk
+    QKV, QKVr = rnd(B * max(Lq, Lk), 3 * inner, dtype=dtype, seed=1, scale=0.5)
+    q, k, v = QKV[:B * Lq, :inner], QKV[:B * Lk, inner:2 * inner], QKV[:B * Lk, 2 * inner:]
+    DO, DOr = rnd(B * Lq, inner, dtype=dtype, seed=2)
+    table = 0.5 * torch.randn(32, H, generator=torch.Generator().manual_seed(3))
+    causal = mode == "dec"
+    has_bias = mode != "cross"
+    lut, rz = o.t5_rel_bucket_lut(Lq, Lk, bidirectional=(mode == "enc"), num_buckets=32, max_distance=128)
+    kw = dict(bias_table=table.cuda() if has_bias else None, lut=lut.cuda() if has_bias else None, rel_zero=rz, causal=causal)
+    ctx, lse = o.t5_attention_fwd(q, k, v, B, H, Lq, Lk, dk, **kw)
+    # reference (oracle arithmetic, no projections)
+    qr = QKVr[:B * Lq, :inner].clone().requires_grad_(True)
+    kr = QKVr[:B * Lk, inner:2 * inner].clone().requires_grad_(True)
+    vr = QKVr[:B * Lk, 2 * inner:].clone().requires_grad_(True)
+    tr = table.clone().requires_grad_(True)
+    s = qr.view(B, Lq, H, dk).transpose(1, 2) @ kr.view(B, Lk, H, dk).transpose(1, 2).transpose(-1, -2)
+    if has_bias:
+        s = s + ot5.t5_bias(tr, Lq, Lk, bidirectional=(mode == "enc"), dims=dims)[None]
+    if causal:
+        s = s + torch.where(torch.arange(Lk)[None, :] > torch.arange(Lq)[:, None], torch.finfo(torch.float32).min, 0.0)
+    p = torch.softmax(s, -1)
+    ref = (p @ vr.view(B, Lk, H, dk).transpose(1, 2)).transpose(1, 2).reshape(B * Lq, inner)
+    close(ctx, ref, dtype, "t5 attn fwd")
+    ref.backward(DOr)
+    dQKV = torch.zeros_like(QKV)
+    dq, dk_, dv = dQKV[:B * Lq, :inner], dQKV[:B * Lk, inner:2 * inner], dQKV[:B * Lk, 2 * inner:]
+    dtab = torch.zeros(32, H, device="cuda")
+    o.t5_attention_bwd(q, k, v, ctx, DO, lse, dq, dk_, dv, B, H, Lq, Lk, dk, dbias_table=dtab if has_bias else None, **kw)
+    close(dq, qr.grad, dtype, "t5 dq")
+    close(dk_, kr.grad, dtype, "t5 dk")
+    close(dv, vr.grad, dtype, "t5 dv")
+    if has_bias:
+        close(dtab, tr.grad, dtype, "t5 dbias")
+
+
+def test_t5_bucket_lut_matches_oracle():
+    o = ops()
+    for bidir in (True, False):
+        lut, rz = o.t5_rel_bucket_lut(200, 300, bidir, 32, 128)
+        rel = torch.arange(-199, 300)
+        ref = ot5.relative_position_bucket(rel, bidir, 32, 128)
+        assert torch.equal(lut.long(), ref) and rz == 199
+
+
+# ------------------------------------------------------------------------------------------------ Swin attention
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("B,res,heads,hd,w,shift", [(2, 8, 2, 32, 4, 2), (1, 8, 1, 32, 8, 0), (2, 14, 2, 32, 7, 3), (1, 16, 3, 16, 4, 0)])
+def test_swin_attention(dtype, B, res, heads, hd, w, shift):
+    o = ops()
+    Cc = heads * hd
+    n = w * w
+    QKV, QKVr = rnd(B * res * res, 3 * Cc, dtype=dtype, seed=1)
+    DO, DOr = rnd(B * res * res, Cc, dtype=dtype, seed=2)
+    gen = torch.Generator().manual_seed(3)
+    sd = {
+        "logit_scale": (math.log(10.0) + 0.3 * torch.randn(heads, 1, 1, generator=gen)),
+        "continuous_position_bias_mlp.0.weight": torch.randn(512, 2, generator=gen) * 0.7,
+        "continuous_position_bias_mlp.0.bias": torch.randn(512, generator=gen) * 0.05,
+        "continuous_position_bias_mlp.2.weight": torch.randn(heads, 512, generator=gen) * 0.05,
+    }
+    sd["logit_scale"][0] = 5.0                                   # exercises the clamp at ln(100)
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    coords, index = o.swin_tables(w, 0)
+    assert torch.equal(index.long(), osw.position_index(w)) and torch.allclose(coords, osw.coords_table(w, 0))
+    w1, b1, w2 = (sd["continuous_position_bias_mlp.0.weight"], sd["continuous_position_bias_mlp.0.bias"],
+                  sd["continuous_position_bias_mlp.2.weight"])
+    bias, hidden, tab = o.swin_cpb_fwd(coords.cuda(), index.cuda(), w1.detach().cuda(), b1.detach().cuda(), w2.detach().cuda(), heads, n)
+    bias_ref = osw.cpb_bias(sd, "", w, 0, heads)
+    close(bias, bias_ref, torch.float32, "cpb bias")
+    ls = sd["logit_scale"].detach().view(-1).cuda()
+    q, k, v = QKV[:, :Cc], QKV[:, Cc:2 * Cc], QKV[:, 2 * Cc:]
+    ctx, lse = o.swin_attention_fwd(q, k, v, B, res, heads, hd, w, shift, ls, bias)
+    # reference: roll -> partition -> cosine attention -> reverse -> roll back (oracle/swinv2.py)
+    qkvr = QKVr.clone().requires_grad_(True)
+    xs = qkvr.view(B, res, res, 3 * Cc)
+    if shift:
+        xs = torch.roll(xs, (-shift, -shift), (1, 2))
+    win = osw._partition(xs, w)
+    bw = win.shape[0]
+    qq, kk, vv = [t.reshape(bw, n, heads, hd).transpose(1, 2) for t in win.split(Cc, dim=-1)]
+    s = F.normalize(qq, dim=-1) @ F.normalize(kk, dim=-1).transpose(-1, -2)
+    s = s * torch.clamp(sd["logit_scale"], max=math.log(100.0)).exp() + bias_ref[None]
+    mask = osw.shift_mask(res, res, w, shift)
+    if mask is not None:
+        nw = mask.shape[0]
+        s = (s.view(bw // nw, nw, heads, n, n) + 2 * mask[None, :, None]).view(bw, heads, n, n)
+    out = (torch.softmax(s, -1) @ vv).transpose(1, 2).reshape(bw, n, Cc)
+    out = osw._reverse(out, w, res, res)
+    if shift:
+        out = torch.roll(out, (shift, shift), (1, 2))
+    ref = out.reshape(B * res * res, Cc)
+    close(ctx, ref, dtype, "swin attn fwd")
+    ref.backward(DOr)
+    dQKV = torch.zeros_like(QKV)
+    dbias, dls = o.swin_attention_bwd(q, k, v, ctx, DO, dQKV[:, :Cc], dQKV[:, Cc:2 * Cc], dQKV[:, 2 * Cc:], B, res, heads, hd, w,
+                                      shift, ls, bias, lse)
+    close(dQKV, qkvr.grad, dtype, "swin dqkv")
+    close(dls, sd["logit_scale"].grad.view(-1), dtype, "swin dlogit_scale")
+    dw1, db1, dw2 = o.swin_cpb_bwd(coords.cuda(), index.cuda(), w2.detach().cuda(), hidden, tab, dbias, heads, n)
+    close(dw2, w2.grad, dtype, "cpb dw2")
+    close(dw1, w1.grad, dtype, "cpb dw1")
+    close(db1, b1.grad, dtype, "cpb db1")
+
+
+# ------------------------------------------------------------------------------------------------ data movement + CE
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_embedding_patch_ce(dtype):
+    o = ops()
+    # embedding with shift_right (labels contain -100) and scatter-add backward
+    V, d, B, Lx = 50, 32, 3, 6
+    T, Tr = rnd(V, d, dtype=dtype, seed=1)
+    labels = torch.randint(2, V, (B, Lx), generator=torch.Generator().manual_seed(2))
+    labels[:, -2:] = -100
+    dims = ot5.T5Dims(vocab_size=V)
+    e = o.embedding_fwd(labels.cuda(), T, shift_right=True)
+    ids = ot5.shift_right(labels, dims)
+    close(e, Tr[ids].view(B * Lx, d), dtype, "embedding")
+    DO, DOr = rnd(B * Lx, d, dtype=dtype, seed=3)
+    dT = torch.zeros(V, d, device="cuda")
+    o.embedding_bwd(labels.cuda(), DO, dT, shift_right=True)
+    ref = torch.zeros(V, d).index_add_(0, ids.view(-1), DOr)
+    close(dT, ref, dtype, "embedding bwd")
+    # patchify == conv2d(k = s = 4) as a GEMM
+    px = torch.randn(2, 3, 16, 24, generator=torch.Generator().manual_seed(4))
+    W, Wr = rnd(8, 48, dtype=dtype, seed=5, scale=0.2)
+    pm = o.patchify(px.cuda(), 4, dtype)
+    y = o.linear_fwd(pm, W, out_dtype=torch.float32)
+    ref = F.conv2d(pm.float().cpu().view(2, 4, 6, 3, 4, 4).permute(0, 3, 1, 4, 2, 5).reshape(2, 3, 16, 24), Wr.view(8, 3, 4, 4), stride=4)
+    close(y, ref.flatten(2).transpose(1, 2).reshape(-1, 8), dtype, "patch embed")
+    assert torch.equal(pm.float().cpu().view(2, 4, 6, 3, 4, 4).permute(0, 3, 1, 4, 2, 5).reshape(2, 3, 16, 24).to(dtype), px.to(dtype))
+    # patch merging gather / scatter
+    X, Xr = rnd(2 * 6 * 6, 8, dtype=dtype, seed=6)
+    g = o.patch_merge(X, 2, 6, 8)
+    gg = Xr.view(2, 6, 6, 8)
+    ref = torch.cat([gg[:, 0::2, 0::2], gg[:, 1::2, 0::2], gg[:, 0::2, 1::2], gg[:, 1::2, 1::2]], -1).reshape(-1, 32)
+    assert torch.equal(g.float().cpu(), ref)
+    assert torch.equal(o.patch_merge(g, 2, 6, 8, scatter=True).float().cpu(), Xr)
+    # cross entropy with ignore_index
+    rows, Vv = B * Lx, 43
+    LG, LGr = rnd(rows, 48, dtype=dtype, seed=7, scale=2.0)
+    lg = LG[:, :Vv]
+    lab = labels.clamp(max=Vv - 1).view(-1)
+    lab[labels.view(-1) == -100] = -100
+    lse, stats = o.ce_fwd(lg, Vv, lab.cuda())
+    lr = LGr[:, :Vv].clone().requires_grad_(True)
+    loss = F.cross_entropy(lr, lab, ignore_index=-100)
+    close(stats[:1], loss.view(1), dtype, "ce loss")
+    loss.backward()
+    gs = torch.tensor([0.5], device="cuda")
+    o.ce_bwd(lg, Vv, 48, lab.cuda(), lse, stats, gs)
+    close(LG[:, :Vv], 0.5 * lr.grad, dtype, "ce bwd")
+    assert (LG[:, Vv:] == 0).all()
+    o.check_err_flag(LG.device)
