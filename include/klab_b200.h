@@ -170,6 +170,15 @@ int klab_ce_fwd(void* stream, int dtype, long long rows, int V, const void* logi
 int klab_ce_bwd(void* stream, int dtype, long long rows, int V, void* logits, long long ld, int ld_pad, const long long* labels,
                 const float* lse, const float* stats, const float* gscale);
 
+/* ---- K14 (part): greedy decode step (HF/generation/utils.py:2762-2800): ids[b,t] = unfinished[b] ? argmax(logits[b,:]) : pad;
+ * unfinished[b] &= ids[b,t] != eos.  logits are fp32 [B,V]; ties resolve to the lowest index. */
+int klab_greedy_step(void* stream, int B, int V, const float* logits, long long ld, long long* ids, long long ld_ids, int t,
+                     int* unfinished, int pad_id, int eos_id);
+
+/* y = x * keep(seed, linear index)/(1-p): the mask klab_gemm's epilogue dropout applied to a contiguous [M,N] output
+ * (T5 dropout sites, HF/models/t5/modeling_t5.py:95,149,375,406,734,768), regenerated for the backward pass. */
+int klab_dropout_apply(void* stream, int dtype, long long n, const void* x, void* y, float p, unsigned long long seed);
+
 /* dtype conversion (fp32 master weights -> bf16 operand copies). */
 int klab_cast(void* stream, int src_dtype, int dst_dtype, long long n, const void* src, void* dst);
 

@@ -191,6 +191,48 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(T* __restrict__ logits, lon
     }
 }
 
+// y[i] = x[i] * keep(seed, i) / (1 - p): regenerates the mask a GEMM epilogue applied to element (row*N + col)
+template <typename T>
+__global__ void dropout_apply_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, unsigned long long seed,
+                                     uint32_t thr, float inv_keep) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
+        y[i] = from_f32<T>(to_f32(x[i]) * dropout_scale(seed, static_cast<uint64_t>(i), thr, inv_keep));
+}
+
+// Greedy decode step (HF/generation/utils.py:2762-2800): next = argmax(fp32 logits row) (first index on ties);
+// finished rows emit pad; ids[b, t] = next; unfinished[b] &= next != eos.
+__global__ void __launch_bounds__(256) greedy_step_kernel(const float* __restrict__ logits, long long ld, int V, long long* __restrict__ ids,
+                                                          long long ld_ids, int t, int* __restrict__ unfinished, int pad_id, int eos_id) {
+    __shared__ float bv[256];
+    __shared__ int bi[256];
+    const int b = blockIdx.x;
+    const float* lr = logits + static_cast<long long>(b) * ld;
+    float best = -INFINITY;
+    int besti = V;
+    for (int c = threadIdx.x; c < V; c += blockDim.x) {
+        const float v = lr[c];
+        if (v > best || (v == best && c < besti)) { best = v; besti = c; }
+    }
+    bv[threadIdx.x] = best;
+    bi[threadIdx.x] = besti;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            const float v = bv[threadIdx.x + o];
+            const int i = bi[threadIdx.x + o];
+            if (v > bv[threadIdx.x] || (v == bv[threadIdx.x] && i < bi[threadIdx.x])) { bv[threadIdx.x] = v; bi[threadIdx.x] = i; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int alive = unfinished[b];
+        const int nxt = alive ? bi[0] : pad_id;
+        ids[static_cast<long long>(b) * ld_ids + t] = nxt;
+        unfinished[b] = alive && nxt != eos_id;
+    }
+}
+
 __global__ void scale_kernel(float* __restrict__ x, long long n, const float* __restrict__ s) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) x[i] *= *s;
@@ -284,6 +326,31 @@ int klab_patch_merge(void* stream, int dtype, int B, int res, int C, const void*
         patch_merge_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), B, res, C, scatter);
     else
         patch_merge_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(out), B, res, C, scatter);
+    KLAB_LAUNCH_CHECK();
+    count_launch();
+    return KLAB_OK;
+}
+
+int klab_greedy_step(void* stream, int B, int V, const float* logits, long long ld, long long* ids, long long ld_ids, int t,
+                     int* unfinished, int pad_id, int eos_id) {
+    if (int rc = klab_check_device()) return rc;
+    KLAB_REQUIRE(B > 0 && V > 0, "greedy_step: empty input");
+    greedy_step_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, ld, V, ids, ld_ids, t, unfinished, pad_id, eos_id);
+    KLAB_LAUNCH_CHECK();
+    count_launch();
+    return KLAB_OK;
+}
+
+int klab_dropout_apply(void* stream, int dtype, long long n, const void* x, void* y, float p, unsigned long long seed) {
+    if (int rc = klab_check_device()) return rc;
+    KLAB_REQUIRE(n > 0 && p >= 0.0f && p < 1.0f, "dropout_apply: bad arguments n=%lld p=%f", n, p);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const uint32_t thr = make_dropout_thr(p);
+    const float inv_keep = 1.0f / (1.0f - p);
+    if (dtype == KLAB_BF16)
+        dropout_apply_kernel<__nv_bfloat16><<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), n, seed, thr, inv_keep);
+    else
+        dropout_apply_kernel<float><<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const float*>(x), reinterpret_cast<float*>(y), n, seed, thr, inv_keep);
     KLAB_LAUNCH_CHECK();
     count_launch();
     return KLAB_OK;

@@ -26,7 +26,7 @@ template <int CH>
 __device__ __forceinline__ void load_chunk(const void* base, int dt, long long idx0, int nvalid, float (&out)[CH]) {
     if (dt == KLAB_BF16) {
         const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(base) + idx0;
-        if (nvalid == CH && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        if (CH % 8 == 0 && nvalid == CH && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
 #pragma unroll
             for (int i = 0; i < CH / 8; ++i) {
                 const uint4 q = reinterpret_cast<const uint4*>(p)[i];
@@ -61,7 +61,7 @@ template <int CH>
 __device__ __forceinline__ void store_chunk(void* base, int dt, long long idx0, int nvalid, const float (&v)[CH]) {
     if (dt == KLAB_BF16) {
         __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(base) + idx0;
-        if (nvalid == CH && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        if (CH % 8 == 0 && nvalid == CH && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
 #pragma unroll
             for (int i = 0; i < CH / 8; ++i) {
                 uint4 q;

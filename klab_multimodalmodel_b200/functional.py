@@ -67,8 +67,18 @@ class Ctx:
         self.__dict__.update(kw)
 
 
+_OUTER_GRAD = [True]
+
+
+def apply_fn(fn_cls, *args):
+    """fn_cls.apply(*args), remembering the caller's grad mode: inside Function.forward autograd is always disabled, so the
+    decision "keep activations for backward?" has to be taken from the outside (frozen sub-models run under no_grad)."""
+    _OUTER_GRAD[0] = torch.is_grad_enabled()
+    return fn_cls.apply(*args)
+
+
 def _needs_grad(tensors) -> bool:
-    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+    return _OUTER_GRAD[0] and any(t is not None and t.requires_grad for t in tensors)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -289,22 +299,24 @@ class DecoderEmbedFn(torch.autograd.Function):
 
 
 class LMHeadLossFn(torch.autograd.Function):
-    """final RMSNorm -> * d_model**-0.5 -> tied LM head -> CrossEntropyLoss(ignore_index=-100),
-    HF/models/t5/modeling_t5.py:767,1105-1117."""
+    """final RMSNorm -> dropout (training) -> * d_model**-0.5 -> tied LM head -> CrossEntropyLoss(ignore_index=-100),
+    HF/models/t5/modeling_t5.py:767-768,1105-1117."""
 
     @staticmethod
-    def forward(ctx, x, ln_w, table, labels, cache, eps):
+    def forward(ctx, x, ln_w, table, labels, cache, eps, p, seed):
         cd = x.dtype
         V, d = table.shape
         tab = cache.get([table], cd)
         n, rstd = O.rmsnorm_fwd(x, ln_w, eps)
+        if p > 0.0:
+            n = O.dropout_apply(n, p, seed)
         vpad = (V + 7) // 8 * 8
         logits = O.linear_fwd(n, tab, alpha=d ** -0.5, ldd_pad=vpad)
         lab = labels.reshape(-1).contiguous()
         lse, stats = O.ce_fwd(logits, V, lab)
         if _needs_grad((x, ln_w, table)):
             ctx.save_for_backward(x, ln_w, table, lab, rstd, n, logits, lse, stats)
-            ctx.cache, ctx.eps, ctx.vpad = cache, eps, vpad
+            ctx.cache, ctx.vpad, ctx.p, ctx.seed = cache, vpad, p, seed
         return stats[0].clone()
 
     @staticmethod
@@ -316,8 +328,10 @@ class LMHeadLossFn(torch.autograd.Function):
         O.ce_bwd(logits, V, ctx.vpad, lab, lse, stats, g)            # logits now hold d loss / d logits
         dn = O.linear_dgrad(logits, tab, alpha=d ** -0.5)
         dtab = O.linear_wgrad(logits, n, alpha=d ** -0.5)
+        if ctx.p > 0.0:
+            dn = O.dropout_apply(dn, ctx.p, ctx.seed)
         dx, dln = O.rmsnorm_bwd(dn, x, ln_w, rstd)
-        return dx, dln, dtab, None, None, None
+        return dx, dln, dtab, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------

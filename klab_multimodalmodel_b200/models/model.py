@@ -1,0 +1,76 @@
+"""Drop-in for /root/reference/models/model.py: same class name, constructor arguments, attributes, forward signature,
+checkpoint keys and error behaviour -- the arithmetic behind `forward` is libklab_b200.so (hand-written sm_100a kernels).
+
+    reference                                      this file
+    ---------------------------------------------  ----------------------------------------------------------
+    T5EncoderModel.from_pretrained  (model.py:14)   modeling.T5EncoderModel.from_pretrained   (frozen)
+    Swinv2Model.from_pretrained     (model.py:15)   modeling.Swinv2Model.from_pretrained
+    T5ForConditionalGeneration...   (model.py:17)   modeling.T5ForConditionalGeneration.from_pretrained
+    forward(images, source_encoding, target_encoding=None, return_loss=True)  (model.py:19-28)   identical
+    save / load                     (model.py:30-42) identical file format ({'transformer': sd[, 'image_model': sd]})
+
+One optional extra: `args.compute_dtype` ("bf16" default | "fp32"); the reference's argparse namespace does not have it, so
+the default applies and train.py needs no change.
+"""
+import os
+
+import torch
+from torch import nn
+
+from .. import functional as Fn
+from ..generation import greedy_generate
+from ..modeling import Swinv2Model, T5EncoderModel, T5ForConditionalGeneration, _compute_dtype
+
+
+class MyModel(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.result_dir = args.result_dir
+
+        self.language_model = T5EncoderModel.from_pretrained(args.language_model_name).requires_grad_(False)
+        self.image_model = Swinv2Model.from_pretrained(args.image_model_name).requires_grad_(args.image_model_train)
+
+        self.transformer = T5ForConditionalGeneration.from_pretrained(args.transformer_model_name)
+        self.compute_dtype = _compute_dtype(getattr(args, "compute_dtype", None))
+
+    def _concat_embeddings(self, images, source_encoding):
+        cd = self.compute_dtype
+        src = source_encoding["input_ids"]
+        pixel_values = images["pixel_values"]
+        B = pixel_values.shape[0]
+        with torch.no_grad():
+            lang = self.language_model.hidden_before_norm(src, cd)
+        img, n_img = self.image_model.features(pixel_values, cd)
+        d_img, d_lang, d_tr = img.shape[1], lang.shape[1], self.transformer.config.d_model
+        if d_img != d_lang:        # torch.cat in the reference (model.py:23) raises the same way
+            raise RuntimeError(f"Sizes of tensors must match except in dimension 1. Expected size {d_img} but got size {d_lang} "
+                               "for tensor number 1 in the list.")
+        if d_img != d_tr:
+            raise RuntimeError(f"inputs_embeds width {d_img} does not match the transformer's d_model {d_tr}")
+        lm, im = self.language_model, self.image_model
+        emb = Fn.apply_fn(Fn.ConcatEmbeddingsFn, img, im.layernorm.weight, im.layernorm.bias, im.config.layer_norm_eps, lang,
+                                          lm.encoder.final_layer_norm.weight, lm.config.layer_norm_epsilon, B)
+        return emb, B, n_img + src.shape[1]
+
+    def forward(self, images, source_encoding, target_encoding=None, return_loss=True):
+        emb, B, Le = self._concat_embeddings(images, source_encoding)
+        if return_loss:
+            return self.transformer.loss_from_embeds(emb, B, Le, target_encoding["input_ids"])
+        else:
+            with torch.no_grad():
+                return greedy_generate(self.transformer, emb, B, Le)
+
+    def save(self, result_name="best.pth"):
+        result_path = os.path.join(self.args.result_dir, result_name)
+        checkpoints = {'transformer': self.transformer.state_dict()}
+        if self.args.image_model_train:
+            checkpoints['image_model'] = self.image_model.state_dict()
+        torch.save(checkpoints, result_path)
+
+    def load(self, result_name="best.pth"):
+        result_path = os.path.join(self.args.result_dir, result_name)
+        checkpoints = torch.load(result_path)
+        self.transformer.load_state_dict(checkpoints['transformer'])
+        if self.args.image_model_train:
+            self.image_model.load_state_dict(checkpoints['image_model'])

@@ -72,9 +72,45 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool
         assert aux_out.dtype == out.dtype
     e.dropout_p = dropout_p
     e.dropout_seed = seed
+    if _GEMM_CHECK and a.dtype == torch.bfloat16:
+        _gemm_cross_check(a, b, M, N, K, a_mn, b_mn, out, e, aux_out)
     L.check(L.lib().klab_gemm(_stream(), _DT[a.dtype], M, N, K, a.data_ptr(), a.stride(0), int(a_mn),
                               b.data_ptr(), b.stride(0), int(b_mn), out.data_ptr(), out.stride(0), C.byref(e)))
+    if _GEMM_CHECK and a.dtype == torch.bfloat16:
+        _gemm_cross_check_finish(out, M, N, K, a_mn, b_mn, e)
     return out
+
+
+# KLAB_GEMM_CHECK=1: run every bf16 tcgen05 GEMM a second time on the fp32-accumulating SIMT kernel (same operands, same
+# epilogue) and report the calls whose results differ -- an on-device self check, not a fallback.
+import os as _os
+_GEMM_CHECK = bool(int(_os.environ.get("KLAB_GEMM_CHECK", "0")))
+_check_state: dict = {}
+
+
+def _gemm_cross_check(a, b, M, N, K, a_mn, b_mn, out, e, aux_out):
+    import copy
+    ref = out.clone() if e.accumulate else torch.empty_like(out)
+    e2 = L.GemmEpilogue()
+    C.memmove(C.byref(e2), C.byref(e), C.sizeof(e))
+    if aux_out is not None:
+        e2.aux_out = None
+    L.check(L.lib().klab_gemm_simt(_stream(), _DT[a.dtype], M, N, K, a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(),
+                                   b.stride(0), int(b_mn), ref.data_ptr(), ref.stride(0), C.byref(e2)))
+    _check_state["ref"] = ref
+
+
+def _gemm_cross_check_finish(out, M, N, K, a_mn, b_mn, e):
+    ref = _check_state.pop("ref")
+    o, r = out.float(), ref.float()
+    err = (o - r).abs().max().item()
+    scale = r.abs().max().item()
+    bad = not (err <= 2e-2 * scale + 1e-6)
+    _check_state["n"] = _check_state.get("n", 0) + 1
+    if bad:
+        print(f"[KLAB_GEMM_CHECK] call #{_check_state['n']} MISMATCH M={M} N={N} K={K} a_mn={int(a_mn)} b_mn={int(b_mn)} act={e.act} "
+              f"alpha={e.alpha:.4f} acc={e.accumulate} out_dtype={e.out_dtype} bias={bool(e.bias)} res={bool(e.residual)} "
+              f"ldd={out.stride(0)}: max err {err:.3e} vs scale {scale:.3e}", flush=True)
 
 
 def linear_fwd(x, w, **kw):
@@ -355,4 +391,11 @@ def cast(x, dtype, out=None):
     x = x.contiguous()
     y = torch.empty(x.shape, dtype=dtype, device=x.device) if out is None else out
     L.check(L.lib().klab_cast(_stream(), _DT[x.dtype], _DT[dtype], x.numel(), x.data_ptr(), y.data_ptr()))
+    return y
+
+
+def dropout_apply(x, p, seed):
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    L.check(L.lib().klab_dropout_apply(_stream(), _DT[x.dtype], x.numel(), x.data_ptr(), y.data_ptr(), p, seed))
     return y

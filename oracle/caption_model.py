@@ -127,10 +127,32 @@ def swin_param_shapes(d: SwinDims) -> dict:
 _TIED = ("encoder.embed_tokens.weight", "decoder.embed_tokens.weight", "lm_head.weight")
 
 
-def _seeded_tensor(seed: int, scope: str, key: str, shape) -> torch.Tensor:
+def _hf_std(scope: str, key: str, shape, dims) -> float | None:
+    """Standard deviations of HF's own initialisers (T5: HF/models/t5/modeling_t5.py:540-593 with factor 1;
+    Swin-V2: HF/models/swinv2/modeling_swinv2.py:883-902, initializer_range 0.02)."""
+    if scope == "image_model":
+        return 0.02 if len(shape) > 1 else None
+    d, dk, h, dff = dims.d_model, dims.d_kv, dims.num_heads, dims.d_ff
+    if key.endswith(".q.weight"):
+        return (d * dk) ** -0.5
+    if key.endswith((".k.weight", ".v.weight", "wi.weight", "relative_attention_bias.weight")):
+        return d ** -0.5
+    if key.endswith(".o.weight"):
+        return (h * dk) ** -0.5
+    if key.endswith("wo.weight"):
+        return dff ** -0.5
+    return None
+
+
+def _seeded_tensor(seed: int, scope: str, key: str, shape, style: str = "hot", dims=None) -> torch.Tensor:
+    """style "hot": 1/sqrt(fan_in) matrices (unscaled T5 attention then has logits of std ~ sqrt(d_kv): sharply peaked
+    softmaxes, a demanding fp32 test); style "hf": HF's initialiser scales (well conditioned: what bf16 parity is quoted on)."""
     rng = np.random.Generator(np.random.PCG64([seed, zlib.crc32(f"{scope}/{key}".encode())]))
     x = rng.standard_normal(size=shape, dtype=np.float32)
-    if key.endswith("logit_scale"):
+    std = _hf_std(scope, key, shape, dims) if style == "hf" else None
+    if std is not None:
+        x = x * np.float32(std)
+    elif key.endswith("logit_scale"):
         x = np.float32(np.log(10.0)) + np.float32(0.3) * x
     elif key.endswith("relative_attention_bias.weight"):
         x = np.float32(0.5) * x
@@ -146,24 +168,24 @@ def _seeded_tensor(seed: int, scope: str, key: str, shape) -> torch.Tensor:
     return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
 
 
-def seeded_state_dict(shapes: dict, seed: int, scope: str) -> dict:
+def seeded_state_dict(shapes: dict, seed: int, scope: str, style: str = "hot", dims=None) -> dict:
     sd = {}
     for key, shape in shapes.items():
         if key in _TIED:
             continue
-        sd[key] = _seeded_tensor(seed, scope, key, shape)
+        sd[key] = _seeded_tensor(seed, scope, key, shape, style, dims)
     for key in _TIED:
         if key in shapes:
             sd[key] = sd["shared.weight"]
     return sd
 
 
-def seeded_state_dicts(lm: T5Dims, swin: SwinDims, tr: T5Dims, seed: int = 0) -> dict:
+def seeded_state_dicts(lm: T5Dims, swin: SwinDims, tr: T5Dims, seed: int = 0, style: str = "hot") -> dict:
     """Weights for the three sub-models of MyModel (models/model.py:14-17), fp32, CPU."""
     return {
-        "language_model": seeded_state_dict(t5_param_shapes(lm, encoder_only=True), seed, "language_model"),
-        "image_model": seeded_state_dict(swin_param_shapes(swin), seed, "image_model"),
-        "transformer": seeded_state_dict(t5_param_shapes(tr), seed, "transformer"),
+        "language_model": seeded_state_dict(t5_param_shapes(lm, encoder_only=True), seed, "language_model", style, lm),
+        "image_model": seeded_state_dict(swin_param_shapes(swin), seed, "image_model", style, swin),
+        "transformer": seeded_state_dict(t5_param_shapes(tr), seed, "transformer", style, tr),
     }
 
 
