@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""Headline benchmark: train samples/sec of the Swin-V2 + T5 image-caption step (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload 2a|2b|1a|tiny] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is exactly what /root/reference/train.py:54-71 does per batch with accumulation_steps = 1:
+    (host->device copy of the batch) -> loss = model(images, src, tgt) -> loss.item() -> loss.backward() ->
+    optimizer.step() (Adam over model.transformer.parameters(), train.py:28) -> optimizer.zero_grad()
+with `model.transformer.train()` (T5 dropout p = 0.1 active, train.py:52) and DistributedDataParallel for N > 1.
+
+Workload at N = 1 ("2a", BASELINE.json configs[1] realised as SURVEY.md 8d recommends because Swin-B + T5-base cannot be
+concatenated, 1024 != 768): Swin-B/256/window 8 trained jointly + T5-large, bf16 tensor-core path, batch 64 per GPU,
+32 source + 32 target tokens, synthetic inputs, random-init weights.  One JSON line on stdout (rank 0).
+
+  value          : whole-job samples/s with the batch already resident in HBM (timed with CUDA events, max over ranks)
+  e2e            : same through the public API with HOST (pinned) inputs: H2D copies and the loss read-back inside the timed region
+  roofline       : the dominant kernel family (tcgen05 GEMM, ~97% of the FLOPs): algorithmic FLOPs of every GEMM launch of one
+                   step / CUDA-event duration of those launches, against MEASURED_PEAKS.json (sustained bf16 figure)
+  cpu_baseline   : the oracle port of the reference path (oracle/, plain torch fp32) on the host cores, bounded sample
+  --impl reference : that same CPU path as its own arm (the reference is Python glue over `transformers`; it has no build to
+                   compile, /root/reference does not exist on the GPU box, so the oracle port stands in: kind "port")
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# GFLOP per sample, fwd+bwd, counted on the reference graph
+WORKLOADS = {
+    "2a": dict(desc="MSCOCO caption train step, Swin-B/256/w8 trained jointly + T5-large (runnable realisation of configs[1])",
+               swin=dict(image_size=256, embed_dim=128, depths=(2, 2, 18, 2), num_heads=(4, 8, 16, 32), window_size=8),
+               t5="t5-large", batch=64, l_src=32, l_tgt=32, train_swin=True, gflop_per_sample=422.14),
+    "2b": dict(desc="MSCOCO caption train step, Swin-S/256/w8 trained jointly + T5-base",
+               swin=dict(image_size=256, embed_dim=96, depths=(2, 2, 18, 2), num_heads=(3, 6, 12, 24), window_size=8),
+               t5="t5-base", batch=64, l_src=32, l_tgt=32, train_swin=True, gflop_per_sample=157.01),
+    "1a": dict(desc="MSCOCO caption train step, frozen Swin-T/224/w7 + T5-base (runnable realisation of configs[0])",
+               swin=dict(image_size=224, embed_dim=96, depths=(2, 2, 6, 2), num_heads=(3, 6, 12, 24), window_size=7),
+               t5="t5-base", batch=2, l_src=32, l_tgt=32, train_swin=False, gflop_per_sample=87.53),
+    "tiny": dict(desc="smoke-sized step", swin=dict(image_size=64, embed_dim=32, depths=(2, 2, 2), num_heads=(1, 2, 4), window_size=4),
+                 t5=dict(vocab_size=512, d_model=128, d_ff=256, num_layers=2, num_heads=2), batch=4, l_src=8, l_tgt=8,
+                 train_swin=True, gflop_per_sample=0.05),
+}
+T5_NAMED = {"t5-small": dict(d_model=512, d_ff=2048, num_layers=6, num_heads=8),
+            "t5-base": dict(d_model=768, d_ff=3072, num_layers=12, num_heads=12),
+            "t5-large": dict(d_model=1024, d_ff=4096, num_layers=24, num_heads=16)}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return dict(tflops=p.get("bf16_tflops_sustained", 1378.2), burst=p.get("bf16_tflops", 1632.1), hbm=p.get("hbm_gbs", 6450.3),
+                    source="measured")
+    return dict(tflops=1400.0, burst=1590.0, hbm=6650.0, source="fallback")
+
+
+def synth_batch(w, vocab, seed, pin):
+    g = torch.Generator().manual_seed(seed)
+    s = w["swin"]["image_size"]
+    px = torch.randn(w["batch"], 3, s, s, generator=g)
+    src = torch.randint(2, vocab - 28, (w["batch"], w["l_src"]), generator=g)
+    tgt = torch.randint(2, vocab - 28, (w["batch"], w["l_tgt"]), generator=g)
+    tgt[:, -1] = 1
+    if pin:
+        px, src, tgt = px.pin_memory(), src.pin_memory(), tgt.pin_memory()
+    return px, src, tgt
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def mark(self):
+        return len(self.rows)
+
+    def summary(self, lo, hi):
+        rows = [r for r in self.rows[lo:max(hi, lo + 1)] if len(r) >= 6 and r[0].isdigit()]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(int(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(rows[0][1]), "reasons": reasons, "samples": len(rows)}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference's CPU path
+# --------------------------------------------------------------------------------------------------------------
+def cpu_reference_steps(w, steps, warmup, sample_batch, log=lambda *_: None):
+    """fwd + bwd + Adam step of the reference path restated in oracle/ (plain torch fp32 on the host cores)."""
+    from oracle.caption_model import caption_loss, swin_param_shapes, t5_param_shapes
+    from oracle.swinv2 import SwinDims
+    from oracle.t5 import T5Dims
+    torch.set_num_threads(os.cpu_count() or 1)
+    t5kw = T5_NAMED[w["t5"]] if isinstance(w["t5"], str) else w["t5"]
+    t5 = T5Dims(**t5kw)
+    sw = dict(w["swin"])
+    sw.setdefault("pretrained_window_sizes", (0,) * len(sw["depths"]))
+    swin = SwinDims(**sw)
+    g = torch.Generator().manual_seed(0)
+
+    def make(shapes, train):
+        sd, tied = {}, ("encoder.embed_tokens.weight", "decoder.embed_tokens.weight", "lm_head.weight")
+        for k, shp in shapes.items():
+            if k in tied:
+                continue
+            if len(shp) == 1 and k.endswith("weight"):
+                t = torch.ones(shp)
+            elif k.endswith("bias"):
+                t = torch.zeros(shp)
+            elif k.endswith("logit_scale"):
+                t = torch.full(shp, 2.302585)
+            else:
+                t = torch.randn(shp, generator=g) * (1.0 if k == "shared.weight" else shp[-1] ** -0.5 * 0.5)
+            sd[k] = t.requires_grad_(train)
+        for k in tied:
+            if k in shapes:
+                sd[k] = sd["shared.weight"]
+        return sd
+
+    sds = {"language_model": make(t5_param_shapes(t5, encoder_only=True), False),
+           "image_model": make(swin_param_shapes(swin), w["train_swin"]),
+           "transformer": make(t5_param_shapes(t5), True)}
+    params = list({id(v): v for v in sds["transformer"].values()}.values())
+    opt = torch.optim.Adam(params, lr=1e-3)
+    wb = dict(w, batch=sample_batch)
+    px, src, tgt = synth_batch(wb, t5.vocab_size, 1234, pin=False)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss = caption_loss(px, src, tgt, sds, t5, swin, t5)
+        lv = loss.item()
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        dt = time.perf_counter() - t0
+        log(f"cpu step {i}: {dt:.2f}s loss {lv:.3f}")
+        if i >= warmup:
+            times.append(dt)
+    return times
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = args.cpu_sample_batch
+    times = cpu_reference_steps(w, args.steps, args.warmup, sample, log=lambda m: print(m, file=sys.stderr))
+    ms = 1e3 * sum(times) / len(times)
+    val = sample / (ms / 1e3)
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": "train samples/sec (Swin+T5 caption step)", "value": val, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["desc"], "name": args.workload, "per_step_sample_batch": sample, "l_src": w["l_src"], "l_tgt": w["l_tgt"]},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} samples/step of the same model + sequence lengths, fwd+bwd+Adam, torch fp32, {cores} threads"},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------------------
+def build_model(w, device, dtype):
+    import types
+
+    from klab_multimodalmodel_b200.modeling import Swinv2Config, T5Config, init_swin_, init_t5_
+    from klab_multimodalmodel_b200.models.model import MyModel
+    t5kw = T5_NAMED[w["t5"]] if isinstance(w["t5"], str) else w["t5"]
+    tcfg = T5Config(**t5kw)
+    sw = dict(w["swin"])
+    sw.setdefault("pretrained_window_sizes", (0,) * len(sw["depths"]))
+    scfg = Swinv2Config(**sw)
+    args = types.SimpleNamespace(result_dir="/tmp", language_model_name=tcfg, image_model_name=scfg, image_model_train=w["train_swin"],
+                                 transformer_model_name=tcfg, compute_dtype=dtype)
+    model = MyModel(args)
+    init_t5_(model.language_model, seed=1)
+    init_swin_(model.image_model, seed=2)
+    init_t5_(model.transformer, seed=3)
+    return model.to(device), tcfg
+
+
+def gemm_roofline(model_step, pk):
+    """One extra instrumented step: CUDA events around every GEMM launch (on the launching stream)."""
+    from klab_multimodalmodel_b200 import ops as O
+    recs = []
+    orig = O.gemm
+
+    def timed(a, b, M, N, K, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        out = orig(a, b, M, N, K, **kw)
+        e.record()
+        recs.append((s, e, 2.0 * M * N * K))
+        return out
+
+    O.gemm = timed
+    try:
+        model_step()
+        torch.cuda.synchronize()
+    finally:
+        O.gemm = orig
+    ms = sum(s.elapsed_time(e) for s, e, _ in recs)
+    fl = sum(f for _, _, f in recs)
+    ach = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+    return {"bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None,
+            "kernel": "gemm_bf16_tc_kernel (tcgen05)", "launches_per_step": len(recs), "gemm_ms_per_step": ms,
+            "gemm_gflop_per_step": fl / 1e9, "peak_source": pk["source"] + " bf16 sustained"}
+
+
+def run_ours(args, w):
+    import torch.distributed as dist
+    from klab_multimodalmodel_b200 import _lib as L
+    from klab_multimodalmodel_b200 import ops as O
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L.check(L.lib().klab_check_device())
+    model, tcfg = build_model(w, dev, args.dtype)
+    model.transformer.train()                                        # train.py:52
+    net = model
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        net = DDP(model, device_ids=[local])
+    opt = torch.optim.Adam(model.transformer.parameters(), lr=1e-4)
+    px_h, src_h, tgt_h = synth_batch(w, tcfg.vocab_size, 1234 + rank, pin=True)
+    px_d, src_d, tgt_d = px_h.to(dev), src_h.to(dev), tgt_h.to(dev)
+    h2d = px_h.numel() * 4 + src_h.numel() * 8 + tgt_h.numel() * 8
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)    # > 126 MB L2
+
+    def step(px, src, tgt, read_loss=True):
+        loss = net({"pixel_values": px}, {"input_ids": src}, {"input_ids": tgt})
+        lv = loss.item() if read_loss else None                          # train.py:59 reads the loss every step
+        loss.backward()
+        opt.step()
+        opt.zero_grad()
+        return lv
+
+    def resident_step():
+        return step(px_d, src_d, tgt_d)
+
+    def e2e_step():
+        return step(px_h.to(dev, non_blocking=True), src_h.to(dev, non_blocking=True), tgt_h.to(dev, non_blocking=True))
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        total = 0.0
+        last = None
+        for _ in range(k):
+            flush.zero_()                                                   # L2 flush between timed iterations (untimed)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            last = fn()
+            e.record()
+            torch.cuda.synchronize()
+            total += s.elapsed_time(e)
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([total], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), last
+
+    for _ in range(max(args.warmup, 3)):
+        resident_step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    time.sleep(0.3)
+    lo = sampler.mark() if sampler else 0
+    l0 = O.launch_count()
+    ms_res, loss_v = timed(resident_step, args.steps)
+    launches = O.launch_count() - l0
+    hi = sampler.mark() if sampler else 0
+    ms_e2e, _ = timed(e2e_step, args.steps)
+    clocks = sampler.summary(lo, hi) if sampler else None
+    if sampler:
+        sampler.stop()
+    B = w["batch"]
+    ms_step = ms_res / args.steps
+    value = world * B / (ms_step * 1e-3)
+    e2e_val = world * B / (ms_e2e / args.steps * 1e-3)
+    pk = peaks()
+    roof = gemm_roofline(lambda: step(px_d, src_d, tgt_d), pk) if rank == 0 else None
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sb = args.cpu_sample_batch
+        times = cpu_reference_steps(w, 2, 1, sb, log=lambda m: print(m, file=sys.stderr))
+        cores = os.cpu_count() or 1
+        cpu = {"value": sb / (sum(times) / len(times)), "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": f"{sb} samples/step of the same model + sequence lengths (1 warm-up + 2 timed steps), fwd+bwd+Adam, torch fp32, {cores} threads"}
+    if rank == 0:
+        step_tflops = value * w["gflop_per_sample"] / 1e3
+        line = {
+            "metric": "train samples/sec (Swin+T5 caption step)", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "name": args.workload, "batch_per_gpu": B, "global_batch": B * world, "l_src": w["l_src"],
+                       "l_tgt": w["l_tgt"], "parallelism": f"dp{world}", "optimizer": "torch.optim.Adam over transformer params (train.py:28)",
+                       "dropout": "T5 p=0.1 active (train.py:52)", "l2_flush": "256 MiB buffer zeroed between timed iterations"},
+            "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "step_model_tflops": step_tflops, "step_frac_of_peak": step_tflops / pk["tflops"], "loss": loss_v,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="2a", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-sample-batch", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.batch:
+        w["batch"] = args.batch
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()
