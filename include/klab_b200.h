@@ -69,6 +69,7 @@ typedef struct klab_gemm_epilogue {
     int out_dtype, res_dtype, aux_in_dtype;
     float dropout_p;        /* 0 = off */
     unsigned long long dropout_seed;
+    const unsigned long long* dropout_seed_ptr; /* optional DEVICE counter added to dropout_seed (CUDA-graph friendly) */
 } klab_gemm_epilogue;
 
 int klab_gemm(void* stream, int in_dtype, int M, int N, int K,
@@ -116,18 +117,20 @@ long long klab_colsum_workspace_bytes(long long rows, int d);
  * causal: key j visible iff j <= i + q_offset.  bias_table NULL = cross-attention (zero bias).  rel_bucket is
  * the int32 LUT of T5Attention._relative_position_bucket built by the host with the reference's own torch ops
  * (bit-exact bucket edges).  lse fp32 [B,H,Lq] is saved for backward.  dropout_p > 0 drops probabilities with a
- * counter-based RNG keyed by (seed, b, h, i, j) that backward regenerates.
+ * counter-based RNG keyed by (seed + *seed_ptr, b, h, i, j) that backward regenerates.  d_kv = 64 with Lq, Lk <= 256 in bf16
+ * runs the tcgen05 kernel (t5_attention_tc.cu); other shapes / fp32 run the exact-fp32 CUDA-core kernel.
  * bwd: dq/dk/dv in the same layouts; dbias_table [num_buckets,H] is ACCUMULATED (the table of block 0 receives
  * the gradient of every block, :758). */
 int klab_t5_attention_fwd(void* stream, int dtype, int B, int H, int Lq, int Lk, int d_kv, const void* q, long long ldq,
                           const void* k, long long ldk, const void* v, long long ldv, void* out, long long ldo,
                           const float* bias_table, const int* rel_bucket, int rel_zero, int num_buckets, int causal,
-                          int q_offset, float* lse, float dropout_p, unsigned long long seed);
+                          int q_offset, float* lse, float dropout_p, unsigned long long seed,
+                          const unsigned long long* seed_ptr);
 int klab_t5_attention_bwd(void* stream, int dtype, int B, int H, int Lq, int Lk, int d_kv, const void* q, long long ldq,
                           const void* k, long long ldk, const void* v, long long ldv, const void* out, const void* dout,
                           long long ldo, void* dq, void* dk, void* dv, const float* bias_table, const int* rel_bucket,
                           int rel_zero, int num_buckets, int causal, int q_offset, const float* lse, float* dbias_table,
-                          float dropout_p, unsigned long long seed, void* workspace);
+                          float dropout_p, unsigned long long seed, const unsigned long long* seed_ptr, void* workspace);
 long long klab_t5_attention_bwd_workspace_bytes(int B, int H, int Lq, int num_buckets);
 
 /* ---- K2+K3+K4: Swin-V2 shifted-window cosine attention (HF/models/swinv2/modeling_swinv2.py:421-487,
@@ -177,7 +180,12 @@ int klab_greedy_step(void* stream, int B, int V, const float* logits, long long 
 
 /* y = x * keep(seed, linear index)/(1-p): the mask klab_gemm's epilogue dropout applied to a contiguous [M,N] output
  * (T5 dropout sites, HF/models/t5/modeling_t5.py:95,149,375,406,734,768), regenerated for the backward pass. */
-int klab_dropout_apply(void* stream, int dtype, long long n, const void* x, void* y, float p, unsigned long long seed);
+int klab_dropout_apply(void* stream, int dtype, long long n, const void* x, void* y, float p, unsigned long long seed,
+                       const unsigned long long* seed_ptr);
+/* Every dropout site takes `seed` (host scalar) plus an optional DEVICE counter `seed_ptr` whose value is added to it inside
+ * the kernel; klab_seed_advance steps that counter on the device once per training step, so a captured CUDA graph replays
+ * with fresh masks and without a host round trip. */
+int klab_seed_advance(void* stream, unsigned long long* seed_counter);
 
 /* dtype conversion (fp32 master weights -> bf16 operand copies). */
 int klab_cast(void* stream, int src_dtype, int dst_dtype, long long n, const void* src, void* dst);

@@ -21,7 +21,7 @@ class GemmEpilogue(C.Structure):
         ("ldr", C.c_longlong), ("ld_aux_in", C.c_longlong), ("ld_aux_out", C.c_longlong),
         ("alpha", C.c_float), ("act", C.c_int), ("accumulate", C.c_int),
         ("out_dtype", C.c_int), ("res_dtype", C.c_int), ("aux_in_dtype", C.c_int),
-        ("dropout_p", C.c_float), ("dropout_seed", C.c_ulonglong),
+        ("dropout_p", C.c_float), ("dropout_seed", C.c_ulonglong), ("dropout_seed_ptr", C.c_void_p),
     ]
 
 
@@ -63,9 +63,9 @@ SIGNATURES = {
     "klab_layernorm_bwd": [_vp, _i, _ll, _i, _vp, _ll, _i, _ll, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _vp, _ll, _vp, _vp, _i, _vp],
     "klab_colsum": [_vp, _i, _ll, _i, _vp, _ll, _vp, _i, _vp],
     "klab_colsum_workspace_bytes": [_ll, _i],
-    "klab_t5_attention_fwd": [_vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _vp, _f, _ull],
+    "klab_t5_attention_fwd": [_vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _i, _i, _i, _i, _vp, _f, _ull, _vp],
     "klab_t5_attention_bwd": [_vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp,
-                              _i, _i, _i, _i, _vp, _vp, _f, _ull, _vp],
+                              _i, _i, _i, _i, _vp, _vp, _f, _ull, _vp, _vp],
     "klab_t5_attention_bwd_workspace_bytes": [_i, _i, _i, _i],
     "klab_swin_attention_fwd": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _ll, _vp, _ll, _vp, _vp, _vp],
     "klab_swin_attention_bwd": [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _ll, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -79,7 +79,8 @@ SIGNATURES = {
     "klab_ce_bwd": [_vp, _i, _ll, _i, _vp, _ll, _i, _vp, _vp, _vp, _vp],
     "klab_cast": [_vp, _i, _i, _ll, _vp, _vp],
     "klab_greedy_step": [_vp, _i, _i, _vp, _ll, _vp, _ll, _i, _vp, _i, _i],
-    "klab_dropout_apply": [_vp, _i, _ll, _vp, _vp, _f, _ull],
+    "klab_dropout_apply": [_vp, _i, _ll, _vp, _vp, _f, _ull, _vp],
+    "klab_seed_advance": [_vp, _vp],
 }
 _RESTYPES = {"klab_last_error": C.c_char_p, "klab_launch_count": C.c_longlong,
              "klab_norm_bwd_workspace_bytes": C.c_longlong, "klab_colsum_workspace_bytes": C.c_longlong,

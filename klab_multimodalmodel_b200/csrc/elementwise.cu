@@ -194,7 +194,8 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(T* __restrict__ logits, lon
 // y[i] = x[i] * keep(seed, i) / (1 - p): regenerates the mask a GEMM epilogue applied to element (row*N + col)
 template <typename T>
 __global__ void dropout_apply_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, unsigned long long seed,
-                                     uint32_t thr, float inv_keep) {
+                                     const unsigned long long* __restrict__ seed_ptr, uint32_t thr, float inv_keep) {
+    if (seed_ptr) seed += *seed_ptr;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
         y[i] = from_f32<T>(to_f32(x[i]) * dropout_scale(seed, static_cast<uint64_t>(i), thr, inv_keep));
@@ -232,6 +233,8 @@ __global__ void __launch_bounds__(256) greedy_step_kernel(const float* __restric
         unfinished[b] = alive && nxt != eos_id;
     }
 }
+
+__global__ void seed_advance_kernel(unsigned long long* c) { *c = (*c) * 6364136223846793005ull + 1442695040888963407ull; }
 
 __global__ void scale_kernel(float* __restrict__ x, long long n, const float* __restrict__ s) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -341,16 +344,25 @@ int klab_greedy_step(void* stream, int B, int V, const float* logits, long long 
     return KLAB_OK;
 }
 
-int klab_dropout_apply(void* stream, int dtype, long long n, const void* x, void* y, float p, unsigned long long seed) {
+int klab_seed_advance(void* stream, unsigned long long* seed_counter) {
+    if (int rc = klab_check_device()) return rc;
+    seed_advance_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(seed_counter);
+    KLAB_LAUNCH_CHECK();
+    count_launch();
+    return KLAB_OK;
+}
+
+int klab_dropout_apply(void* stream, int dtype, long long n, const void* x, void* y, float p, unsigned long long seed,
+                       const unsigned long long* seed_ptr) {
     if (int rc = klab_check_device()) return rc;
     KLAB_REQUIRE(n > 0 && p >= 0.0f && p < 1.0f, "dropout_apply: bad arguments n=%lld p=%f", n, p);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const uint32_t thr = make_dropout_thr(p);
     const float inv_keep = 1.0f / (1.0f - p);
     if (dtype == KLAB_BF16)
-        dropout_apply_kernel<__nv_bfloat16><<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), n, seed, thr, inv_keep);
+        dropout_apply_kernel<__nv_bfloat16><<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), n, seed, seed_ptr, thr, inv_keep);
     else
-        dropout_apply_kernel<float><<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const float*>(x), reinterpret_cast<float*>(y), n, seed, thr, inv_keep);
+        dropout_apply_kernel<float><<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const float*>(x), reinterpret_cast<float*>(y), n, seed, seed_ptr, thr, inv_keep);
     KLAB_LAUNCH_CHECK();
     count_launch();
     return KLAB_OK;

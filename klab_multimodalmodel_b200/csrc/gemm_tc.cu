@@ -141,6 +141,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         // ===================== epilogue (warps 2..5) =====================
         const int sub = warp & 3;                              // TMEM sub-partition this warp may access
         const EpiDropout dr = make_dropout(epi.dropout_p);
+        if (dr.on && epi.dropout_seed_ptr) epi.dropout_seed += *epi.dropout_seed_ptr;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {

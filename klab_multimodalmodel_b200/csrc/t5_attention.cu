@@ -5,6 +5,8 @@
 // q/k/v/o are read and written in the [B*L, H*d_kv] layout the projection GEMMs produce (no transposes).
 // This kernel is exact-fp32 and serves the strict parity path for every shape; the bf16 hot path for
 // d_kv = 64 is the tcgen05 kernel in t5_attention_tc.cu.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace klab {
@@ -30,6 +32,7 @@ struct AttnArgs {
     float* dbias_partial;      // [B*H*chunks, num_buckets]
     float dropout_p;
     unsigned long long seed;
+    const unsigned long long* seed_ptr;
 };
 
 __device__ __forceinline__ float drop_mult(const AttnArgs& a, uint32_t thr, float inv_keep, int bh, int i, int j) {
@@ -41,6 +44,7 @@ __device__ __forceinline__ float drop_mult(const AttnArgs& a, uint32_t thr, floa
 template <typename T>
 __global__ void __launch_bounds__(NW * 32) t5_attn_fwd_kernel(AttnArgs a) {
     extern __shared__ float sm[];
+    if (a.seed_ptr) a.seed += *a.seed_ptr;
     const int dk = a.dk_, Lk = a.Lk, Lq = a.Lq, dp = dk + 1;
     float* Ks = sm;
     float* Vs = Ks + Lk * dp;
@@ -109,6 +113,7 @@ __global__ void __launch_bounds__(NW * 32) t5_attn_fwd_kernel(AttnArgs a) {
 template <typename T>
 __global__ void __launch_bounds__(NW * 32) t5_attn_bwd_dq_kernel(AttnArgs a) {
     extern __shared__ float sm[];
+    if (a.seed_ptr) a.seed += *a.seed_ptr;
     const int dk = a.dk_, Lk = a.Lk, Lq = a.Lq, dp = dk + 1;
     float* Ks = sm;
     float* Vs = Ks + Lk * dp;
@@ -195,6 +200,7 @@ __global__ void __launch_bounds__(NW * 32) t5_attn_bwd_dq_kernel(AttnArgs a) {
 template <typename T>
 __global__ void __launch_bounds__(NW * 32) t5_attn_bwd_dkv_kernel(AttnArgs a) {
     extern __shared__ float sm[];
+    if (a.seed_ptr) a.seed += *a.seed_ptr;
     const int dk = a.dk_, Lk = a.Lk, Lq = a.Lq, dp = dk + 1;
     float* Qs = sm;
     float* dOs = Qs + Lq * dp;
@@ -299,9 +305,31 @@ int set_smem(K kern, size_t bytes) {
 }
 
 }  // namespace
+
+// tensor-core path (t5_attention_tc.cu)
+bool t5_attention_tc_supported(int dtype, int Lq, int Lk, int d_kv, long long ldq, long long ldk, long long ldv, long long ldo,
+                               const void* q, const void* k, const void* v, const void* o);
+int t5_attention_fwd_tc(cudaStream_t st, int B, int H, int Lq, int Lk, const void* q, long long ldq, const void* k, long long ldk,
+                        const void* v, long long ldv, void* out, long long ldo, const float* bias_table, const int* rel_bucket,
+                        int rel_zero, int num_buckets, int causal, int q_offset, float* lse, float dropout_p, unsigned long long seed,
+                        const unsigned long long* seed_ptr);
+int t5_attention_bwd_tc(cudaStream_t st, int B, int H, int Lq, int Lk, const void* q, long long ldq, const void* k, long long ldk,
+                        const void* v, long long ldv, const void* out, const void* dout, long long ldo, void* dq, void* dk, void* dv,
+                        const float* bias_table, const int* rel_bucket, int rel_zero, int num_buckets, int causal, int q_offset,
+                        const float* lse, float* dbias_table, float dropout_p, unsigned long long seed,
+                        const unsigned long long* seed_ptr, void* workspace);
 }  // namespace klab
 
 using namespace klab;
+
+static bool force_generic_attention() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("KLAB_ATTENTION_GENERIC");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
 
 extern "C" {
 
@@ -313,15 +341,19 @@ long long klab_t5_attention_bwd_workspace_bytes(int B, int H, int Lq, int num_bu
 int klab_t5_attention_fwd(void* stream, int dtype, int B, int H, int Lq, int Lk, int d_kv, const void* q, long long ldq,
                           const void* k, long long ldk, const void* v, long long ldv, void* out, long long ldo,
                           const float* bias_table, const int* rel_bucket, int rel_zero, int num_buckets, int causal,
-                          int q_offset, float* lse, float dropout_p, unsigned long long seed) {
+                          int q_offset, float* lse, float dropout_p, unsigned long long seed,
+                          const unsigned long long* seed_ptr) {
     if (int rc = klab_check_device()) return rc;
     KLAB_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0 && d_kv > 0, "t5_attention_fwd: empty problem");
+    if (!force_generic_attention() && t5_attention_tc_supported(dtype, Lq, Lk, d_kv, ldq, ldk, ldv, ldo, q, k, v, out))
+        return t5_attention_fwd_tc(static_cast<cudaStream_t>(stream), B, H, Lq, Lk, q, ldq, k, ldk, v, ldv, out, ldo, bias_table,
+                                   rel_bucket, rel_zero, num_buckets, causal, q_offset, lse, dropout_p, seed, seed_ptr);
     AttnArgs a{};
     a.q = q; a.k = k; a.v = v; a.out = out;
     a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;
     a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.dk_ = d_kv;
     a.bias_table = bias_table; a.rel_bucket = rel_bucket; a.rel_zero = rel_zero; a.num_buckets = num_buckets;
-    a.causal = causal; a.q_offset = q_offset; a.lse = lse; a.dropout_p = dropout_p; a.seed = seed;
+    a.causal = causal; a.q_offset = q_offset; a.lse = lse; a.dropout_p = dropout_p; a.seed = seed; a.seed_ptr = seed_ptr;
     const size_t smem = fwd_smem(Lq, Lk, d_kv);
     const dim3 grid(B * H, (Lq + RPC - 1) / RPC);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -341,15 +373,20 @@ int klab_t5_attention_bwd(void* stream, int dtype, int B, int H, int Lq, int Lk,
                           const void* k, long long ldk, const void* v, long long ldv, const void* out, const void* dout,
                           long long ldo, void* dq, void* dk, void* dv, const float* bias_table, const int* rel_bucket,
                           int rel_zero, int num_buckets, int causal, int q_offset, const float* lse, float* dbias_table,
-                          float dropout_p, unsigned long long seed, void* workspace) {
+                          float dropout_p, unsigned long long seed, const unsigned long long* seed_ptr, void* workspace) {
     if (int rc = klab_check_device()) return rc;
     KLAB_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0 && d_kv > 0, "t5_attention_bwd: empty problem");
+    if (!force_generic_attention() && t5_attention_tc_supported(dtype, Lq, Lk, d_kv, ldq, ldk, ldv, ldo, q, k, v, out) &&
+        (reinterpret_cast<uintptr_t>(dout) & 15) == 0)
+        return t5_attention_bwd_tc(static_cast<cudaStream_t>(stream), B, H, Lq, Lk, q, ldq, k, ldk, v, ldv, out, dout, ldo, dq, dk, dv,
+                                   bias_table, rel_bucket, rel_zero, num_buckets, causal, q_offset, lse, dbias_table, dropout_p, seed,
+                                   seed_ptr, workspace);
     AttnArgs a{};
     a.q = q; a.k = k; a.v = v; a.o = out; a.dout = dout; a.dq = dq; a.dk = dk; a.dv = dv;
     a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;
     a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.dk_ = d_kv;
     a.bias_table = bias_table; a.rel_bucket = rel_bucket; a.rel_zero = rel_zero; a.num_buckets = num_buckets;
-    a.causal = causal; a.q_offset = q_offset; a.lse = const_cast<float*>(lse); a.dropout_p = dropout_p; a.seed = seed;
+    a.causal = causal; a.q_offset = q_offset; a.lse = const_cast<float*>(lse); a.dropout_p = dropout_p; a.seed = seed; a.seed_ptr = seed_ptr;
     const int chunks = (Lq + RPC - 1) / RPC;
     a.dvec = static_cast<float*>(workspace);
     a.dbias_partial = a.dvec + 1ll * B * H * Lq;

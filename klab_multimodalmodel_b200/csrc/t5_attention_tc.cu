@@ -1,0 +1,553 @@
+// K9 (hot path): T5 attention on the 5th-gen tensor cores, d_kv = 64, bf16 operands, whole (batch, head) problem resident.
+//
+// Semantics are exactly those of t5_attention.cu (HF/models/t5/modeling_t5.py:253-344: unscaled q k^T + bucketed relative bias
+// [+ causal mask], fp32 softmax, dropout on the probabilities, P v); this file only changes WHERE the arithmetic runs:
+//   * Q / K / V (and dO) tiles are fetched by TMA straight from the [B*L, H*64] projection-GEMM layout into 128B-swizzled
+//     shared memory -- no head transpose, no padding copies (rows past the sequence end are masked, not copied);
+//   * S = Q K^T, dP = dO V^T, O = P V, dV = P^T dO, dK = dS^T Q, dQ = dS K are tcgen05.mma with fp32 accumulators in TMEM;
+//     one smem tile serves both as a K-major and as an MN-major operand (P as A of P V and as A^T of P^T dO, ...);
+//   * softmax / dS run one-thread-per-row out of TMEM (tcgen05.ld), so S, P and dS never touch HBM.
+// Limits: d_kv == 64, Lq <= 256, Lk <= 256 (the reference's sequences are <= 176); anything else takes the generic kernel.
+#include "common.cuh"
+
+namespace klab {
+void count_launch(int n = 1);
+namespace {
+
+constexpr int DK = 64;
+constexpr int TILE = 128;
+
+struct TcArgs {
+    void* out;                 // fwd: ctx [B*Lq, ldo]
+    const void* o;             // bwd: ctx
+    const void* dout;          // bwd
+    void *dq, *dk, *dv;        // bwd outputs (row strides ldq / ldk / ldv)
+    long long ldq, ldk, ldv, ldo;
+    int B, H, Lq, Lk;
+    const float* bias_table;   // [num_buckets, H] or null
+    const int* rel_bucket;     // LUT, index (j - i - q_offset) + rel_zero
+    int rel_zero, num_buckets, causal, q_offset;
+    float* lse;                // [B, H, Lq]
+    float* dbias_partial;      // bwd: [B*H, num_buckets]
+    float dropout_p;
+    unsigned long long seed;
+    const unsigned long long* seed_ptr;
+};
+
+// byte offset of element (row, col) inside a [rows x 64] bf16 tile stored with the 128-byte swizzle (TMA SWIZZLE_128B /
+// UMMA SWIZZLE_128B): 16-byte chunk index XOR (row % 8)
+__device__ __forceinline__ uint32_t sw128(int row, int col) {
+    return static_cast<uint32_t>(row * 128 + ((((col >> 3) ^ (row & 7)) << 4) | ((col & 7) << 1)));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// store 8 consecutive columns [col8*8, col8*8+8) of row `row` of a swizzled [128 x 64] tile
+__device__ __forceinline__ void st_tile8(uint8_t* tile, int row, int col8, const float* v) {
+    uint4 q;
+    q.x = pack_bf16(v[0], v[1]); q.y = pack_bf16(v[2], v[3]); q.z = pack_bf16(v[4], v[5]); q.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(tile + row * 128 + ((col8 ^ (row & 7)) << 4)) = q;
+}
+
+__device__ __forceinline__ float drop_mult(const TcArgs& a, uint64_t seed, uint32_t thr, float inv_keep, int bh, int i, int j) {
+    const uint64_t idx = (static_cast<uint64_t>(bh) * a.Lq + i) * a.Lk + j;
+    return dropout_scale(seed, idx, thr, inv_keep);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// forward: grid (ceil(Lq/128), H, B), 128 threads; thread t owns query row q0 + t (TMEM lane t)
+// smem: Q 16K | K <=32K | V <=32K | P <=64K (k-blocks of 64 keys, 16K each) | brel | barriers
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) t5_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
+                                                             const __grid_constant__ CUtensorMap tmv, TcArgs a, int lk_pad, int o_col,
+                                                             int tmem_cols) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + TILE * 128;
+    uint8_t* sV = sK + lk_pad * 128;
+    uint8_t* sP = sV + lk_pad * 128;
+    const int nkb = (lk_pad + 63) / 64;
+    float* brel = reinterpret_cast<float*>(sP + nkb * TILE * 128);           // [Lq + Lk]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(brel + ((a.Lq + a.Lk + 3) & ~3));
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+
+    const int q0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z, bh = b * a.H + h;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int Lq = a.Lq, Lk = a.Lk;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);     // TMA
+        mbar_init(&bars[1], 1);     // S ready
+        mbar_init(&bars[2], 1);     // O ready
+        fence_barrier_init();
+        mbar_arrive_expect_tx(&bars[0], TILE * 128 + 2 * lk_pad * 128);
+        tma_load_2d(sQ, &tmq, &bars[0], h * DK, b * Lq + q0);
+        tma_load_2d(sK, &tmk, &bars[0], h * DK, b * Lk);
+        tma_load_2d(sV, &tmv, &bars[0], h * DK, b * Lk);
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tmem_alloc(tmem_ptr, tmem_cols);
+        tmem_relinquish();
+    }
+    if (a.bias_table)
+        for (int r = tid; r < Lq + Lk - 1; r += blockDim.x) {
+            const int rel = r - (Lq - 1) - a.q_offset;
+            brel[r] = a.bias_table[a.rel_bucket[rel + a.rel_zero] * a.H + h];
+        }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+
+    if (tid == 0) {
+        mbar_wait(&bars[0], 0);
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_bf16(TILE, lk_pad, false, false);
+        const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
+#pragma unroll
+        for (int k = 0; k < DK / 16; ++k)
+            umma_bf16(tmem, umma_smem_desc_sw128(qa + k * 32, 16, 1024), umma_smem_desc_sw128(ka + k * 32, 16, 1024), idesc, k != 0);
+        umma_commit(&bars[1]);
+    }
+    mbar_wait(&bars[1], 0);
+    tc_fence_after();
+
+    const int i = q0 + tid;                                   // query row of this thread (may be >= Lq: computed, never stored)
+    const int jmax = a.causal ? min(Lk, i + a.q_offset + 1) : Lk;
+    const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint64_t seed = a.seed + (a.seed_ptr ? *a.seed_ptr : 0ull);
+    const uint32_t thr = make_dropout_thr(a.dropout_p);
+    const float inv_keep = a.dropout_p > 0.0f ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
+    const float* br = brel + (Lq - 1 - i);                     // br[j] = bias(j - i)
+    const bool has_bias = a.bias_table != nullptr && i < Lq;
+
+    // pass 1: row maximum
+    float mx = -INFINITY;
+    for (int c0 = 0; c0 < lk_pad; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(trow + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+            const int j = c0 + t;
+            if (j < jmax) mx = fmaxf(mx, __uint_as_float(r[t]) + (has_bias ? br[j] : 0.0f));
+        }
+    }
+    // pass 2: p = exp(s - max), row sum, P (bf16, dropout applied) -> smem
+    float sum = 0.0f;
+    for (int c0 = 0; c0 < lk_pad; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(trow + c0, r);
+        tmem_ld_wait();
+        float p[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+            const int j = c0 + t;
+            float e = 0.0f;
+            if (j < jmax) {
+                e = __expf(__uint_as_float(r[t]) + (has_bias ? br[j] : 0.0f) - mx);
+                sum += e;
+                if (a.dropout_p > 0.0f) e *= drop_mult(a, seed, thr, inv_keep, bh, i, j);
+            }
+            p[t] = e;
+        }
+        uint8_t* blk = sP + (c0 >> 6) * (TILE * 128);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) st_tile8(blk, tid, ((c0 & 63) >> 3) + g, p + 8 * g);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (tid == 0) {
+        const uint32_t idesc = umma_idesc_bf16(TILE, DK, false, true);
+        const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
+        for (int ks = 0; ks < lk_pad / 16; ++ks) {
+            const uint64_t da = umma_smem_desc_sw128(pa + (ks >> 2) * (TILE * 128) + (ks & 3) * 32, 16, 1024);
+            const uint64_t db = umma_smem_desc_sw128(va + ks * 2048, 8192, 1024);
+            umma_bf16(tmem + o_col, da, db, idesc, ks != 0);
+        }
+        umma_commit(&bars[2]);
+    }
+    mbar_wait(&bars[2], 0);
+    tc_fence_after();
+
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int c0 = 0; c0 < DK; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(trow + o_col + c0, r);
+        tmem_ld_wait();
+        if (i < Lq) {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + (static_cast<long long>(b) * Lq + i) * a.ldo + h * DK + c0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint4 q;
+                q.x = pack_bf16(__uint_as_float(r[8 * g]) * inv, __uint_as_float(r[8 * g + 1]) * inv);
+                q.y = pack_bf16(__uint_as_float(r[8 * g + 2]) * inv, __uint_as_float(r[8 * g + 3]) * inv);
+                q.z = pack_bf16(__uint_as_float(r[8 * g + 4]) * inv, __uint_as_float(r[8 * g + 5]) * inv);
+                q.w = pack_bf16(__uint_as_float(r[8 * g + 6]) * inv, __uint_as_float(r[8 * g + 7]) * inv);
+                reinterpret_cast<uint4*>(op)[g] = q;
+            }
+        }
+    }
+    if (i < Lq) a.lse[static_cast<long long>(bh) * Lq + i] = mx + __logf(sum);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, tmem_cols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// backward: grid (H, B), 128 threads.  Key blocks of 128 (kb) x query tiles of 128 (qt):
+//   S = Q_qt K_kb^T, dP = dO_qt V_kb^T            -> TMEM (2 x 128 cols)
+//   P = exp(S + bias - lse), dS = P (dP*m - D)    -> smem (bf16, two [128 x 64] swizzled blocks each)
+//   dV_kb += P^T dO_qt, dK_kb += dS^T Q_qt        -> TMEM (2 x 64 cols), written out after the qt loop
+//   dQ_qt += dS K_kb                              -> TMEM (2 x 64 cols), written out at the end
+// smem: Q 2x16K | dO 2x16K | K 2x16K | V 2x16K | P 32K | dS 32K | brel/drel | barriers      (~200 KB, 1 CTA / SM)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) t5_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
+                                                             const __grid_constant__ CUtensorMap tmv, const __grid_constant__ CUtensorMap tmdo,
+                                                             TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int T = TILE * 128;          // bytes of one [128 x 64] bf16 tile
+    const int nq = (a.Lq + TILE - 1) / TILE, nk = (a.Lk + TILE - 1) / TILE;
+    uint8_t* sQ = smem;
+    uint8_t* sdO = sQ + nq * T;
+    uint8_t* sK = sdO + nq * T;
+    uint8_t* sV = sK + nk * T;
+    uint8_t* sP = sV + nk * T;              // 2 blocks of 64 keys
+    uint8_t* sdS = sP + 2 * T;
+    float* brel = reinterpret_cast<float*>(sdS + 2 * T);                     // [Lq + Lk] bias per relative position
+    float* drel = brel + ((a.Lq + a.Lk + 3) & ~3);                           // [Lq + Lk] dS summed per relative position
+    float* bins = drel + ((a.Lq + a.Lk + 3) & ~3);                           // [num_buckets] per-bucket sums
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bins + ((a.num_buckets + 3) & ~3));
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+
+    const int h = blockIdx.x, b = blockIdx.y, bh = b * a.H + h;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int Lq = a.Lq, Lk = a.Lk;
+    constexpr int TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;   // + 64 per query tile
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_barrier_init();
+        mbar_arrive_expect_tx(&bars[0], 2 * (nq + nk) * T);
+        for (int t = 0; t < nq; ++t) {
+            tma_load_2d(sQ + t * T, &tmq, &bars[0], h * DK, b * Lq + t * TILE);
+            tma_load_2d(sdO + t * T, &tmdo, &bars[0], h * DK, b * Lq + t * TILE);
+        }
+        for (int t = 0; t < nk; ++t) {
+            tma_load_2d(sK + t * T, &tmk, &bars[0], h * DK, b * Lk + t * TILE);
+            tma_load_2d(sV + t * T, &tmv, &bars[0], h * DK, b * Lk + t * TILE);
+        }
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tmem_alloc(tmem_ptr, 512);
+        tmem_relinquish();
+    }
+    const bool has_bias = a.bias_table != nullptr;
+    if (has_bias)
+        for (int r = tid; r < Lq + Lk - 1; r += blockDim.x) {
+            const int rel = r - (Lq - 1) - a.q_offset;
+            brel[r] = a.bias_table[a.rel_bucket[rel + a.rel_zero] * a.H + h];
+            drel[r] = 0.0f;
+        }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+    const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint64_t seed = a.seed + (a.seed_ptr ? *a.seed_ptr : 0ull);
+    const uint32_t thr = make_dropout_thr(a.dropout_p);
+    const float inv_keep = a.dropout_p > 0.0f ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
+
+    // per query tile: D_i = dO_i . O_i and lse_i of the row this thread owns (global loads, overlapped with the TMA)
+    float Dv[2] = {0.0f, 0.0f}, lsev[2] = {0.0f, 0.0f};
+    for (int qt = 0; qt < nq; ++qt) {
+        const int i = qt * TILE + tid;
+        if (i < Lq) {
+            const long long row = static_cast<long long>(b) * Lq + i;
+            const uint4* dop = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.dout) + row * a.ldo + h * DK);
+            const uint4* op = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(a.o) + row * a.ldo + h * DK);
+            float acc = 0.0f;
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const uint4 x = dop[g], y = op[g];
+                const __nv_bfloat162* xh = reinterpret_cast<const __nv_bfloat162*>(&x);
+                const __nv_bfloat162* yh = reinterpret_cast<const __nv_bfloat162*>(&y);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const float2 xf = __bfloat1622float2(xh[t]), yf = __bfloat1622float2(yh[t]);
+                    acc = fmaf(xf.x, yf.x, fmaf(xf.y, yf.y, acc));
+                }
+            }
+            Dv[qt] = acc;
+            lsev[qt] = a.lse[static_cast<long long>(bh) * Lq + i];
+        }
+    }
+
+    uint32_t phase = 0;
+    if (tid == 0) {
+        mbar_wait(&bars[0], 0);
+        tc_fence_after();
+    }
+    __syncthreads();
+
+    const uint32_t id_s = umma_idesc_bf16(TILE, TILE, false, false);     // S / dP : A K-major, B K-major, N = 128
+    const uint32_t id_t = umma_idesc_bf16(TILE, DK, true, true);         // dV / dK: A MN-major (P^T), B MN-major, N = 64
+    const uint32_t id_q = umma_idesc_bf16(TILE, DK, false, true);        // dQ     : A K-major (dS), B MN-major (K), N = 64
+
+    for (int kb = 0; kb < nk; ++kb) {
+        for (int qt = 0; qt < nq; ++qt) {
+            if (tid == 0) {
+                const uint32_t qa = smem_u32(sQ + qt * T), doa = smem_u32(sdO + qt * T);
+                const uint32_t ka = smem_u32(sK + kb * T), va = smem_u32(sV + kb * T);
+#pragma unroll
+                for (int k = 0; k < DK / 16; ++k)
+                    umma_bf16(tmem + TM_S, umma_smem_desc_sw128(qa + k * 32, 16, 1024), umma_smem_desc_sw128(ka + k * 32, 16, 1024), id_s, k != 0);
+#pragma unroll
+                for (int k = 0; k < DK / 16; ++k)
+                    umma_bf16(tmem + TM_DP, umma_smem_desc_sw128(doa + k * 32, 16, 1024), umma_smem_desc_sw128(va + k * 32, 16, 1024), id_s, k != 0);
+                umma_commit(&bars[1]);
+            }
+            mbar_wait(&bars[1], phase);
+            phase ^= 1;
+            tc_fence_after();
+
+            const int i = qt * TILE + tid;
+            const int jmax = a.causal ? min(Lk, i + a.q_offset + 1) : Lk;
+            const float* br = brel + (Lq - 1 - i);
+            float* dr = drel + (Lq - 1 - i);
+            const bool row_ok = i < Lq;
+            for (int c0 = 0; c0 < TILE; c0 += 32) {
+                uint32_t rs[32], rp[32];
+                tmem_ld_32x32(trow + TM_S + c0, rs);
+                tmem_ld_32x32(trow + TM_DP + c0, rp);
+                tmem_ld_wait();
+                float pv[32], dsv[32];
+#pragma unroll
+                for (int t = 0; t < 32; ++t) {
+                    const int j = kb * TILE + c0 + t;
+                    float p = 0.0f, ds = 0.0f;
+                    if (row_ok && j < jmax) {
+                        const float pr = __expf(__uint_as_float(rs[t]) + (has_bias ? br[j] : 0.0f) - lsev[qt]);
+                        const float m = a.dropout_p > 0.0f ? drop_mult(a, seed, thr, inv_keep, bh, i, j) : 1.0f;
+                        p = pr * m;
+                        ds = pr * (__uint_as_float(rp[t]) * m - Dv[qt]);
+                        if (has_bias) atomicAdd(&dr[j], ds);
+                    }
+                    pv[t] = p;
+                    dsv[t] = ds;
+                }
+                uint8_t* pb = sP + (c0 >> 6) * T;
+                uint8_t* db = sdS + (c0 >> 6) * T;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    st_tile8(pb, tid, ((c0 & 63) >> 3) + g, pv + 8 * g);
+                    st_tile8(db, tid, ((c0 & 63) >> 3) + g, dsv + 8 * g);
+                }
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            tc_fence_after();
+            if (tid == 0) {
+                const uint32_t pa = smem_u32(sP), dsa = smem_u32(sdS);
+                const uint32_t qa = smem_u32(sQ + qt * T), doa = smem_u32(sdO + qt * T), ka = smem_u32(sK + kb * T);
+                // dV_kb += P^T dO_qt ; dK_kb += dS^T Q_qt : M = 128 keys (MN-major A: atoms of 64 keys are T bytes apart), K = 128 queries
+#pragma unroll
+                for (int ks = 0; ks < TILE / 16; ++ks) {
+                    umma_bf16(tmem + TM_DV, umma_smem_desc_sw128(pa + ks * 2048, T, 1024), umma_smem_desc_sw128(doa + ks * 2048, 8192, 1024),
+                              id_t, (qt | ks) != 0);
+                    umma_bf16(tmem + TM_DK, umma_smem_desc_sw128(dsa + ks * 2048, T, 1024), umma_smem_desc_sw128(qa + ks * 2048, 8192, 1024),
+                              id_t, (qt | ks) != 0);
+                }
+                // dQ_qt += dS K_kb : A K-major (k-blocks of 64 keys are T bytes apart), B = K_kb MN-major, K = 128 keys
+#pragma unroll
+                for (int ks = 0; ks < TILE / 16; ++ks)
+                    umma_bf16(tmem + TM_DQ + qt * DK, umma_smem_desc_sw128(dsa + (ks >> 2) * T + (ks & 3) * 32, 16, 1024),
+                              umma_smem_desc_sw128(ka + ks * 2048, 8192, 1024), id_q, (kb | ks) != 0);
+                umma_commit(&bars[1]);
+            }
+            // the MMAs above read sP / sdS: wait for them before the next iteration overwrites the tiles
+            mbar_wait(&bars[1], phase);
+            phase ^= 1;
+            tc_fence_after();
+        }
+        // dV_kb, dK_kb complete: lane t = key kb*128 + t
+        const int j = kb * TILE + tid;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+#pragma unroll
+            for (int c0 = 0; c0 < DK; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(trow + (which ? TM_DK : TM_DV) + c0, r);
+                tmem_ld_wait();
+                if (j < Lk) {
+                    __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(which ? a.dk : a.dv);
+                    const long long ld = which ? a.ldk : a.ldv;
+                    uint4* dst = reinterpret_cast<uint4*>(base + (static_cast<long long>(b) * Lk + j) * ld + h * DK + c0);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 q;
+                        q.x = pack_bf16(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1]));
+                        q.y = pack_bf16(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
+                        q.z = pack_bf16(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
+                        q.w = pack_bf16(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
+                        dst[g] = q;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();          // all lanes have drained dV / dK before the next key block re-initialises them
+        tc_fence_after();
+    }
+    // dQ
+    for (int qt = 0; qt < nq; ++qt) {
+        const int i = qt * TILE + tid;
+#pragma unroll
+        for (int c0 = 0; c0 < DK; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(trow + TM_DQ + qt * DK + c0, r);
+            tmem_ld_wait();
+            if (i < Lq) {
+                uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.dq) + (static_cast<long long>(b) * Lq + i) * a.ldq + h * DK + c0);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 q;
+                    q.x = pack_bf16(__uint_as_float(r[8 * g]), __uint_as_float(r[8 * g + 1]));
+                    q.y = pack_bf16(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
+                    q.z = pack_bf16(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
+                    q.w = pack_bf16(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
+                    dst[g] = q;
+                }
+            }
+        }
+    }
+    // bias gradient: per relative position -> per bucket partial of this (b, h)
+    if (has_bias) {
+        __syncthreads();
+        float* part = a.dbias_partial + static_cast<long long>(bh) * a.num_buckets;
+        for (int r = tid; r < a.num_buckets; r += blockDim.x) bins[r] = 0.0f;
+        __syncthreads();
+        for (int r = tid; r < Lq + Lk - 1; r += blockDim.x) {
+            const int rel = r - (Lq - 1) - a.q_offset;
+            atomicAdd(&bins[a.rel_bucket[rel + a.rel_zero]], drel[r]);
+        }
+        __syncthreads();
+        for (int r = tid; r < a.num_buckets; r += blockDim.x) part[r] = bins[r];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+// dtable[bucket, h] += sum_b partial[(b*H + h), bucket]      (one thread per (bucket, h); B is small)
+__global__ void t5_dbias_reduce_tc_kernel(const float* __restrict__ part, int B, int H, int nb, float* __restrict__ dtable) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nb * H) return;
+    const int bucket = idx / H, h = idx % H;
+    float s = 0.0f;
+    for (int b = 0; b < B; ++b) s += part[(static_cast<long long>(b) * H + h) * nb + bucket];
+    dtable[idx] += s;
+}
+
+int make_head_map(CUtensorMap* m, const void* base, long long rows, int H, long long ld, int box_rows) {
+    return make_tmap_2d_bf16(m, base, static_cast<uint64_t>(rows), static_cast<uint64_t>(H) * DK, static_cast<uint64_t>(ld), box_rows, DK);
+}
+
+}  // namespace
+
+bool t5_attention_tc_supported(int dtype, int Lq, int Lk, int d_kv, long long ldq, long long ldk, long long ldv, long long ldo,
+                               const void* q, const void* k, const void* v, const void* o) {
+    if (dtype != KLAB_BF16 || d_kv != DK || Lq > 256 || Lk > 256) return false;
+    if ((ldq | ldk | ldv | ldo) % 8) return false;
+    return ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(o)) & 15) == 0;
+}
+
+int t5_attention_fwd_tc(cudaStream_t st, int B, int H, int Lq, int Lk, const void* q, long long ldq, const void* k, long long ldk,
+                        const void* v, long long ldv, void* out, long long ldo, const float* bias_table, const int* rel_bucket,
+                        int rel_zero, int num_buckets, int causal, int q_offset, float* lse, float dropout_p, unsigned long long seed,
+                        const unsigned long long* seed_ptr) {
+    const int lk_pad = (Lk + 15) / 16 * 16;
+    const int o_col = lk_pad <= 64 ? 64 : (lk_pad <= 192 ? 192 : 256);
+    const int tmem_cols = o_col + 64 <= 128 ? 128 : (o_col + 64 <= 256 ? 256 : 512);
+    CUtensorMap tq, tk, tv;
+    if (int rc = make_head_map(&tq, q, 1ll * B * Lq, H, ldq, TILE)) return rc;
+    if (int rc = make_head_map(&tk, k, 1ll * B * Lk, H, ldk, lk_pad)) return rc;
+    if (int rc = make_head_map(&tv, v, 1ll * B * Lk, H, ldv, lk_pad)) return rc;
+    TcArgs a{};
+    a.out = out; a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo; a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk;
+    a.bias_table = bias_table; a.rel_bucket = rel_bucket; a.rel_zero = rel_zero; a.num_buckets = num_buckets; a.causal = causal;
+    a.q_offset = q_offset; a.lse = lse; a.dropout_p = dropout_p; a.seed = seed; a.seed_ptr = seed_ptr;
+    const int nkb = (lk_pad + 63) / 64;
+    const size_t smem = 1024 + TILE * 128 + 2 * lk_pad * 128 + nkb * TILE * 128 + sizeof(float) * ((Lq + Lk + 3) & ~3) + 64;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        KLAB_CHECK_CUDA(cudaFuncSetAttribute(t5_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    const dim3 grid((Lq + TILE - 1) / TILE, H, B);
+    t5_attn_fwd_tc_kernel<<<grid, 128, smem, st>>>(tq, tk, tv, a, lk_pad, o_col, tmem_cols);
+    KLAB_LAUNCH_CHECK();
+    count_launch();
+    return KLAB_OK;
+}
+
+long long t5_attention_bwd_tc_workspace_bytes(int B, int H, int num_buckets) { return sizeof(float) * 1ll * B * H * num_buckets; }
+
+int t5_attention_bwd_tc(cudaStream_t st, int B, int H, int Lq, int Lk, const void* q, long long ldq, const void* k, long long ldk,
+                        const void* v, long long ldv, const void* out, const void* dout, long long ldo, void* dq, void* dk, void* dv,
+                        const float* bias_table, const int* rel_bucket, int rel_zero, int num_buckets, int causal, int q_offset,
+                        const float* lse, float* dbias_table, float dropout_p, unsigned long long seed,
+                        const unsigned long long* seed_ptr, void* workspace) {
+    CUtensorMap tq, tk, tv, tdo;
+    if (int rc = make_head_map(&tq, q, 1ll * B * Lq, H, ldq, TILE)) return rc;
+    if (int rc = make_head_map(&tk, k, 1ll * B * Lk, H, ldk, TILE)) return rc;
+    if (int rc = make_head_map(&tv, v, 1ll * B * Lk, H, ldv, TILE)) return rc;
+    if (int rc = make_head_map(&tdo, dout, 1ll * B * Lq, H, ldo, TILE)) return rc;
+    TcArgs a{};
+    a.o = out; a.dout = dout; a.dq = dq; a.dk = dk; a.dv = dv;
+    a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo; a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk;
+    a.bias_table = bias_table; a.rel_bucket = rel_bucket; a.rel_zero = rel_zero; a.num_buckets = num_buckets; a.causal = causal;
+    a.q_offset = q_offset; a.lse = const_cast<float*>(lse); a.dropout_p = dropout_p; a.seed = seed; a.seed_ptr = seed_ptr;
+    a.dbias_partial = static_cast<float*>(workspace);
+    const int nq = (Lq + TILE - 1) / TILE, nk = (Lk + TILE - 1) / TILE;
+    const size_t smem = 1024 + static_cast<size_t>(2 * nq + 2 * nk + 4) * TILE * 128 + 2 * sizeof(float) * ((Lq + Lk + 3) & ~3) +
+                        sizeof(float) * ((num_buckets + 3) & ~3) + 64;
+    KLAB_REQUIRE(smem <= 227 * 1024, "t5_attention_bwd_tc: %zu bytes of shared memory", smem);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        KLAB_CHECK_CUDA(cudaFuncSetAttribute(t5_attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    const dim3 grid(H, B);
+    t5_attn_bwd_tc_kernel<<<grid, 128, smem, st>>>(tq, tk, tv, tdo, a);
+    KLAB_LAUNCH_CHECK();
+    count_launch();
+    if (bias_table && dbias_table) {
+        const int n = num_buckets * H;
+        t5_dbias_reduce_tc_kernel<<<(n + 127) / 128, 128, 0, st>>>(a.dbias_partial, B, H, num_buckets, dbias_table);
+        KLAB_LAUNCH_CHECK();
+        count_launch();
+    }
+    return KLAB_OK;
+}
+
+}  // namespace klab

@@ -38,7 +38,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool
          out: torch.Tensor | None = None, out_dtype: torch.dtype | None = None, bias: torch.Tensor | None = None,
          act: int = L.ACT_NONE, residual: torch.Tensor | None = None, aux_in: torch.Tensor | None = None,
          aux_out: torch.Tensor | None = None, alpha: float = 1.0, accumulate: bool = False,
-         dropout_p: float = 0.0, seed: int = 0, ldd_pad: int | None = None) -> torch.Tensor:
+         dropout_p: float = 0.0, seed: int = 0, seed_ptr: torch.Tensor | None = None, ldd_pad: int | None = None) -> torch.Tensor:
     """D[M,N] = epilogue(alpha * A(m,k) B(n,k)); see klab_gemm in include/klab_b200.h.
 
     `a` / `b` are 2-D tensors whose row stride is taken from .stride(0) (column slices of a wider buffer are fine).
@@ -72,6 +72,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool
         assert aux_out.dtype == out.dtype
     e.dropout_p = dropout_p
     e.dropout_seed = seed
+    e.dropout_seed_ptr = _p(seed_ptr)
     if _GEMM_CHECK and a.dtype == torch.bfloat16:
         _gemm_cross_check(a, b, M, N, K, a_mn, b_mn, out, e, aux_out)
     L.check(L.lib().klab_gemm(_stream(), _DT[a.dtype], M, N, K, a.data_ptr(), a.stride(0), int(a_mn),
@@ -216,17 +217,18 @@ def t5_rel_bucket_lut(lq: int, lk: int, bidirectional: bool, num_buckets: int, m
 
 
 def t5_attention_fwd(q, k, v, B, H, Lq, Lk, dk, *, bias_table=None, lut=None, rel_zero=0, num_buckets=32, causal=False,
-                     q_offset=0, dropout_p=0.0, seed=0, out=None):
+                     q_offset=0, dropout_p=0.0, seed=0, seed_ptr=None, out=None):
     ctx = torch.empty(B * Lq, H * dk, dtype=q.dtype, device=q.device) if out is None else out
     lse = torch.empty(B, H, Lq, dtype=torch.float32, device=q.device)
     L.check(L.lib().klab_t5_attention_fwd(_stream(), _DT[q.dtype], B, H, Lq, Lk, dk, q.data_ptr(), q.stride(0), k.data_ptr(),
                                           k.stride(0), v.data_ptr(), v.stride(0), ctx.data_ptr(), ctx.stride(0), _p(bias_table),
-                                          _p(lut), rel_zero, num_buckets, int(causal), q_offset, lse.data_ptr(), dropout_p, seed))
+                                          _p(lut), rel_zero, num_buckets, int(causal), q_offset, lse.data_ptr(), dropout_p, seed,
+                                          _p(seed_ptr)))
     return ctx, lse
 
 
 def t5_attention_bwd(q, k, v, ctx, dctx, lse, dq, dk_, dv, B, H, Lq, Lk, dk, *, bias_table=None, lut=None, rel_zero=0,
-                     num_buckets=32, causal=False, q_offset=0, dbias_table=None, dropout_p=0.0, seed=0):
+                     num_buckets=32, causal=False, q_offset=0, dbias_table=None, dropout_p=0.0, seed=0, seed_ptr=None):
     """dq / dk_ / dv are preallocated outputs with the same row strides as q / k / v."""
     assert dq.stride(0) == q.stride(0) and dk_.stride(0) == k.stride(0) and dv.stride(0) == v.stride(0)
     assert dctx.stride(0) == ctx.stride(0)
@@ -235,7 +237,7 @@ def t5_attention_bwd(q, k, v, ctx, dctx, lse, dq, dk_, dv, B, H, Lq, Lk, dk, *, 
                                           k.stride(0), v.data_ptr(), v.stride(0), ctx.data_ptr(), dctx.data_ptr(), ctx.stride(0),
                                           dq.data_ptr(), dk_.data_ptr(), dv.data_ptr(), _p(bias_table), _p(lut), rel_zero,
                                           num_buckets, int(causal), q_offset, lse.data_ptr(), _p(dbias_table), dropout_p, seed,
-                                          ws.data_ptr()))
+                                          _p(seed_ptr), ws.data_ptr()))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -394,8 +396,13 @@ def cast(x, dtype, out=None):
     return y
 
 
-def dropout_apply(x, p, seed):
+def dropout_apply(x, p, seed, seed_ptr=None):
     x = x.contiguous()
     y = torch.empty_like(x)
-    L.check(L.lib().klab_dropout_apply(_stream(), _DT[x.dtype], x.numel(), x.data_ptr(), y.data_ptr(), p, seed))
+    L.check(L.lib().klab_dropout_apply(_stream(), _DT[x.dtype], x.numel(), x.data_ptr(), y.data_ptr(), p, seed, _p(seed_ptr)))
     return y
+
+
+def seed_advance(counter: torch.Tensor) -> None:
+    """Step the device-side dropout counter (uint64 stored in an int64 tensor) once per training step."""
+    L.check(L.lib().klab_seed_advance(_stream(), counter.data_ptr()))

@@ -169,7 +169,9 @@ def test_norm_grouped_output():
 # ------------------------------------------------------------------------------------------------ T5 attention
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("mode,B,H,Lq,Lk,dk", [("enc", 2, 3, 13, 13, 64), ("dec", 2, 2, 9, 9, 64), ("cross", 2, 2, 7, 13, 64),
-                                               ("enc", 1, 2, 81, 81, 16), ("dec", 1, 1, 40, 40, 32)])
+                                               ("enc", 1, 2, 81, 81, 16), ("dec", 1, 1, 40, 40, 32),
+                                               ("enc", 2, 2, 96, 96, 64), ("enc", 1, 2, 176, 176, 64), ("dec", 2, 2, 130, 130, 64),
+                                               ("cross", 1, 2, 32, 200, 64), ("cross", 2, 1, 150, 96, 64), ("dec", 3, 2, 32, 32, 64)])
 def test_t5_attention(dtype, mode, B, H, Lq, Lk, dk):
     o = ops()
     dims = ot5.T5Dims(num_heads=H, d_kv=dk)
