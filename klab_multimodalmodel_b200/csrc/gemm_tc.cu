@@ -33,7 +33,7 @@ template <int BN> struct TileCfg {
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    void* __restrict__ D, long long ldd, int M, int N, int K, klab_gemm_epilogue epi) {
+                    void* __restrict__ D, long long ldd, int M, int N, int K, int splits, klab_gemm_epilogue epi) {
     using Cfg = TileCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -48,8 +48,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int lane = threadIdx.x & 31;
     const int num_m = (M + BM - 1) / BM;
     const int num_n = (N + BN - 1) / BN;
-    const int num_tiles = num_m * num_n;
     const int num_k = (K + BK - 1) / BK;
+    // split-K (wgrad of tall-skinny activations): a work item is (output tile, K range); partial tiles are reduced with
+    // fp32 red.global.add into a zero-initialised (or accumulating) D
+    const int kps = (num_k + splits - 1) / splits;
+    const int num_tiles = num_m * num_n * splits;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
@@ -78,10 +81,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+                const int tile = item / splits, split = item - tile * splits;
                 const int m0 = (tile / num_n) * BM;
                 const int n0 = (tile % num_n) * BN;
-                for (int kb = 0; kb < num_k; ++kb) {
+                const int kb0 = split * kps, kb1 = min(num_k, kb0 + kps);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + A_TILE_BYTES;
@@ -113,11 +118,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+                const int split = item % splits;
+                const int kb0 = split * kps, kb1 = min(num_k, kb0 + kps);
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (int kb = 0; kb < num_k; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -128,7 +135,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                                  : umma_smem_desc_sw128(sa + k * 32, 16, 1024);
                         const uint64_t db = B_MN ? umma_smem_desc_sw128(sb + k * 2048, 8192, 1024)
                                                  : umma_smem_desc_sw128(sb + k * 32, 16, 1024);
-                        umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_bf16(d_tmem, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);           // frees the smem slot once these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -144,7 +151,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (dr.on && epi.dropout_seed_ptr) epi.dropout_seed += *epi.dropout_seed_ptr;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+            const int tile = item / splits;
             const int m0 = (tile / num_n) * BM;
             const int n0 = (tile % num_n) * BN;
             mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -159,10 +167,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const int col0 = n0 + c * 32;
                 const int nvalid = min(32, N - col0);
                 if (row < M && nvalid > 0) {
-                    float v[32];
+                    if (splits > 1) {
+                        float* dst = reinterpret_cast<float*>(D) + row * ldd + col0;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                    epilogue_apply_store<32>(epi, dr, v, row, col0, nvalid, N, D, ldd);
+                        for (int i = 0; i < 32; ++i)
+                            if (i < nvalid) atomicAdd(dst + i, __uint_as_float(r[i]) * epi.alpha);
+                    } else {
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                        epilogue_apply_store<32>(epi, dr, v, row, col0, nvalid, N, D, ldd);
+                    }
                 }
             }
             tc_fence_before();
@@ -200,8 +215,23 @@ int launch_cfg(cudaStream_t stream, int M, int N, int K, const void* A, long lon
         attr_set = true;
     }
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-    const int grid = tiles < sm_count() ? tiles : sm_count();
-    kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, D, ldd, M, N, K, epi);
+    const int num_k = (K + BK - 1) / BK;
+    int splits = 1;
+    const bool linear = epi.act == KLAB_ACT_NONE && !epi.bias && !epi.residual && !epi.aux_out && epi.dropout_p == 0.0f &&
+                        epi.out_dtype == KLAB_F32;
+    if (linear && A_MN && B_MN && tiles * 2 <= sm_count() && num_k >= 16) {
+        splits = (2 * sm_count() + tiles - 1) / tiles;
+        if (splits > num_k / 4) splits = num_k / 4;
+        const int kps = (num_k + splits - 1) / splits;
+        splits = (num_k + kps - 1) / kps;                 // no empty K ranges
+    }
+    if (splits > 1 && !epi.accumulate) {
+        if (ldd == N) KLAB_CHECK_CUDA(cudaMemsetAsync(D, 0, sizeof(float) * static_cast<size_t>(M) * N, stream));
+        else KLAB_CHECK_CUDA(cudaMemset2DAsync(D, sizeof(float) * ldd, 0, sizeof(float) * N, M, stream));
+    }
+    const int items = tiles * splits;
+    const int grid = items < sm_count() ? items : sm_count();
+    kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, D, ldd, M, N, K, splits, epi);
     KLAB_LAUNCH_CHECK();
     count_launch();
     return KLAB_OK;
@@ -217,7 +247,8 @@ int launch_major(cudaStream_t stream, int M, int N, int K, const void* A, long l
 }
 
 // Pick the N tile: maximise (wave efficiency) x (per-tile efficiency: wider tiles amortise smem reads).
-int pick_bn(int M, int N) {
+int pick_bn(int M, int N, bool split_k_candidate) {
+    if (split_k_candidate) return N > 128 ? 256 : (N > 64 ? 128 : 64);   // occupancy comes from the K split: keep tiles wide
     const int sms = sm_count();
     const int num_m = (M + BM - 1) / BM;
     const int cand[3] = {256, 128, 64};
@@ -245,7 +276,10 @@ int gemm_tc_launch(cudaStream_t stream, int M, int N, int K, const void* A, long
     KLAB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm(bf16): lda=%lld / ldb=%lld must be multiples of 8", lda, ldb);
     KLAB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
                  "gemm(bf16): operand base pointers must be 16-byte aligned");
-    switch (pick_bn(M, N)) {
+    const bool split_k_candidate = a_mn && b_mn && epi.act == KLAB_ACT_NONE && !epi.bias && !epi.residual && !epi.aux_out &&
+                                   epi.dropout_p == 0.0f && epi.out_dtype == KLAB_F32 && K >= 16 * BK &&
+                                   ((M + BM - 1) / BM) * ((N + 255) / 256) * 2 <= sm_count();
+    switch (pick_bn(M, N, split_k_candidate)) {
         case 256: return launch_major<256>(stream, M, N, K, A, lda, a_mn, B, ldb, b_mn, D, ldd, epi);
         case 128: return launch_major<128>(stream, M, N, K, A, lda, a_mn, B, ldb, b_mn, D, ldd, epi);
         default: return launch_major<64>(stream, M, N, K, A, lda, a_mn, B, ldb, b_mn, D, ldd, epi);

@@ -25,7 +25,169 @@ struct RowMap {
 };
 
 constexpr int WARPS = 4;
+constexpr int VEC = 4;            // elements per lane per step on the vector path (8 B of bf16 / 16 B of fp32)
+constexpr int MAXV = 8;           // vector path covers d <= 32 * VEC * MAXV = 1024 with d % 128 == 0
 
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+        const float4 q = *reinterpret_cast<const float4*>(p);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct Vec4<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[4]) {
+        const uint2 q = *reinterpret_cast<const uint2*>(p);
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.x));
+        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.y));
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[4]) {
+        uint2 q;
+        *reinterpret_cast<__nv_bfloat162*>(&q.x) = __floats2bfloat162_rn(v[0], v[1]);
+        *reinterpret_cast<__nv_bfloat162*>(&q.y) = __floats2bfloat162_rn(v[2], v[3]);
+        *reinterpret_cast<uint2*>(p) = q;
+    }
+};
+
+// ---- vector path: the whole row lives in registers (one HBM read), d % 128 == 0, d <= 1024, 8/16-byte aligned rows ----
+template <typename T, bool IS_LN, int NV>
+__global__ void __launch_bounds__(WARPS * 32)
+norm_fwd_vec_kernel(const T* __restrict__ x, RowMap xm, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    const T* __restrict__ residual, RowMap rm, T* __restrict__ y, RowMap ym, float* __restrict__ mean_out,
+                    float* __restrict__ rstd_out, long long rows, int d, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long long row = static_cast<long long>(blockIdx.x) * WARPS + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const T* xr = x + xm.off(row);
+    float v[NV][4];
+    float s = 0.0f, ss = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        Vec4<T>::load(xr + (k * 32 + lane) * VEC, v[k]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { s += v[k][t]; ss += v[k][t] * v[k][t]; }
+    }
+    float mean = 0.0f, var;
+    if (IS_LN) {
+        mean = warp_sum(s) / d;
+        float sv = 0.0f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { const float c = v[k][t] - mean; sv += c * c; }
+        var = warp_sum(sv) / d;
+    } else {
+        var = warp_sum(ss) / d;
+    }
+    const float rstd = rsqrtf(var + eps);
+    if (lane == 0) {
+        if (mean_out) mean_out[row] = mean;
+        if (rstd_out) rstd_out[row] = rstd;
+    }
+    T* yr = y + ym.off(row);
+    const T* rr = residual ? residual + rm.off(row) : nullptr;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int c0 = (k * 32 + lane) * VEC;
+        const float4 g = *reinterpret_cast<const float4*>(gamma + c0);
+        float o[4] = {(v[k][0] - mean) * rstd * g.x, (v[k][1] - mean) * rstd * g.y, (v[k][2] - mean) * rstd * g.z, (v[k][3] - mean) * rstd * g.w};
+        if (IS_LN) {
+            const float4 b = *reinterpret_cast<const float4*>(beta + c0);
+            o[0] += b.x; o[1] += b.y; o[2] += b.z; o[3] += b.w;
+        }
+        if (rr) {
+            float r4[4];
+            Vec4<T>::load(rr + c0, r4);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) o[t] += r4[t];
+        }
+        Vec4<T>::store(yr + c0, o);
+    }
+}
+
+template <typename T, bool IS_LN, int NV>
+__global__ void __launch_bounds__(WARPS * 32)
+norm_bwd_vec_kernel(const T* __restrict__ dy, RowMap dym, const T* __restrict__ x, RowMap xm, const float* __restrict__ gamma,
+                    const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const T* __restrict__ dres, RowMap drm,
+                    T* __restrict__ dx, RowMap dxm, float* __restrict__ part_dgamma, float* __restrict__ part_dbeta,
+                    long long rows, int d) {
+    extern __shared__ float sm[];          // [WARPS][d] dgamma (, [WARPS][d] dbeta)
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float g4[NV][4], ag[NV][4], ab[NV][4];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma + (k * 32 + lane) * VEC);
+        g4[k][0] = g.x; g4[k][1] = g.y; g4[k][2] = g.z; g4[k][3] = g.w;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { ag[k][t] = 0.0f; ab[k][t] = 0.0f; }
+    }
+    for (long long row = static_cast<long long>(blockIdx.x) * WARPS + warp; row < rows;
+         row += static_cast<long long>(gridDim.x) * WARPS) {
+        const T* dyr = dy + dym.off(row);
+        const T* xr = x + xm.off(row);
+        const float mean = IS_LN ? mean_in[row] : 0.0f;
+        const float rstd = rstd_in[row];
+        float dv[NV][4], xh[NV][4];
+        float sg = 0.0f, sgx = 0.0f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int c0 = (k * 32 + lane) * VEC;
+            Vec4<T>::load(dyr + c0, dv[k]);
+            Vec4<T>::load(xr + c0, xh[k]);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                xh[k][t] = (xh[k][t] - mean) * rstd;
+                const float g = dv[k][t] * g4[k][t];
+                sg += g;
+                sgx += g * xh[k][t];
+                ag[k][t] += dv[k][t] * xh[k][t];
+                if (IS_LN) ab[k][t] += dv[k][t];
+            }
+        }
+        sg = IS_LN ? warp_sum(sg) / d : 0.0f;
+        sgx = warp_sum(sgx) / d;
+        T* dxr = dx + dxm.off(row);
+        const T* drr = dres ? dres + drm.off(row) : nullptr;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int c0 = (k * 32 + lane) * VEC;
+            float o[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) o[t] = rstd * (dv[k][t] * g4[k][t] - sg - xh[k][t] * sgx);
+            if (drr) {
+                float r4[4];
+                Vec4<T>::load(drr + c0, r4);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) o[t] += r4[t];
+            }
+            Vec4<T>::store(dxr + c0, o);
+        }
+    }
+    // combine the 4 warps' register partials through shared memory, one row of partials per CTA
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            sm[warp * d + (k * 32 + lane) * VEC + t] = ag[k][t];
+            if (IS_LN) sm[(WARPS + warp) * d + (k * 32 + lane) * VEC + t] = ab[k][t];
+        }
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        float a = 0.0f, b = 0.0f;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) {
+            a += sm[w * d + c];
+            if (IS_LN) b += sm[(WARPS + w) * d + c];
+        }
+        part_dgamma[static_cast<long long>(blockIdx.x) * d + c] = a;
+        if (IS_LN) part_dbeta[static_cast<long long>(blockIdx.x) * d + c] = b;
+    }
+}
+
+// ---- generic path (any d, any alignment) ----
 template <typename T, bool IS_LN>
 __global__ void __launch_bounds__(WARPS * 32)
 norm_fwd_kernel(const T* __restrict__ x, RowMap xm, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -46,7 +208,6 @@ norm_fwd_kernel(const T* __restrict__ x, RowMap xm, const float* __restrict__ ga
     float mean = 0.0f, var;
     if (IS_LN) {
         mean = s / d;
-        // two-pass variance for accuracy (matches aten native_layer_norm to fp32 rounding)
         float sv = 0.0f;
         for (int c = lane; c < d; c += 32) {
             const float v = to_f32(xr[c]) - mean;
@@ -71,8 +232,6 @@ norm_fwd_kernel(const T* __restrict__ x, RowMap xm, const float* __restrict__ ga
     }
 }
 
-// dx = rstd * (g - mean(g) [LN only] - xhat * mean(g * xhat)) (+ dres),   g = dy * gamma
-// partial dgamma / dbeta: per-CTA column sums written to workspace [gridDim.x, d] (reduced by colsum_finalize).
 template <typename T, bool IS_LN>
 __global__ void __launch_bounds__(WARPS * 32)
 norm_bwd_kernel(const T* __restrict__ dy, RowMap dym, const T* __restrict__ x, RowMap xm, const float* __restrict__ gamma,
@@ -120,16 +279,28 @@ norm_bwd_kernel(const T* __restrict__ dy, RowMap dym, const T* __restrict__ x, R
     }
 }
 
-// out[c] (+)= sum_p part[p, c]
-__global__ void colsum_finalize_kernel(const float* __restrict__ part, int nparts, int d, float* __restrict__ out, int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= d) return;
+// out[a][c] (+)= sum_p part[a][p, c] for a in {0 (, 1)}: blockDim = (32 cols, 8 part lanes), grid = (ceil(d/32), arrays)
+__global__ void __launch_bounds__(256)
+colsum_finalize_kernel(const float* __restrict__ part0, const float* __restrict__ part1, int nparts, int d, float* __restrict__ out0,
+                       float* __restrict__ out1, int accumulate) {
+    __shared__ float red[8][33];
+    const float* part = blockIdx.y ? part1 : part0;
+    float* out = blockIdx.y ? out1 : out0;
+    const int c = blockIdx.x * 32 + threadIdx.x;
     float s = 0.0f;
-    for (int p = 0; p < nparts; ++p) s += part[static_cast<long long>(p) * d + c];
-    out[c] = accumulate ? out[c] + s : s;
+    if (c < d)
+        for (int p = threadIdx.y; p < nparts; p += 8) s += part[static_cast<long long>(p) * d + c];
+    red[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < d) {
+        float t = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+        out[c] = accumulate ? out[c] + t : t;
+    }
 }
 
-// Column sums of a [rows, d] matrix (bias gradients): partial[gridDim.x, d]
+// Column sums of a [rows, d] matrix (bias gradients): partial[gridDim.y, d]
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const T* __restrict__ x, long long ld, long long rows, int d, float* __restrict__ part) {
@@ -150,13 +321,34 @@ colsum_partial_kernel(const T* __restrict__ x, long long ld, long long rows, int
     }
 }
 
+template <typename T>
+bool vec_ok(const void* a, long long lda, const void* b, long long ldb, const void* c, long long ldc, const void* e, long long lde,
+            const RowMap& m1, const RowMap& m2, int d) {
+    if (d % 128 != 0 || d > 32 * VEC * MAXV) return false;
+    const uintptr_t mask = sizeof(T) * VEC - 1;
+    auto ok = [&](const void* p, long long ld) { return p == nullptr || ((reinterpret_cast<uintptr_t>(p) & mask) == 0 && ld % VEC == 0); };
+    return ok(a, lda) && ok(b, ldb) && ok(c, ldc) && ok(e, lde) && m1.group_stride % VEC == 0 && m2.group_stride % VEC == 0;
+}
+
 template <typename T, bool IS_LN>
 int norm_fwd_t(cudaStream_t st, const void* x, RowMap xm, const float* gamma, const float* beta, const void* res, RowMap rm,
                void* y, RowMap ym, float* mean, float* rstd, long long rows, int d, float eps) {
     const unsigned grid = static_cast<unsigned>((rows + WARPS - 1) / WARPS);
-    norm_fwd_kernel<T, IS_LN><<<grid, WARPS * 32, 0, st>>>(reinterpret_cast<const T*>(x), xm, gamma, beta,
-                                                           reinterpret_cast<const T*>(res), rm, reinterpret_cast<T*>(y), ym,
-                                                           mean, rstd, rows, d, eps);
+#define KLAB_NORM_FWD_ARGS reinterpret_cast<const T*>(x), xm, gamma, beta, reinterpret_cast<const T*>(res), rm, reinterpret_cast<T*>(y), ym, mean, rstd, rows, d, eps
+    if (vec_ok<T>(x, xm.ld, res, rm.ld, y, ym.ld, nullptr, 0, xm, ym, d)) {
+        switch (d / 128) {
+            case 1: norm_fwd_vec_kernel<T, IS_LN, 1><<<grid, WARPS * 32, 0, st>>>(KLAB_NORM_FWD_ARGS); break;
+            case 2: norm_fwd_vec_kernel<T, IS_LN, 2><<<grid, WARPS * 32, 0, st>>>(KLAB_NORM_FWD_ARGS); break;
+            case 3: norm_fwd_vec_kernel<T, IS_LN, 3><<<grid, WARPS * 32, 0, st>>>(KLAB_NORM_FWD_ARGS); break;
+            case 4: norm_fwd_vec_kernel<T, IS_LN, 4><<<grid, WARPS * 32, 0, st>>>(KLAB_NORM_FWD_ARGS); break;
+            case 6: norm_fwd_vec_kernel<T, IS_LN, 6><<<grid, WARPS * 32, 0, st>>>(KLAB_NORM_FWD_ARGS); break;
+            case 8: norm_fwd_vec_kernel<T, IS_LN, 8><<<grid, WARPS * 32, 0, st>>>(KLAB_NORM_FWD_ARGS); break;
+            default: norm_fwd_kernel<T, IS_LN><<<grid, WARPS * 32, 0, st>>>(KLAB_NORM_FWD_ARGS); break;
+        }
+    } else {
+        norm_fwd_kernel<T, IS_LN><<<grid, WARPS * 32, 0, st>>>(KLAB_NORM_FWD_ARGS);
+    }
+#undef KLAB_NORM_FWD_ARGS
     KLAB_LAUNCH_CHECK();
     count_launch();
     return KLAB_OK;
@@ -171,18 +363,27 @@ int norm_bwd_t(cudaStream_t st, const void* dy, RowMap dym, const void* x, RowMa
     if (grid > cap) grid = cap;
     float* part_dg = workspace;
     float* part_db = workspace + static_cast<long long>(grid) * d;
-    const size_t smem = (IS_LN ? 2 : 1) * d * sizeof(float);
-    norm_bwd_kernel<T, IS_LN><<<grid, WARPS * 32, smem, st>>>(
-        reinterpret_cast<const T*>(dy), dym, reinterpret_cast<const T*>(x), xm, gamma, mean, rstd,
-        reinterpret_cast<const T*>(dres), drm, reinterpret_cast<T*>(dx), dxm, part_dg, part_db, rows, d);
-    KLAB_LAUNCH_CHECK();
-    colsum_finalize_kernel<<<(d + 127) / 128, 128, 0, st>>>(part_dg, grid, d, dgamma, accumulate);
-    KLAB_LAUNCH_CHECK();
-    if (IS_LN) {
-        colsum_finalize_kernel<<<(d + 127) / 128, 128, 0, st>>>(part_db, grid, d, dbeta, accumulate);
-        KLAB_LAUNCH_CHECK();
+#define KLAB_NORM_BWD_ARGS reinterpret_cast<const T*>(dy), dym, reinterpret_cast<const T*>(x), xm, gamma, mean, rstd, reinterpret_cast<const T*>(dres), drm, reinterpret_cast<T*>(dx), dxm, part_dg, part_db, rows, d
+    const bool vec = vec_ok<T>(dy, dym.ld, x, xm.ld, dres, drm.ld, dx, dxm.ld, dym, xm, d) && (d / 128 <= 4 || d / 128 == 6 || d / 128 == 8);
+    if (vec) {
+        const size_t smem = (IS_LN ? 2 : 1) * WARPS * d * sizeof(float);
+        switch (d / 128) {
+            case 1: norm_bwd_vec_kernel<T, IS_LN, 1><<<grid, WARPS * 32, smem, st>>>(KLAB_NORM_BWD_ARGS); break;
+            case 2: norm_bwd_vec_kernel<T, IS_LN, 2><<<grid, WARPS * 32, smem, st>>>(KLAB_NORM_BWD_ARGS); break;
+            case 3: norm_bwd_vec_kernel<T, IS_LN, 3><<<grid, WARPS * 32, smem, st>>>(KLAB_NORM_BWD_ARGS); break;
+            case 4: norm_bwd_vec_kernel<T, IS_LN, 4><<<grid, WARPS * 32, smem, st>>>(KLAB_NORM_BWD_ARGS); break;
+            case 6: norm_bwd_vec_kernel<T, IS_LN, 6><<<grid, WARPS * 32, smem, st>>>(KLAB_NORM_BWD_ARGS); break;
+            default: norm_bwd_vec_kernel<T, IS_LN, 8><<<grid, WARPS * 32, smem, st>>>(KLAB_NORM_BWD_ARGS); break;
+        }
+    } else {
+        const size_t smem = (IS_LN ? 2 : 1) * d * sizeof(float);
+        norm_bwd_kernel<T, IS_LN><<<grid, WARPS * 32, smem, st>>>(KLAB_NORM_BWD_ARGS);
     }
-    count_launch(IS_LN ? 3 : 2);
+#undef KLAB_NORM_BWD_ARGS
+    KLAB_LAUNCH_CHECK();
+    colsum_finalize_kernel<<<dim3((d + 31) / 32, IS_LN ? 2 : 1), dim3(32, 8), 0, st>>>(part_dg, part_db, grid, d, dgamma, dbeta, accumulate);
+    KLAB_LAUNCH_CHECK();
+    count_launch(2);
     return KLAB_OK;
 }
 
@@ -272,7 +473,7 @@ int klab_colsum(void* stream, int dtype, long long rows, int d, const void* x, l
     else
         colsum_partial_kernel<float><<<grid, block, 0, st>>>(reinterpret_cast<const float*>(x), ldx, rows, d, part);
     KLAB_LAUNCH_CHECK();
-    colsum_finalize_kernel<<<(d + 127) / 128, 128, 0, st>>>(part, static_cast<int>(chunks), d, out, accumulate);
+    colsum_finalize_kernel<<<dim3((d + 31) / 32, 1), dim3(32, 8), 0, st>>>(part, nullptr, static_cast<int>(chunks), d, out, nullptr, accumulate);
     KLAB_LAUNCH_CHECK();
     count_launch(2);
     return KLAB_OK;

@@ -336,13 +336,15 @@ __global__ void cpb_bwd_w2_kernel(const float* __restrict__ dtab, const float* _
 }
 
 // dhidden[t,u] = [hidden > 0] sum_h dtab[t,h] W2[h,u];  dW1[u,:] = sum_t dhidden[t,u] coords[t,:];  db1[u] = sum_t dhidden[t,u]
-__global__ void cpb_bwd_w1_kernel(const float* __restrict__ dtab, const float* __restrict__ hidden, const float* __restrict__ w2,
-                                  const float* __restrict__ coords, int Tn, int U, int heads, float* __restrict__ dw1,
-                                  float* __restrict__ db1, int accumulate) {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= U) return;
+// one CTA per hidden unit u, threads over table rows t
+__global__ void __launch_bounds__(128)
+cpb_bwd_w1_kernel(const float* __restrict__ dtab, const float* __restrict__ hidden, const float* __restrict__ w2,
+                  const float* __restrict__ coords, int Tn, int U, int heads, float* __restrict__ dw1,
+                  float* __restrict__ db1, int accumulate) {
+    __shared__ float red[3][4];
+    const int u = blockIdx.x;
     float g0 = 0.0f, g1 = 0.0f, gb = 0.0f;
-    for (int t = 0; t < Tn; ++t) {
+    for (int t = threadIdx.x; t < Tn; t += blockDim.x) {
         if (hidden[static_cast<long long>(t) * U + u] > 0.0f) {
             float dh = 0.0f;
             for (int h = 0; h < heads; ++h) dh = fmaf(dtab[t * heads + h], w2[static_cast<long long>(h) * U + u], dh);
@@ -351,10 +353,18 @@ __global__ void cpb_bwd_w1_kernel(const float* __restrict__ dtab, const float* _
             gb += dh;
         }
     }
-    if (accumulate) {
-        dw1[2 * u] += g0; dw1[2 * u + 1] += g1; db1[u] += gb;
-    } else {
-        dw1[2 * u] = g0; dw1[2 * u + 1] = g1; db1[u] = gb;
+    g0 = warp_sum(g0); g1 = warp_sum(g1); gb = warp_sum(gb);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = g0; red[1][threadIdx.x >> 5] = g1; red[2][threadIdx.x >> 5] = gb; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        g0 = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+        g1 = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+        gb = red[2][0] + red[2][1] + red[2][2] + red[2][3];
+        if (accumulate) {
+            dw1[2 * u] += g0; dw1[2 * u + 1] += g1; db1[u] += gb;
+        } else {
+            dw1[2 * u] = g0; dw1[2 * u + 1] = g1; db1[u] = gb;
+        }
     }
 }
 
@@ -458,7 +468,7 @@ int klab_swin_cpb_bwd(void* stream, int table_rows, int hidden_units, int heads,
     KLAB_LAUNCH_CHECK();
     cpb_bwd_w2_kernel<<<(heads * hidden_units + 127) / 128, 128, 0, st>>>(dtab, hidden, table_rows, hidden_units, heads, dw2, accumulate);
     KLAB_LAUNCH_CHECK();
-    cpb_bwd_w1_kernel<<<(hidden_units + 127) / 128, 128, 0, st>>>(dtab, hidden, w2, coords, table_rows, hidden_units, heads, dw1, db1, accumulate);
+    cpb_bwd_w1_kernel<<<hidden_units, 128, 0, st>>>(dtab, hidden, w2, coords, table_rows, hidden_units, heads, dw1, db1, accumulate);
     KLAB_LAUNCH_CHECK();
     count_launch(3);
     return KLAB_OK;
