@@ -9,6 +9,8 @@
 //   * cosine attention (:444-449): S = normalize(q) normalize(k)^T * exp(min(logit_scale, ln 100));
 //   * bias (:450-460): 16 * sigmoid(MLP(coords)[index]) precomputed once per block per step by cpb kernels.
 // CUDA-core fp32 arithmetic, any window size / head dim; the bf16 hot path is swin_attention_tc.cu.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace klab {
@@ -374,9 +376,27 @@ size_t swin_bwd_smem(int N, int d) {
 }
 
 }  // namespace
+
+// tensor-core path (swin_attention_tc.cu)
+bool swin_attention_tc_supported(int dtype, int head_dim, int window, long long ld, long long ldc, const void* q, const void* k,
+                                 const void* v, const void* ctx);
+int swin_attention_fwd_tc(cudaStream_t st, int B, int res, int heads, int window, int shift, const void* q, const void* k, const void* v,
+                          long long ld, void* ctx, long long ldc, const float* logit_scale, const float* bias, float* lse);
+int swin_attention_bwd_tc(cudaStream_t st, int B, int res, int heads, int window, int shift, const void* q, const void* k, const void* v,
+                          long long ld, const void* ctx, const void* dctx, long long ldc, void* dq, void* dk, void* dv,
+                          const float* logit_scale, const float* bias, const float* lse, float* dbias, float* dlogit_scale);
 }  // namespace klab
 
 using namespace klab;
+
+static bool swin_force_generic() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("KLAB_ATTENTION_GENERIC");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
 
 extern "C" {
 
@@ -386,6 +406,8 @@ int klab_swin_attention_fwd(void* stream, int dtype, int B, int res, int heads, 
     if (int rc = klab_check_device()) return rc;
     KLAB_REQUIRE(B > 0 && res > 0 && window > 0 && res % window == 0, "swin_attention_fwd: grid %d is not a multiple of window %d", res, window);
     KLAB_REQUIRE(head_dim <= 128, "swin_attention: head_dim %d > 128", head_dim);
+    if (!swin_force_generic() && swin_attention_tc_supported(dtype, head_dim, window, ld, ldc, q, k, v, ctx))
+        return swin_attention_fwd_tc(static_cast<cudaStream_t>(stream), B, res, heads, window, shift, q, k, v, ld, ctx, ldc, logit_scale, bias, lse);
     SwinArgs a{};
     a.q = q; a.k = k; a.v = v; a.out = ctx; a.ld = ld; a.ldc = ldc;
     a.B = B; a.res = res; a.heads = heads; a.d = head_dim; a.w = window; a.shift = shift;
@@ -415,6 +437,10 @@ int klab_swin_attention_bwd(void* stream, int dtype, int B, int res, int heads, 
     if (int rc = klab_check_device()) return rc;
     KLAB_REQUIRE(B > 0 && res > 0 && window > 0 && res % window == 0, "swin_attention_bwd: grid %d is not a multiple of window %d", res, window);
     KLAB_REQUIRE(head_dim <= 128, "swin_attention: head_dim %d > 128", head_dim);
+    if (!swin_force_generic() && swin_attention_tc_supported(dtype, head_dim, window, ld, ldc, q, k, v, ctx) &&
+        (reinterpret_cast<uintptr_t>(dctx) & 15) == 0)
+        return swin_attention_bwd_tc(static_cast<cudaStream_t>(stream), B, res, heads, window, shift, q, k, v, ld, ctx, dctx, ldc, dq, dk, dv,
+                                     logit_scale, bias, lse, dbias, dlogit_scale);
     SwinArgs a{};
     a.q = q; a.k = k; a.v = v; a.ctx = ctx; a.dctx = dctx; a.dq = dq; a.dk = dk; a.dv = dv; a.ld = ld; a.ldc = ldc;
     a.B = B; a.res = res; a.heads = heads; a.d = head_dim; a.w = window; a.shift = shift;

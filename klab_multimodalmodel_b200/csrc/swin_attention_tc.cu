@@ -1,0 +1,533 @@
+// K2 + K3 + K4 (hot path): Swin-V2 shifted-window cosine attention on the 5th-gen tensor cores, head_dim = 32, window <= 8x8.
+//
+// Same semantics as swin_attention.cu (HF/models/swinv2/modeling_swinv2.py:421-487 with window partition / cyclic roll /
+// shift mask folded into index math); this file moves the arithmetic onto tcgen05:
+//   * two windows share one 128-row UMMA tile (window slot g = row / 64); S = Qh Kh^T is computed for all 128 x 128 pairs and
+//     the cross-window half is simply never read; P of the other slot is written as zeros so O = P V needs no masking;
+//   * the token gather (roll + partition), the L2 normalisation of q and k (fp32) and the bf16 conversion happen while the
+//     operands are staged into 128B-swizzled shared memory -- q/k/v/ctx stay in natural token order in HBM;
+//   * S, P, dP, dS live in TMEM / shared memory only; backward keeps the bias gradient of all windows a CTA visits in shared
+//     memory and flushes it once (one atomicAdd per element per CTA instead of per window).
+// Limits: bf16, head_dim == 32, window*window <= 64 (7x7 and 8x8 of the BASELINE geometries); 12x12 windows (384^2 inputs)
+// and fp32 take the generic kernel.
+#include "tc_tiles.cuh"
+
+namespace klab {
+void count_launch(int n = 1);
+namespace {
+
+constexpr int HD = 32;
+constexpr int TILE = 128;
+constexpr int SLOT = 64;
+constexpr int TB = TILE * 128;                 // bytes of one [128 x 64] bf16 tile
+constexpr float LOGIT_MAX = 4.605170185988092f;
+constexpr float NORM_EPS = 1e-12f;
+
+struct SwinTcArgs {
+    const __nv_bfloat16 *q, *k, *v, *ctx, *dctx;
+    __nv_bfloat16 *out, *dq, *dk, *dv;
+    long long ld, ldc;
+    int B, res, heads, w, shift, N, nW;
+    const float* logit_scale;
+    const float* bias;
+    float* lse;
+    float* dbias;
+    float* dlogit_scale;
+};
+
+__device__ __forceinline__ int region_of(int y, int res, int w, int shift) { return y < res - w ? 0 : (y < res - shift ? 1 : 2); }
+
+// token row index and shift-mask region of token n of global window bw (-1 if the slot is padding)
+__device__ __forceinline__ int window_token(const SwinTcArgs& a, int bw, int n, int& region) {
+    region = 0;
+    if (n >= a.N || bw >= a.B * a.nW) return -1;
+    const int b = bw / a.nW, win = bw % a.nW;
+    const int nwx = a.res / a.w;
+    const int ys = (win / nwx) * a.w + n / a.w, xs = (win % nwx) * a.w + n % a.w;
+    int y = ys + a.shift, x = xs + a.shift;
+    if (y >= a.res) y -= a.res;
+    if (x >= a.res) x -= a.res;
+    if (a.shift > 0) region = region_of(ys, a.res, a.w, a.shift) * 3 + region_of(xs, a.res, a.w, a.shift);
+    return (b * a.res + y) * a.res + x;
+}
+
+// load one 32-element bf16 head slice (64 B) of a token row
+__device__ __forceinline__ void load_row32(const __nv_bfloat16* base, long long ld, int tok, int h, float* v) {
+    const uint4* p = reinterpret_cast<const uint4*>(base + static_cast<long long>(tok) * ld + h * HD);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) unpack8(p[c], v + 8 * c);
+}
+__device__ __forceinline__ void store_row32(__nv_bfloat16* base, long long ld, int tok, int h, const float* v) {
+    uint4* p = reinterpret_cast<uint4*>(base + static_cast<long long>(tok) * ld + h * HD);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) p[c] = pack8(v + 8 * c);
+}
+__device__ __forceinline__ void stage_row32(uint8_t* tile, int row, const float* v) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) st_tile8(tile, row, c, v + 8 * c);
+}
+// Stage a unit vector as bf16 hi (columns 0..31) + bf16 lo = v - hi (columns 32..63).  The cosine logits are multiplied by
+// up to 100 (logit_scale clamp) before the softmax, so S = Qh Kh^T is accumulated as hi*hi + lo*hi + hi*lo (three
+// K = 32 tcgen05 passes): ~16 mantissa bits on the operands instead of 8, at negligible cost for a K = 32 product.
+__device__ __forceinline__ void stage_row32_hilo(uint8_t* tile, int row, const float* v) {
+    float lo[HD];
+#pragma unroll
+    for (int c = 0; c < HD; ++c) lo[c] = v[c] - __bfloat162float(__float2bfloat16_rn(v[c]));
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        st_tile8(tile, row, c, v + 8 * c);
+        st_tile8(tile, row, 4 + c, lo + 8 * c);
+    }
+}
+// S[tmem] = Qhi Khi^T + Qlo Khi^T + Qhi Klo^T  (qa / ka: shared addresses of the hi|lo tiles)
+__device__ __forceinline__ void issue_cosine_logits(uint32_t tmem_s, uint32_t qa, uint32_t ka, uint32_t idesc) {
+#pragma unroll
+    for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t qo = pass == 1 ? 64 : 0, ko = pass == 2 ? 64 : 0;
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+            umma_bf16(tmem_s, umma_smem_desc_sw128(qa + qo + k * 32, 16, 1024), umma_smem_desc_sw128(ka + ko + k * 32, 16, 1024), idesc,
+                      (pass | k) != 0);
+    }
+}
+
+__device__ __forceinline__ float inv_norm32(const float* v, float& norm) {
+    float s = 0.0f;
+#pragma unroll
+    for (int c = 0; c < HD; ++c) s = fmaf(v[c], v[c], s);
+    norm = fmaxf(sqrtf(s), NORM_EPS);
+    return 1.0f / norm;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// forward: grid (ceil(B*nW / 2), heads), 128 threads; thread t = row t = (slot t/64, token t%64)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) swin_attn_fwd_tc_kernel(SwinTcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + TB;
+    uint8_t* sV = sK + TB;
+    uint8_t* sP = sV + TB;                               // 2 key blocks of 64
+    int* sreg = reinterpret_cast<int*>(sP + 2 * TB);     // [128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sreg + TILE);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, h = blockIdx.y;
+    const int g = tid >> 6, n = tid & 63;
+    const int bw = blockIdx.x * 2 + g;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tmem_alloc(tmem_ptr, 256);
+        tmem_relinquish();
+    }
+    int region;
+    const int tok = window_token(a, bw, n, region);
+    sreg[tid] = region;
+    {
+        float q[HD], k[HD], v[HD];
+        if (tok >= 0) {
+            load_row32(a.q, a.ld, tok, h, q);
+            load_row32(a.k, a.ld, tok, h, k);
+            load_row32(a.v, a.ld, tok, h, v);
+            float nq, nk;
+            const float iq = inv_norm32(q, nq), ik = inv_norm32(k, nk);
+#pragma unroll
+            for (int c = 0; c < HD; ++c) { q[c] *= iq; k[c] *= ik; }
+        } else {
+#pragma unroll
+            for (int c = 0; c < HD; ++c) { q[c] = 0.0f; k[c] = 0.0f; v[c] = 0.0f; }
+        }
+        stage_row32_hilo(sQ, tid, q);
+        stage_row32_hilo(sK, tid, k);
+        stage_row32(sV, tid, v);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+    constexpr int O_COL = 128;
+
+    if (tid == 0) {
+        issue_cosine_logits(tmem, smem_u32(sQ), smem_u32(sK), umma_idesc_bf16(TILE, TILE, false, false));
+        umma_commit(&bars[0]);
+    }
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+
+    const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const float scale = __expf(fminf(a.logit_scale[h], LOGIT_MAX));
+    const float* brow = a.bias + (static_cast<long long>(h) * a.N + (tok >= 0 ? n : 0)) * a.N;
+    const int N = a.N;
+    float sv[SLOT];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int c0 = 0; c0 < SLOT; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(trow + g * SLOT + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+            const int j = c0 + t;
+            float s = -INFINITY;
+            if (tok >= 0 && j < N) {
+                s = __uint_as_float(r[t]) * scale + brow[j];
+                if (sreg[g * SLOT + j] != region) s += -200.0f;
+                mx = fmaxf(mx, s);
+            }
+            sv[j] = s;
+        }
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int j = 0; j < SLOT; ++j) {
+        const float e = (tok >= 0 && j < N) ? __expf(sv[j] - mx) : 0.0f;
+        sv[j] = e;
+        sum += e;
+    }
+    // own slot's 64 keys -> key block g; the other slot's keys -> zeros
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        st_tile8(sP + g * TB, tid, c, sv + 8 * c);
+        st_tile8_raw(sP + (1 - g) * TB, tid, c, make_uint4(0, 0, 0, 0));
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+        const uint32_t idesc = umma_idesc_bf16(TILE, HD, false, true);
+        const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
+#pragma unroll
+        for (int ks = 0; ks < TILE / 16; ++ks)
+            umma_bf16(tmem + O_COL, umma_smem_desc_sw128(pa + (ks >> 2) * TB + (ks & 3) * 32, 16, 1024),
+                      umma_smem_desc_sw128(va + ks * 2048, 8192, 1024), idesc, ks != 0);
+        umma_commit(&bars[1]);
+    }
+    mbar_wait(&bars[1], 0);
+    tc_fence_after();
+    {
+        uint32_t r[32];
+        tmem_ld_32x32(trow + O_COL, r);
+        tmem_ld_wait();
+        if (tok >= 0) {
+            const float inv = 1.0f / sum;
+            float o[HD];
+#pragma unroll
+            for (int c = 0; c < HD; ++c) o[c] = __uint_as_float(r[c]) * inv;
+            store_row32(a.out, a.ldc, tok, h, o);
+            a.lse[(static_cast<long long>(bw) * a.heads + h) * N + n] = mx + __logf(sum);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 256);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// backward: grid (nchunks, heads), 128 threads; the CTA walks window pairs pair = blockIdx.x, blockIdx.x + nchunks, ...
+// TMEM: S 0..127 | dP 128..255 | dV 256..287 | dK 288..351 | dQ 352..415
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) swin_attn_bwd_tc_kernel(SwinTcArgs a, int npairs) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + TB;
+    uint8_t* sV = sK + TB;
+    uint8_t* sdO = sV + TB;
+    uint8_t* sP = sdO + TB;
+    uint8_t* sdS = sP + 2 * TB;
+    uint8_t* sdSl = sdS + 2 * TB;                                  // low-order bf16 part of dS
+    float* dbias_s = reinterpret_cast<float*>(sdSl + 2 * TB);      // [2 slots][N][N]
+    const int N = a.N;
+    int* sreg = reinterpret_cast<int*>(dbias_s + 2 * N * N);
+    float* red = reinterpret_cast<float*>(sreg + TILE);            // [4]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 4);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
+    constexpr int TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 288, TM_DQ = 352;      // dK / dQ: 64 columns ([hi | lo] of B)
+
+    const int tid = threadIdx.x, warp = tid >> 5, h = blockIdx.y;
+    const int g = tid >> 6, n = tid & 63;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tmem_alloc(tmem_ptr, 512);
+        tmem_relinquish();
+    }
+    for (int idx = tid; idx < 2 * N * N; idx += blockDim.x) dbias_s[idx] = 0.0f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+    const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const float raw_ls = a.logit_scale[h];
+    const float scale = __expf(fminf(raw_ls, LOGIT_MAX));
+    const uint32_t id_s = umma_idesc_bf16(TILE, TILE, false, false);   // S / dP
+    const uint32_t id_t = umma_idesc_bf16(TILE, HD, true, true);       // dV / dK : A = P^T (MN-major), B MN-major
+    const uint32_t id_q = umma_idesc_bf16(TILE, HD, false, true);      // dQ      : A = dS (K-major), B = Kh MN-major
+    const uint32_t id_t64 = umma_idesc_bf16(TILE, 2 * HD, true, true);
+    const uint32_t id_q64 = umma_idesc_bf16(TILE, 2 * HD, false, true);
+    float dscale_acc = 0.0f;
+    uint32_t phase = 0;
+
+    for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+        const int bw = pair * 2 + g;
+        int region;
+        const int tok = window_token(a, bw, n, region);
+        float qn = 1.0f, kn = 1.0f, Di = 0.0f, lse = 0.0f;
+        {
+            float q[HD], k[HD], v[HD], go[HD];
+            if (tok >= 0) {
+                load_row32(a.q, a.ld, tok, h, q);
+                load_row32(a.k, a.ld, tok, h, k);
+                load_row32(a.v, a.ld, tok, h, v);
+                load_row32(a.dctx, a.ldc, tok, h, go);
+                float o[HD];
+                load_row32(a.ctx, a.ldc, tok, h, o);
+#pragma unroll
+                for (int c = 0; c < HD; ++c) Di = fmaf(go[c], o[c], Di);
+                const float iq = inv_norm32(q, qn), ik = inv_norm32(k, kn);
+#pragma unroll
+                for (int c = 0; c < HD; ++c) { q[c] *= iq; k[c] *= ik; }
+                lse = a.lse[(static_cast<long long>(bw) * a.heads + h) * N + n];
+            } else {
+#pragma unroll
+                for (int c = 0; c < HD; ++c) { q[c] = 0.0f; k[c] = 0.0f; v[c] = 0.0f; go[c] = 0.0f; }
+            }
+            stage_row32_hilo(sQ, tid, q);
+            stage_row32_hilo(sK, tid, k);
+            stage_row32(sV, tid, v);
+            stage_row32(sdO, tid, go);
+        }
+        sreg[tid] = region;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (tid == 0) {
+            const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK), va = smem_u32(sV), doa = smem_u32(sdO);
+            issue_cosine_logits(tmem + TM_S, qa, ka, id_s);
+#pragma unroll
+            for (int k = 0; k < HD / 16; ++k)
+                umma_bf16(tmem + TM_DP, umma_smem_desc_sw128(doa + k * 32, 16, 1024), umma_smem_desc_sw128(va + k * 32, 16, 1024), id_s, k != 0);
+            umma_commit(&bars[0]);
+        }
+        mbar_wait(&bars[0], phase);
+        phase ^= 1;
+        tc_fence_after();
+
+        const float* brow = a.bias + (static_cast<long long>(h) * N + (tok >= 0 ? n : 0)) * N;
+        float* dbrow = dbias_s + (static_cast<long long>(g) * N + (tok >= 0 ? n : 0)) * N;
+#pragma unroll
+        for (int c0 = 0; c0 < SLOT; c0 += 32) {
+            uint32_t rs[32], rp[32];
+            tmem_ld_32x32(trow + TM_S + g * SLOT + c0, rs);
+            tmem_ld_32x32(trow + TM_DP + g * SLOT + c0, rp);
+            tmem_ld_wait();
+            float pv[32], dsv[32];
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+                const int j = c0 + t;
+                float p = 0.0f, ds = 0.0f;
+                if (tok >= 0 && j < N) {
+                    const float cs = __uint_as_float(rs[t]);
+                    float s = cs * scale + brow[j];
+                    if (sreg[g * SLOT + j] != region) s += -200.0f;
+                    p = __expf(s - lse);
+                    ds = p * (__uint_as_float(rp[t]) - Di);
+                    dbrow[j] += ds;                       // row (slot g, token n) is owned by this thread: no race
+                    dscale_acc = fmaf(ds, cs, dscale_acc);
+                }
+                pv[t] = p;
+                dsv[t] = ds;
+            }
+            float dlo[32];                                   // dS = hi + lo (both bf16): see the dQ / dK passes below
+#pragma unroll
+            for (int t = 0; t < 32; ++t) dlo[t] = dsv[t] - __bfloat162float(__float2bfloat16_rn(dsv[t]));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                st_tile8(sP + g * TB, tid, (c0 >> 3) + c, pv + 8 * c);
+                st_tile8(sdS + g * TB, tid, (c0 >> 3) + c, dsv + 8 * c);
+                st_tile8(sdSl + g * TB, tid, (c0 >> 3) + c, dlo + 8 * c);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            st_tile8_raw(sP + (1 - g) * TB, tid, c, make_uint4(0, 0, 0, 0));
+            st_tile8_raw(sdS + (1 - g) * TB, tid, c, make_uint4(0, 0, 0, 0));
+            st_tile8_raw(sdSl + (1 - g) * TB, tid, c, make_uint4(0, 0, 0, 0));
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (tid == 0) {
+            const uint32_t pa = smem_u32(sP), dsa = smem_u32(sdS), dla = smem_u32(sdSl);
+            const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK), doa = smem_u32(sdO);
+            // dV = P^T dO.  dK = dS^T Qh and dQ = dS Kh at ~16-bit operand precision (their results go through the
+            // cancelling normalisation backward): the B operand covers the [hi | lo] halves of Qh / Kh (N = 64, columns
+            // c and 32 + c are summed in the epilogue) and a second pass adds dS_lo x hi.
+#pragma unroll
+            for (int ks = 0; ks < TILE / 16; ++ks) {
+                umma_bf16(tmem + TM_DV, umma_smem_desc_sw128(pa + ks * 2048, TB, 1024), umma_smem_desc_sw128(doa + ks * 2048, 8192, 1024), id_t, ks != 0);
+                umma_bf16(tmem + TM_DK, umma_smem_desc_sw128(dsa + ks * 2048, TB, 1024), umma_smem_desc_sw128(qa + ks * 2048, 8192, 1024), id_t64, ks != 0);
+                umma_bf16(tmem + TM_DQ, umma_smem_desc_sw128(dsa + (ks >> 2) * TB + (ks & 3) * 32, 16, 1024),
+                          umma_smem_desc_sw128(ka + ks * 2048, 8192, 1024), id_q64, ks != 0);
+            }
+#pragma unroll
+            for (int ks = 0; ks < TILE / 16; ++ks) {
+                umma_bf16(tmem + TM_DK, umma_smem_desc_sw128(dla + ks * 2048, TB, 1024), umma_smem_desc_sw128(qa + ks * 2048, 8192, 1024), id_t, 1u);
+                umma_bf16(tmem + TM_DQ, umma_smem_desc_sw128(dla + (ks >> 2) * TB + (ks & 3) * 32, 16, 1024),
+                          umma_smem_desc_sw128(ka + ks * 2048, 8192, 1024), id_q, 1u);
+            }
+            umma_commit(&bars[0]);
+        }
+        mbar_wait(&bars[0], phase);
+        phase ^= 1;
+        tc_fence_after();
+        {
+            uint32_t rq[32], rk[32], rv[32];
+            {
+                uint32_t lo[32];
+                tmem_ld_32x32(trow + TM_DQ, rq);
+                tmem_ld_32x32(trow + TM_DQ + HD, lo);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < HD; ++c) rq[c] = __float_as_uint(__uint_as_float(rq[c]) + __uint_as_float(lo[c]));
+                tmem_ld_32x32(trow + TM_DK, rk);
+                tmem_ld_32x32(trow + TM_DK + HD, lo);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < HD; ++c) rk[c] = __float_as_uint(__uint_as_float(rk[c]) + __uint_as_float(lo[c]));
+            }
+            tmem_ld_32x32(trow + TM_DV, rv);
+            tmem_ld_wait();
+            if (tok >= 0) {
+                float qh[HD], kh[HD], o[HD];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    unpack8(ld_tile8_raw(sQ, tid, c), qh + 8 * c);
+                    unpack8(ld_tile8_raw(sK, tid, c), kh + 8 * c);
+                }
+                // d q = (d qh - qh (qh . d qh)) / |q| with d qh = scale * (dS Kh)   (normalisation backward)
+                float dot = 0.0f;
+#pragma unroll
+                for (int c = 0; c < HD; ++c) dot = fmaf(__uint_as_float(rq[c]) * scale, qh[c], dot);
+                const float iq = 1.0f / qn;
+#pragma unroll
+                for (int c = 0; c < HD; ++c) o[c] = (__uint_as_float(rq[c]) * scale - qh[c] * dot) * iq;
+                store_row32(a.dq, a.ld, tok, h, o);
+                dot = 0.0f;
+#pragma unroll
+                for (int c = 0; c < HD; ++c) dot = fmaf(__uint_as_float(rk[c]) * scale, kh[c], dot);
+                const float ik = 1.0f / kn;
+#pragma unroll
+                for (int c = 0; c < HD; ++c) o[c] = (__uint_as_float(rk[c]) * scale - kh[c] * dot) * ik;
+                store_row32(a.dk, a.ld, tok, h, o);
+#pragma unroll
+                for (int c = 0; c < HD; ++c) o[c] = __uint_as_float(rv[c]);
+                store_row32(a.dv, a.ld, tok, h, o);
+            }
+        }
+        tc_fence_before();
+        __syncthreads();          // tiles and TMEM accumulators are reused by the next window pair
+        tc_fence_after();
+    }
+
+    // flush: bias gradient of every window this CTA visited, and d(logit_scale)
+    float* dbias = a.dbias + static_cast<long long>(h) * N * N;
+    for (int idx = tid; idx < N * N; idx += blockDim.x) {
+        const float v = dbias_s[idx] + dbias_s[N * N + idx];
+        if (v != 0.0f) atomicAdd(&dbias[idx], v);
+    }
+    dscale_acc = warp_sum(dscale_acc);
+    if ((tid & 31) == 0) red[warp] = dscale_acc;
+    __syncthreads();
+    if (tid == 0) {
+        const float t = red[0] + red[1] + red[2] + red[3];
+        atomicAdd(&a.dlogit_scale[h], raw_ls <= LOGIT_MAX ? t * scale : 0.0f);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+}  // namespace
+
+bool swin_attention_tc_supported(int dtype, int head_dim, int window, long long ld, long long ldc, const void* q, const void* k,
+                                 const void* v, const void* ctx) {
+    if (dtype != KLAB_BF16 || head_dim != HD || window * window > SLOT) return false;
+    if ((ld | ldc) % 8) return false;
+    return ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(ctx)) & 15) == 0;
+}
+
+static SwinTcArgs make_args(int B, int res, int heads, int window, int shift, const void* q, const void* k, const void* v, long long ld,
+                            long long ldc, const float* logit_scale, const float* bias, float* lse) {
+    SwinTcArgs a{};
+    a.q = static_cast<const __nv_bfloat16*>(q); a.k = static_cast<const __nv_bfloat16*>(k); a.v = static_cast<const __nv_bfloat16*>(v);
+    a.ld = ld; a.ldc = ldc; a.B = B; a.res = res; a.heads = heads; a.w = window; a.shift = shift; a.N = window * window;
+    a.nW = (res / window) * (res / window);
+    a.logit_scale = logit_scale; a.bias = bias; a.lse = lse;
+    return a;
+}
+
+int swin_attention_fwd_tc(cudaStream_t st, int B, int res, int heads, int window, int shift, const void* q, const void* k, const void* v,
+                          long long ld, void* ctx, long long ldc, const float* logit_scale, const float* bias, float* lse) {
+    SwinTcArgs a = make_args(B, res, heads, window, shift, q, k, v, ld, ldc, logit_scale, bias, lse);
+    a.out = static_cast<__nv_bfloat16*>(ctx);
+    const size_t smem = 1024 + 5 * TB + sizeof(int) * TILE + 64;
+    static bool set = false;
+    if (!set) {
+        KLAB_CHECK_CUDA(cudaFuncSetAttribute(swin_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        set = true;
+    }
+    const dim3 grid((B * a.nW + 1) / 2, heads);
+    swin_attn_fwd_tc_kernel<<<grid, 128, smem, st>>>(a);
+    KLAB_LAUNCH_CHECK();
+    count_launch();
+    return KLAB_OK;
+}
+
+int swin_attention_bwd_tc(cudaStream_t st, int B, int res, int heads, int window, int shift, const void* q, const void* k, const void* v,
+                          long long ld, const void* ctx, const void* dctx, long long ldc, void* dq, void* dk, void* dv,
+                          const float* logit_scale, const float* bias, const float* lse, float* dbias, float* dlogit_scale) {
+    SwinTcArgs a = make_args(B, res, heads, window, shift, q, k, v, ld, ldc, logit_scale, bias, const_cast<float*>(lse));
+    a.ctx = static_cast<const __nv_bfloat16*>(ctx); a.dctx = static_cast<const __nv_bfloat16*>(dctx);
+    a.dq = static_cast<__nv_bfloat16*>(dq); a.dk = static_cast<__nv_bfloat16*>(dk); a.dv = static_cast<__nv_bfloat16*>(dv);
+    a.dbias = dbias; a.dlogit_scale = dlogit_scale;
+    const int N = a.N;
+    const size_t smem = 1024 + 10 * TB + sizeof(float) * 2 * N * N + sizeof(int) * TILE + 64;
+    static size_t set = 0;
+    if (smem > set) {
+        KLAB_CHECK_CUDA(cudaFuncSetAttribute(swin_attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        set = smem;
+    }
+    KLAB_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * heads * N * N, st));
+    KLAB_CHECK_CUDA(cudaMemsetAsync(dlogit_scale, 0, sizeof(float) * heads, st));
+    const int npairs = (B * a.nW + 1) / 2;
+    int nchunks = (sm_count() + heads - 1) / heads;
+    if (nchunks > npairs) nchunks = npairs;
+    if (nchunks < 1) nchunks = 1;
+    const dim3 grid(nchunks, heads);
+    swin_attn_bwd_tc_kernel<<<grid, 128, smem, st>>>(a, npairs);
+    KLAB_LAUNCH_CHECK();
+    count_launch();
+    return KLAB_OK;
+}
+
+}  // namespace klab

@@ -329,7 +329,6 @@ __global__ void __launch_bounds__(128) t5_attn_bwd_tc_kernel(const __grid_consta
             const int i = qt * TILE + tid;
             const int jmax = a.causal ? min(Lk, i + a.q_offset + 1) : Lk;
             const float* br = brel + (Lq - 1 - i);
-            float* dr = drel + (Lq - 1 - i);
             const bool row_ok = i < Lq;
             for (int c0 = 0; c0 < TILE; c0 += 32) {
                 uint32_t rs[32], rp[32];
@@ -346,7 +345,6 @@ __global__ void __launch_bounds__(128) t5_attn_bwd_tc_kernel(const __grid_consta
                         const float m = a.dropout_p > 0.0f ? drop_mult(a, seed, thr, inv_keep, bh, i, j) : 1.0f;
                         p = pr * m;
                         ds = pr * (__uint_as_float(rp[t]) * m - Dv[qt]);
-                        if (has_bias) atomicAdd(&dr[j], ds);
                     }
                     pv[t] = p;
                     dsv[t] = ds;
@@ -380,6 +378,24 @@ __global__ void __launch_bounds__(128) t5_attn_bwd_tc_kernel(const __grid_consta
                     umma_bf16(tmem + TM_DQ + qt * DK, umma_smem_desc_sw128(dsa + (ks >> 2) * T + (ks & 3) * 32, 16, 1024),
                               umma_smem_desc_sw128(ka + ks * 2048, 8192, 1024), id_q, (kb | ks) != 0);
                 umma_commit(&bars[1]);
+            }
+            // bias gradient, overlapped with the MMAs: sum the dS tile along its diagonals (j - i = const).  Thread t owns
+            // diagonals t and t + 128 of this tile, so the adds into drel[] are race free; at a fixed row the 32 lanes of a
+            // warp read 32 consecutive bf16 of that row (no bank conflicts) -- replaces 128 shared atomics per thread.
+            if (has_bias) {
+                for (int half = 0; half < 2; ++half) {
+                    const int dd = tid + half * TILE;                 // j_local - i_local + 127
+                    if (dd > 2 * TILE - 2) break;
+                    const int lo = max(0, TILE - 1 - dd), hi = min(TILE - 1, 2 * TILE - 2 - dd);
+                    float acc = 0.0f;
+                    for (int il = lo; il <= hi; ++il) {
+                        const int jl = il + dd - (TILE - 1);
+                        const __nv_bfloat16 v = *reinterpret_cast<const __nv_bfloat16*>(sdS + (jl >> 6) * T + sw128(il, jl & 63));
+                        acc += __bfloat162float(v);
+                    }
+                    const int r = dd - (TILE - 1) + (kb - qt) * TILE + (Lq - 1);
+                    if (r >= 0 && r < Lq + Lk - 1) drel[r] += acc;
+                }
             }
             // the MMAs above read sP / sdS: wait for them before the next iteration overwrites the tiles
             mbar_wait(&bars[1], phase);
