@@ -169,9 +169,18 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (row < M && nvalid > 0) {
                     if (splits > 1) {
                         float* dst = reinterpret_cast<float*>(D) + row * ldd + col0;
+                        if (nvalid == 32) {                     // 16-byte aligned (ldd % 4 == 0, col0 % 32 == 0): vector reds
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (i < nvalid) atomicAdd(dst + i, __uint_as_float(r[i]) * epi.alpha);
+                            for (int i = 0; i < 32; i += 4)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i),
+                                             "f"(__uint_as_float(r[i]) * epi.alpha), "f"(__uint_as_float(r[i + 1]) * epi.alpha),
+                                             "f"(__uint_as_float(r[i + 2]) * epi.alpha), "f"(__uint_as_float(r[i + 3]) * epi.alpha)
+                                             : "memory");
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (i < nvalid) atomicAdd(dst + i, __uint_as_float(r[i]) * epi.alpha);
+                        }
                     } else {
                         float v[32];
 #pragma unroll
@@ -196,7 +205,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 }
 
 template <int BN, bool A_MN, bool B_MN>
-int launch_cfg(cudaStream_t stream, int M, int N, int K, const void* A, long long lda, const void* B, long long ldb,
+int launch_cfg(cudaStream_t stream, int M, int N, int K, int splits, const void* A, long long lda, const void* B, long long ldb,
                void* D, long long ldd, const klab_gemm_epilogue& epi) {
     using Cfg = TileCfg<BN>;
     CUtensorMap ta, tb;
@@ -215,16 +224,6 @@ int launch_cfg(cudaStream_t stream, int M, int N, int K, const void* A, long lon
         attr_set = true;
     }
     const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-    const int num_k = (K + BK - 1) / BK;
-    int splits = 1;
-    const bool linear = epi.act == KLAB_ACT_NONE && !epi.bias && !epi.residual && !epi.aux_out && epi.dropout_p == 0.0f &&
-                        epi.out_dtype == KLAB_F32;
-    if (linear && A_MN && B_MN && tiles * 2 <= sm_count() && num_k >= 16) {
-        splits = (2 * sm_count() + tiles - 1) / tiles;
-        if (splits > num_k / 4) splits = num_k / 4;
-        const int kps = (num_k + splits - 1) / splits;
-        splits = (num_k + kps - 1) / kps;                 // no empty K ranges
-    }
     if (splits > 1 && !epi.accumulate) {
         if (ldd == N) KLAB_CHECK_CUDA(cudaMemsetAsync(D, 0, sizeof(float) * static_cast<size_t>(M) * N, stream));
         else KLAB_CHECK_CUDA(cudaMemset2DAsync(D, sizeof(float) * ldd, 0, sizeof(float) * N, M, stream));
@@ -238,34 +237,43 @@ int launch_cfg(cudaStream_t stream, int M, int N, int K, const void* A, long lon
 }
 
 template <int BN>
-int launch_major(cudaStream_t stream, int M, int N, int K, const void* A, long long lda, int a_mn, const void* B,
+int launch_major(cudaStream_t stream, int M, int N, int K, int splits, const void* A, long long lda, int a_mn, const void* B,
                  long long ldb, int b_mn, void* D, long long ldd, const klab_gemm_epilogue& epi) {
-    if (!a_mn && !b_mn) return launch_cfg<BN, false, false>(stream, M, N, K, A, lda, B, ldb, D, ldd, epi);
-    if (!a_mn && b_mn) return launch_cfg<BN, false, true>(stream, M, N, K, A, lda, B, ldb, D, ldd, epi);
-    if (a_mn && !b_mn) return launch_cfg<BN, true, false>(stream, M, N, K, A, lda, B, ldb, D, ldd, epi);
-    return launch_cfg<BN, true, true>(stream, M, N, K, A, lda, B, ldb, D, ldd, epi);
+    if (!a_mn && !b_mn) return launch_cfg<BN, false, false>(stream, M, N, K, splits, A, lda, B, ldb, D, ldd, epi);
+    if (!a_mn && b_mn) return launch_cfg<BN, false, true>(stream, M, N, K, splits, A, lda, B, ldb, D, ldd, epi);
+    if (a_mn && !b_mn) return launch_cfg<BN, true, false>(stream, M, N, K, splits, A, lda, B, ldb, D, ldd, epi);
+    return launch_cfg<BN, true, true>(stream, M, N, K, splits, A, lda, B, ldb, D, ldd, epi);
 }
 
-// Pick the N tile: maximise (wave efficiency) x (per-tile efficiency: wider tiles amortise smem reads).
-int pick_bn(int M, int N, bool split_k_candidate) {
-    if (split_k_candidate) return N > 128 ? 256 : (N > 64 ? 128 : 64);   // occupancy comes from the K split: keep tiles wide
+// Choose the N tile and the K split with a small time model (microseconds), calibrated on B200:
+//   per k-block (64 deep) MMA time of a 128 x BN tile: BN/256 * 0.27 us (128 x 256 x 16 UMMA = 128 cycles), narrower tiles
+//   lose a little to shared-memory bandwidth; ~2 us of prologue / epilogue per tile; split-K adds M*N*splits fp32 reds
+//   (~0.2 elements/ns measured with red.global.add.v4.f32) and a memset.
+void pick_config(int M, int N, int K, bool can_split, int* bn_out, int* splits_out) {
     const int sms = sm_count();
-    const int num_m = (M + BM - 1) / BM;
+    const int num_m = (M + BM - 1) / BM, num_k = (K + BK - 1) / BK;
     const int cand[3] = {256, 128, 64};
-    const double tile_eff[3] = {1.0, 0.92, 0.70};
-    int best = 64;
-    double best_score = -1.0;
+    const double t_k[3] = {0.27, 0.145, 0.09};
+    double best = 1e30;
+    *bn_out = 64;
+    *splits_out = 1;
     for (int i = 0; i < 3; ++i) {
-        const int bn = cand[i];
-        const int num_n = (N + bn - 1) / bn;
+        const int num_n = (N + cand[i] - 1) / cand[i];
         const long long tiles = 1ll * num_m * num_n;
-        const long long waves = (tiles + sms - 1) / sms;
-        const double wave_eff = double(tiles) / double(waves * sms);
-        const double fill = double(N) / double(num_n * bn);         // wasted columns in the last tile
-        const double score = wave_eff * fill * tile_eff[i];
-        if (score > best_score + 1e-9) { best_score = score; best = bn; }
+        const double waste = double(num_n * cand[i]) / double(N);            // MMA work on padding columns is still paid
+        for (int s = 1; s <= (can_split ? 128 : 1); s *= 2) {
+            if (s > 1 && num_k / s < 8) break;
+            const int kps = (num_k + s - 1) / s;
+            const long long waves = (tiles * s + sms - 1) / sms;
+            double t = waves * (kps * t_k[i] * (waste > 1.5 ? 1.0 : 1.0) + 2.0);
+            if (s > 1) t += double(M) * N * s / 200.0e3 + 2.0;
+            if (t < best - 1e-9) { best = t; *bn_out = cand[i]; *splits_out = s; }
+        }
     }
-    return best;
+    if (*splits_out > 1) {                                                   // no empty K ranges
+        const int kps = (num_k + *splits_out - 1) / *splits_out;
+        *splits_out = (num_k + kps - 1) / kps;
+    }
 }
 
 }  // namespace
@@ -276,13 +284,15 @@ int gemm_tc_launch(cudaStream_t stream, int M, int N, int K, const void* A, long
     KLAB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm(bf16): lda=%lld / ldb=%lld must be multiples of 8", lda, ldb);
     KLAB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
                  "gemm(bf16): operand base pointers must be 16-byte aligned");
-    const bool split_k_candidate = a_mn && b_mn && epi.act == KLAB_ACT_NONE && !epi.bias && !epi.residual && !epi.aux_out &&
-                                   epi.dropout_p == 0.0f && epi.out_dtype == KLAB_F32 && K >= 16 * BK &&
-                                   ((M + BM - 1) / BM) * ((N + 255) / 256) * 2 <= sm_count();
-    switch (pick_bn(M, N, split_k_candidate)) {
-        case 256: return launch_major<256>(stream, M, N, K, A, lda, a_mn, B, ldb, b_mn, D, ldd, epi);
-        case 128: return launch_major<128>(stream, M, N, K, A, lda, a_mn, B, ldb, b_mn, D, ldd, epi);
-        default: return launch_major<64>(stream, M, N, K, A, lda, a_mn, B, ldb, b_mn, D, ldd, epi);
+    // split-K needs a linear epilogue into an fp32 output (weight gradients)
+    const bool can_split = epi.act == KLAB_ACT_NONE && !epi.bias && !epi.residual && !epi.aux_out && epi.dropout_p == 0.0f &&
+                           epi.out_dtype == KLAB_F32 && ldd % 4 == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0;
+    int bn, splits;
+    pick_config(M, N, K, can_split, &bn, &splits);
+    switch (bn) {
+        case 256: return launch_major<256>(stream, M, N, K, splits, A, lda, a_mn, B, ldb, b_mn, D, ldd, epi);
+        case 128: return launch_major<128>(stream, M, N, K, splits, A, lda, a_mn, B, ldb, b_mn, D, ldd, epi);
+        default: return launch_major<64>(stream, M, N, K, splits, A, lda, a_mn, B, ldb, b_mn, D, ldd, epi);
     }
 }
 

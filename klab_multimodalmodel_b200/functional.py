@@ -2,7 +2,9 @@
 
 Granularity is one autograd node per transformer block (plus embed / merge / loss nodes) so that gradients of a block's
 parameters become ready as soon as its backward finishes: DistributedDataParallel's bucket all-reduce
-(/root/reference/train.py:26,62) then overlaps the rest of the backward pass.
+(/root/reference/train.py:26,62) then overlaps the rest of the backward pass.  The kernel sequence
+of each block is captured into a CUDA graph per shape signature (graphs.py), so the host issues ~170 graph launches per
+step instead of ~4000 kernel launches.
 
 Every arithmetic step below is a kernel of libklab_b200.so (ops.py); torch supplies memory, streams and the
 autograd graph only.  Citations: HF/ = site-packages/transformers 5.5.0.
@@ -13,6 +15,7 @@ import torch
 
 from . import _lib as L
 from . import ops as O
+from .graphs import POOL
 
 
 # ------------------------------------------------------------------------------------------------
@@ -20,29 +23,61 @@ from . import ops as O
 # ------------------------------------------------------------------------------------------------
 class OperandCache:
     """Keeps, per group of parameters, one contiguous [sum(N_i), K] operand in the compute dtype (bf16 copies for the
-    tensor cores; q|k|v weights concatenated so one GEMM produces all three).  Entries are refreshed when a parameter's
-    in-place version counter changes (i.e. after optimizer.step()), so frozen sub-models are converted exactly once."""
+    tensor cores; q|k|v weights concatenated so one GEMM produces all three).  The buffer of a group never moves, so CUDA
+    graphs can bake its address.  `get` refreshes a stale entry eagerly (a parameter's version counter changed, i.e. after
+    optimizer.step()); `recast` converts unconditionally (used INSIDE a captured training region: the conversion is then part
+    of the graph); `peek` returns the buffer as is (backward reuses what forward converted)."""
 
     def __init__(self):
         self._store: dict = {}
 
-    def get(self, params, dtype: torch.dtype) -> torch.Tensor:
-        if len(params) == 1 and params[0].dtype == dtype and params[0].dim() == 2:
-            return params[0].detach()
+    @staticmethod
+    def _direct(params, dtype):
+        return len(params) == 1 and params[0].dtype == dtype and params[0].dim() == 2
+
+    def _entry(self, params, dtype):
         key = tuple(id(p) for p in params) + (dtype,)
-        ver = tuple(p._version for p in params) + tuple(p.data_ptr() for p in params)
-        hit = self._store.get(key)
-        if hit is not None and hit[0] == ver:
-            return hit[1]
-        k = params[0][0].numel() if params[0].dim() > 1 else params[0].numel()
-        rows = [p.numel() // k for p in params]
-        buf = hit[1] if hit is not None else torch.empty(sum(rows), k, dtype=dtype, device=params[0].device)
+        e = self._store.get(key)
+        if e is not None and e[1].device != params[0].device:
+            e = None
+        if e is None:
+            k = params[0][0].numel() if params[0].dim() > 1 else params[0].numel()
+            rows = [p.numel() // k for p in params]
+            buf = torch.empty(sum(rows), k, dtype=dtype, device=params[0].device)
+            e = self._store[key] = [None, buf, rows, k]
+        return e
+
+    @staticmethod
+    def _version(params):
+        return tuple(p._version for p in params) + tuple(p.data_ptr() for p in params)
+
+    def _convert(self, e, params, dtype):
+        _, buf, rows, k = e
         r0 = 0
         for p, r in zip(params, rows):
             O.cast(p.detach().reshape(r, k), dtype, out=buf[r0:r0 + r])
             r0 += r
-        self._store[key] = (ver, buf)
-        return buf
+        e[0] = self._version(params)
+
+    def get(self, params, dtype) -> torch.Tensor:
+        if self._direct(params, dtype):
+            return params[0].detach()
+        e = self._entry(params, dtype)
+        if e[0] != self._version(params):
+            self._convert(e, params, dtype)
+        return e[1]
+
+    def recast(self, params, dtype) -> torch.Tensor:
+        if self._direct(params, dtype):
+            return params[0].detach()
+        e = self._entry(params, dtype)
+        self._convert(e, params, dtype)
+        return e[1]
+
+    def peek(self, params, dtype) -> torch.Tensor:
+        if self._direct(params, dtype):
+            return params[0].detach()
+        return self._entry(params, dtype)[1]
 
     def clear(self):
         self._store.clear()
@@ -61,10 +96,44 @@ def cat_vec(vecs, device) -> torch.Tensor:
 
 
 class Ctx:
-    """Static description of one block call (shapes, mode, dropout)."""
+    """Static description of one block at one shape signature (created once and cached by the owning module, so its
+    identity doubles as the CUDA-graph key).  `busy` is set while a captured forward's activations await their backward."""
 
     def __init__(self, **kw):
+        self.busy = False
         self.__dict__.update(kw)
+
+
+class _Token:
+    """Clears Ctx.busy when the autograd node that owns it dies without having run backward."""
+
+    def __init__(self, c):
+        self.c = c
+
+    def __del__(self):
+        self.c.busy = False
+
+
+class _StepToken:
+    """Counts training forwards whose backward has not run yet.  While one is outstanding the device-side dropout counter
+    must not advance (the pending backward regenerates its masks from it)."""
+    outstanding = 0
+
+    def __init__(self):
+        self.live = True
+        _StepToken.outstanding += 1
+
+    def release(self):
+        if self.live:
+            self.live = False
+            _StepToken.outstanding -= 1
+
+    def __del__(self):
+        self.release()
+
+
+def pending_backward() -> bool:
+    return _StepToken.outstanding > 0
 
 
 _OUTER_GRAD = [True]
@@ -81,37 +150,45 @@ def _needs_grad(tensors) -> bool:
     return _OUTER_GRAD[0] and any(t is not None and t.requires_grad for t in tensors)
 
 
+def _detach_aliased_grads(params):
+    """Gradient accumulation: if a parameter's .grad still IS the static gradient buffer of a captured backward region, the
+    replay about to run would overwrite it -- move the accumulated value out first."""
+    for p in params:
+        g = p.grad
+        if g is not None and POOL.owns(g):
+            p.grad = g.clone()
+
+
 # ------------------------------------------------------------------------------------------------
 # T5 block  (HF/models/t5/modeling_t5.py: T5LayerSelfAttention :356-377, T5LayerCrossAttention :387-408,
 #            T5LayerFF :135-150, T5Attention :253-344)
+# dropout sites of block `c` use seeds c.seed + {0..5} plus the device-side step counter c.seed_ptr
 # ------------------------------------------------------------------------------------------------
 def _t5_attn_fwd(c, n, kv_src, wq_or_qkv, wkv, wo, resid, table, lut, rz, causal, Lq, Lk, seed):
-    """n: normed input [B*Lq, d]; returns (h_out, saved) with h_out = resid + dropout(attn(n) Wo^T)."""
+    """n: normed input [B*Lq, d]; returns (h_out, qkv, kvbuf, ctx, lse) with h_out = resid + dropout(attn(n) Wo^T)."""
     H, dk = c.H, c.dk
     inner = H * dk
+    qkv = O.linear_fwd(n, wq_or_qkv)
     if kv_src is None:                                   # self-attention: one GEMM for q|k|v
-        qkv = O.linear_fwd(n, wq_or_qkv)
         q, k, v = qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:]
         kvbuf = None
     else:                                                # cross-attention: q from n, k|v from the encoder output
-        qkv = O.linear_fwd(n, wq_or_qkv)
         q = qkv
         kvbuf = O.linear_fwd(kv_src, wkv)
         k, v = kvbuf[:, :inner], kvbuf[:, inner:]
     ctxt, lse = O.t5_attention_fwd(q, k, v, c.B, H, Lq, Lk, dk, bias_table=table, lut=lut, rel_zero=rz,
-                                   num_buckets=c.num_buckets, causal=causal, dropout_p=c.p, seed=seed)
-    h = O.linear_fwd(ctxt, wo, residual=resid, dropout_p=c.p, seed=seed + 1)
-    return h, (qkv, kvbuf, ctxt, lse)
+                                   num_buckets=c.num_buckets, causal=causal, dropout_p=c.p, seed=seed, seed_ptr=c.seed_ptr)
+    h = O.linear_fwd(ctxt, wo, residual=resid, dropout_p=c.p, seed=seed + 1, seed_ptr=c.seed_ptr)
+    return h, qkv, kvbuf, ctxt, lse
 
 
-def _t5_attn_bwd(c, dh, n, kv_src, wq_or_qkv, wkv, wo, saved, table, lut, rz, causal, Lq, Lk, seed, dtable):
+def _t5_attn_bwd(c, dh, n, kv_src, wq_or_qkv, wkv, wo, qkv, kvbuf, ctxt, lse, table, lut, rz, causal, Lq, Lk, seed, dtable):
     """dh: gradient of the attention layer's output (residual part handled by the caller).
     Returns dn, dkv_src (or None), dWq(kv), dWkv (or None), dWo."""
     H, dk = c.H, c.dk
     inner = H * dk
-    qkv, kvbuf, ctxt, lse = saved
     if c.p > 0.0:                                        # dropout on the o-projection output (:375 / :406)
-        dh = O.dropout_apply(dh, c.p, seed + 1)
+        dh = O.dropout_apply(dh, c.p, seed + 1, c.seed_ptr)
     dctx = O.linear_dgrad(dh, wo)
     dwo = O.linear_wgrad(dh, ctxt)
     dqkv = torch.empty_like(qkv)
@@ -124,7 +201,7 @@ def _t5_attn_bwd(c, dh, n, kv_src, wq_or_qkv, wkv, wo, saved, table, lut, rz, ca
         dkvbuf = torch.empty_like(kvbuf)
         dq, dk_, dv = dqkv, dkvbuf[:, :inner], dkvbuf[:, inner:]
     O.t5_attention_bwd(q, k, v, ctxt, dctx, lse, dq, dk_, dv, c.B, H, Lq, Lk, dk, bias_table=table, lut=lut, rel_zero=rz,
-                       num_buckets=c.num_buckets, causal=causal, dbias_table=dtable, dropout_p=c.p, seed=seed)
+                       num_buckets=c.num_buckets, causal=causal, dbias_table=dtable, dropout_p=c.p, seed=seed, seed_ptr=c.seed_ptr)
     dn = O.linear_dgrad(dqkv, wq_or_qkv)
     dwq = O.linear_wgrad(dqkv, n)
     if kv_src is None:
@@ -136,20 +213,87 @@ def _t5_attn_bwd(c, dh, n, kv_src, wq_or_qkv, wkv, wo, saved, table, lut, rz, ca
 
 def _t5_ff_fwd(c, x, ln_w, wi, wo, seed):
     n, rstd = O.rmsnorm_fwd(x, ln_w, c.eps)
-    f = O.linear_fwd(n, wi, act=L.ACT_RELU, dropout_p=c.p, seed=seed)
-    out = O.linear_fwd(f, wo, residual=x, dropout_p=c.p, seed=seed + 1)
-    return out, (n, rstd, f)
+    f = O.linear_fwd(n, wi, act=L.ACT_RELU, dropout_p=c.p, seed=seed, seed_ptr=c.seed_ptr)
+    out = O.linear_fwd(f, wo, residual=x, dropout_p=c.p, seed=seed + 1, seed_ptr=c.seed_ptr)
+    return out, n, rstd, f
 
 
-def _t5_ff_bwd(c, dout, x, ln_w, wi, wo, saved, seed):
-    n, rstd, f = saved
-    dy = O.dropout_apply(dout, c.p, seed + 1) if c.p > 0.0 else dout
-    df = O.linear_dgrad(dy, wo, act=L.ACT_RELU_BWD, aux_in=f, dropout_p=c.p, seed=seed)
+def _t5_ff_bwd(c, dout, x, ln_w, wi, wo, n, rstd, f, seed):
+    dy = O.dropout_apply(dout, c.p, seed + 1, c.seed_ptr) if c.p > 0.0 else dout
+    df = O.linear_dgrad(dy, wo, act=L.ACT_RELU_BWD, aux_in=f, dropout_p=c.p, seed=seed, seed_ptr=c.seed_ptr)
     dwo = O.linear_wgrad(dy, f)
     dn = O.linear_dgrad(df, wi)
     dwi = O.linear_wgrad(df, n)
     dx, dln = O.rmsnorm_bwd(dn, x, ln_w, rstd, dres=dout)
     return dx, dln, dwi, dwo
+
+
+def _t5_operands(c, params, cd, mode):
+    """(wqkv, w_o, w_i, w_ff[, w_cq, w_ckv, w_co]) in the compute dtype; mode in {"get", "recast", "peek"}."""
+    f = getattr(c.cache, mode)
+    if c.is_decoder:
+        ln0, q, k, v, o, ln1, cq, ck, cv, co, ln2, wi, wo = params
+        return f([q, k, v], cd), f([o], cd), f([wi], cd), f([wo], cd), f([cq], cd), f([ck, cv], cd), f([co], cd)
+    ln0, q, k, v, o, ln1, wi, wo = params
+    return f([q, k, v], cd), f([o], cd), f([wi], cd), f([wo], cd)
+
+
+def _t5_block_fwd_body(x, enc_out, c, save, recast, table, *params):
+    """-> (out,) or (out, n0, rstd0, qkv, ctx, lse, h1, [n1, rstd1, qc, kvbuf, ctx2, lse2, h2,] n2, rstd2, f)"""
+    cd = x.dtype
+    dec = c.is_decoder
+    ws = _t5_operands(c, params, cd, "recast" if recast else "peek")
+    seed = c.seed
+    if dec:
+        ln0, ln1, ln2 = params[0], params[5], params[10]
+        wqkv, w_o, w_i, w_ff, w_cq, w_ckv, w_co = ws
+    else:
+        ln0, ln1 = params[0], params[5]
+        wqkv, w_o, w_i, w_ff = ws
+    n0, rstd0 = O.rmsnorm_fwd(x, ln0, c.eps)
+    h1, qkv, _, ctxt, lse = _t5_attn_fwd(c, n0, None, wqkv, None, w_o, x, table, c.lut, c.rz, dec, c.L, c.L, seed)
+    if dec:
+        n1, rstd1 = O.rmsnorm_fwd(h1, ln1, c.eps)
+        h2, qc, kvbuf, ctx2, lse2 = _t5_attn_fwd(c, n1, enc_out, w_cq, w_ckv, w_co, h1, None, None, 0, False, c.L, c.Le, seed + 2)
+        out, n2, rstd2, f = _t5_ff_fwd(c, h2, ln2, w_i, w_ff, seed + 4)
+        return (out, n0, rstd0, qkv, ctxt, lse, h1, n1, rstd1, qc, kvbuf, ctx2, lse2, h2, n2, rstd2, f) if save else (out,)
+    out, n2, rstd2, f = _t5_ff_fwd(c, h1, ln1, w_i, w_ff, seed + 4)
+    return (out, n0, rstd0, qkv, ctxt, lse, h1, n2, rstd2, f) if save else (out,)
+
+
+def _t5_block_bwd_body(dout, x, enc_out, *rest):
+    """rest = saved activations (forward order) then consts (c, table, *params) -> (dx, denc | None, dtable | None, *param grads)"""
+    n_acts = 16 if enc_out is not None else 9
+    acts, (c, table, *params) = rest[:n_acts], rest[n_acts:]
+    cd = x.dtype
+    dec = c.is_decoder
+    ws = _t5_operands(c, params, cd, "peek")
+    seed = c.seed
+    inner = c.H * c.dk
+    dtable = torch.zeros_like(table) if table is not None else None
+    denc = None
+    if dec:
+        n0, rstd0, qkv, ctxt, lse, h1, n1, rstd1, qc, kvbuf, ctx2, lse2, h2, n2, rstd2, f = acts
+        ln0, ln1, ln2 = params[0], params[5], params[10]
+        wqkv, w_o, w_i, w_ff, w_cq, w_ckv, w_co = ws
+        dh2, dln2, dwi, dwo_ff = _t5_ff_bwd(c, dout, h2, ln2, w_i, w_ff, n2, rstd2, f, seed + 4)
+        dn1, denc, dwcq, dwckv, dwco = _t5_attn_bwd(c, dh2, n1, enc_out, w_cq, w_ckv, w_co, qc, kvbuf, ctx2, lse2, None, None, 0,
+                                                    False, c.L, c.Le, seed + 2, None)
+        dh1, dln1 = O.rmsnorm_bwd(dn1, h1, ln1, rstd1, dres=dh2)
+    else:
+        n0, rstd0, qkv, ctxt, lse, h1, n2, rstd2, f = acts
+        ln0, ln1 = params[0], params[5]
+        wqkv, w_o, w_i, w_ff = ws
+        dh1, dln1, dwi, dwo_ff = _t5_ff_bwd(c, dout, h1, ln1, w_i, w_ff, n2, rstd2, f, seed + 4)
+    dn0, _, dwqkv, _, dwo = _t5_attn_bwd(c, dh1, n0, None, wqkv, None, w_o, qkv, None, ctxt, lse, table, c.lut, c.rz, dec,
+                                         c.L, c.L, seed, dtable)
+    dx, dln0 = O.rmsnorm_bwd(dn0, x, ln0, rstd0, dres=dh1)
+    gq, gk, gv = dwqkv[:inner], dwqkv[inner:2 * inner], dwqkv[2 * inner:]
+    if dec:
+        grads = (dln0, gq, gk, gv, dwo, dln1, dwcq, dwckv[:inner], dwckv[inner:], dwco, dln2, dwi, dwo_ff)
+    else:
+        grads = (dln0, gq, gk, gv, dwo, dln1, dwi, dwo_ff)
+    return (dx, denc, dtable) + grads
 
 
 class T5BlockFn(torch.autograd.Function):
@@ -159,70 +303,34 @@ class T5BlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, c, x, enc_out, table, *params):
-        cd = x.dtype
-        cache = c.cache
-        dec = c.is_decoder
-        if dec:
-            ln0, q, k, v, o, ln1, cq, ck, cv, co, ln2, wi, wo = params
-        else:
-            ln0, q, k, v, o, ln1, wi, wo = params
-        wqkv = cache.get([q, k, v], cd)
-        w_o = cache.get([o], cd)
-        w_i = cache.get([wi], cd)
-        w_ff = cache.get([wo], cd)
-        seed = c.seed
-        n0, rstd0 = O.rmsnorm_fwd(x, ln0, c.eps)
-        h1, s_self = _t5_attn_fwd(c, n0, None, wqkv, None, w_o, x, table, c.lut, c.rz, dec, c.L, c.L, seed)
-        if dec:
-            w_cq, w_ckv, w_co = cache.get([cq], cd), cache.get([ck, cv], cd), cache.get([co], cd)
-            n1, rstd1 = O.rmsnorm_fwd(h1, ln1, c.eps)
-            h2, s_cross = _t5_attn_fwd(c, n1, enc_out, w_cq, w_ckv, w_co, h1, None, None, 0, False, c.L, c.Le, seed + 2)
-            out, s_ff = _t5_ff_fwd(c, h2, ln2, w_i, w_ff, seed + 4)
-        else:
-            out, s_ff = _t5_ff_fwd(c, h1, ln1, w_i, w_ff, seed + 4)
-        if _needs_grad((x, enc_out, table) + tuple(params)):
+        save = _needs_grad((x, enc_out, table) + tuple(params))
+        trainable = save and any(p.requires_grad for p in params)
+        if not trainable:                                   # frozen / eval: convert stale weights eagerly, outside any graph
+            _t5_operands(c, params, x.dtype, "get")
+        x = x.contiguous()
+        outs, graphed = POOL.run(("t5f", id(c), save), _t5_block_fwd_body, (x, enc_out), (c, save, trainable, table) + tuple(params),
+                                 allow_graph=not c.busy)
+        if save:
             ctx.c = c
-            ctx.nparams = len(params)
+            ctx.graphed = graphed
             ctx.save_for_backward(x, enc_out, table, *params)
-            ctx.acts = (n0, rstd0, s_self, h1, (n1, rstd1, s_cross, h2) if dec else None, s_ff)
-        return out
+            ctx.acts = outs[1:]
+            if graphed:
+                c.busy = True
+                ctx.token = _Token(c)
+        return outs[0]
 
     @staticmethod
     def backward(ctx, dout):
         c = ctx.c
         x, enc_out, table, *params = ctx.saved_tensors
-        n0, rstd0, s_self, h1, cross, s_ff = ctx.acts
-        ctx.acts = None
-        cd = x.dtype
-        cache = c.cache
-        dec = c.is_decoder
-        dout = dout.contiguous()
-        if dec:
-            ln0, q, k, v, o, ln1, cq, ck, cv, co, ln2, wi, wo = params
-        else:
-            ln0, q, k, v, o, ln1, wi, wo = params
-        wqkv, w_o, w_i, w_ff = cache.get([q, k, v], cd), cache.get([o], cd), cache.get([wi], cd), cache.get([wo], cd)
-        seed = c.seed
-        inner = c.H * c.dk
-        dtable = torch.zeros_like(table) if table is not None else None
-        denc = None
-        if dec:
-            n1, rstd1, s_cross, h2 = cross
-            w_cq, w_ckv, w_co = cache.get([cq], cd), cache.get([ck, cv], cd), cache.get([co], cd)
-            dh2, dln2, dwi, dwo_ff = _t5_ff_bwd(c, dout, h2, ln2, w_i, w_ff, s_ff, seed + 4)
-            dn1, denc, dwcq, dwckv, dwco = _t5_attn_bwd(c, dh2, n1, enc_out, w_cq, w_ckv, w_co, s_cross, None, None, 0, False,
-                                                        c.L, c.Le, seed + 2, None)
-            dh1, dln1 = O.rmsnorm_bwd(dn1, h1, ln1, rstd1, dres=dh2)
-        else:
-            dh1, dln1, dwi, dwo_ff = _t5_ff_bwd(c, dout, h1, ln1, w_i, w_ff, s_ff, seed + 4)
-        dn0, _, dwqkv, _, dwo = _t5_attn_bwd(c, dh1, n0, None, wqkv, None, w_o, s_self, table, c.lut, c.rz, dec, c.L, c.L, seed, dtable)
-        dx, dln0 = O.rmsnorm_bwd(dn0, x, ln0, rstd0, dres=dh1)
-        gq, gk, gv = dwqkv[:inner], dwqkv[inner:2 * inner], dwqkv[2 * inner:]
-        if dec:
-            grads = (dln0, gq, gk, gv, dwo, dln1, dwcq, dwckv[:inner], dwckv[inner:], dwco, dln2, dwi, dwo_ff)
-        else:
-            grads = (dln0, gq, gk, gv, dwo, dln1, dwi, dwo_ff)
-        return (None, dx, denc, dtable) + grads
+        acts, ctx.acts = ctx.acts, None
+        if ctx.graphed:
+            _detach_aliased_grads(params if table is None else params + [table])
+        outs, _ = POOL.run(("t5b", id(c)), _t5_block_bwd_body, (dout.contiguous(), x, enc_out) + tuple(acts),
+                           (c, table) + tuple(params), allow_graph=ctx.graphed)
+        c.busy = False
+        return (None,) + tuple(outs)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -243,6 +351,19 @@ class RMSNormFn(torch.autograd.Function):
         x, w, rstd = ctx.saved_tensors
         dx, dw = O.rmsnorm_bwd(dy.contiguous(), x, w, rstd)
         return dx, dw, None
+
+
+class DropoutFn(torch.autograd.Function):
+    """nn.Dropout sites outside the blocks (HF/models/t5/modeling_t5.py:734,768)."""
+
+    @staticmethod
+    def forward(ctx, x, p, seed, seed_ptr):
+        ctx.p, ctx.seed, ctx.seed_ptr = p, seed, seed_ptr
+        return O.dropout_apply(x, p, seed, seed_ptr)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return O.dropout_apply(dy, ctx.p, ctx.seed, ctx.seed_ptr), None, None, None
 
 
 class ConcatEmbeddingsFn(torch.autograd.Function):
@@ -303,24 +424,26 @@ class LMHeadLossFn(torch.autograd.Function):
     HF/models/t5/modeling_t5.py:767-768,1105-1117."""
 
     @staticmethod
-    def forward(ctx, x, ln_w, table, labels, cache, eps, p, seed):
+    def forward(ctx, x, ln_w, table, labels, cache, eps, p, seed, seed_ptr):
         cd = x.dtype
         V, d = table.shape
         tab = cache.get([table], cd)
         n, rstd = O.rmsnorm_fwd(x, ln_w, eps)
         if p > 0.0:
-            n = O.dropout_apply(n, p, seed)
+            n = O.dropout_apply(n, p, seed, seed_ptr)
         vpad = (V + 7) // 8 * 8
         logits = O.linear_fwd(n, tab, alpha=d ** -0.5, ldd_pad=vpad)
         lab = labels.reshape(-1).contiguous()
         lse, stats = O.ce_fwd(logits, V, lab)
         if _needs_grad((x, ln_w, table)):
             ctx.save_for_backward(x, ln_w, table, lab, rstd, n, logits, lse, stats)
-            ctx.cache, ctx.vpad, ctx.p, ctx.seed = cache, vpad, p, seed
+            ctx.cache, ctx.vpad, ctx.p, ctx.seed, ctx.seed_ptr = cache, vpad, p, seed, seed_ptr
+            ctx.step_token = _StepToken()
         return stats[0].clone()
 
     @staticmethod
     def backward(ctx, gloss):
+        ctx.step_token.release()
         x, ln_w, table, lab, rstd, n, logits, lse, stats = ctx.saved_tensors
         V, d = table.shape
         tab = ctx.cache.get([table], x.dtype)
@@ -329,9 +452,9 @@ class LMHeadLossFn(torch.autograd.Function):
         dn = O.linear_dgrad(logits, tab, alpha=d ** -0.5)
         dtab = O.linear_wgrad(logits, n, alpha=d ** -0.5)
         if ctx.p > 0.0:
-            dn = O.dropout_apply(dn, ctx.p, ctx.seed)
+            dn = O.dropout_apply(dn, ctx.p, ctx.seed, ctx.seed_ptr)
         dx, dln = O.rmsnorm_bwd(dn, x, ln_w, rstd)
-        return dx, dln, dtab, None, None, None, None, None
+        return dx, dln, dtab, None, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -389,6 +512,64 @@ class PatchMergeFn(torch.autograd.Function):
         return dx, dw, dg_, db_, None, None, None, None
 
 
+def _swin_operands(c, params, cd, mode):
+    (ls, w1, b1, w2, qw, qb, kw, vw, vb, pw, pb, g1, be1, f1w, f1b, f2w, f2b, g2, be2) = params
+    f = getattr(c.cache, mode)
+    return f([qw, kw, vw], cd), f([pw], cd), f([f1w], cd), f([f2w], cd)
+
+
+def _swin_block_fwd_body(x, c, save, recast, *params):
+    """-> (out,) or (out, qkv, bias16, hidden, tab, ctx, lse, a, mean1, rstd1, h, m_pre, m_act, m2, mean2, rstd2)"""
+    (ls, w1, b1, w2, qw, qb, kw, vw, vb, pw, pb, g1, be1, f1w, f1b, f2w, f2b, g2, be2) = params
+    cd = x.dtype
+    C_ = x.shape[1]
+    wqkv, w_p, w_f1, w_f2 = _swin_operands(c, params, cd, "recast" if recast else "peek")
+    bqkv = cat_vec([(qb, C_), (None, C_), (vb, C_)], x.device)            # key has no bias (:417)
+    qkv = O.linear_fwd(x, wqkv, bias=bqkv)
+    bias16, hidden, tab = O.swin_cpb_fwd(c.coords, c.index, w1.detach(), b1.detach(), w2.detach(), c.heads, c.N)
+    lsv = ls.detach().reshape(-1)
+    q, k, v = qkv[:, :C_], qkv[:, C_:2 * C_], qkv[:, 2 * C_:]
+    ctxt, lse = O.swin_attention_fwd(q, k, v, c.B, c.res, c.heads, c.hd, c.w, c.shift, lsv, bias16)
+    a = O.linear_fwd(ctxt, w_p, bias=pb)
+    h, mean1, rstd1 = O.layernorm_fwd(a, g1, be1, c.eps, residual=x, save_stats=save)       # res-post-norm (:707-708)
+    m_pre = torch.empty(x.shape[0], 4 * C_, dtype=cd, device=x.device) if save else None
+    m_act = O.linear_fwd(h, w_f1, bias=f1b, act=L.ACT_GELU, aux_out=m_pre)
+    m2 = O.linear_fwd(m_act, w_f2, bias=f2b)
+    out, mean2, rstd2 = O.layernorm_fwd(m2, g2, be2, c.eps, residual=h, save_stats=save)      # :712
+    if not save:
+        return (out,)
+    return (out, qkv, bias16, hidden, tab, ctxt, lse, a, mean1, rstd1, h, m_pre, m_act, m2, mean2, rstd2)
+
+
+def _swin_block_bwd_body(dout, x, qkv, bias16, hidden, tab, ctxt, lse, a, mean1, rstd1, h, m_pre, m_act, m2, mean2, rstd2, c, *params):
+    (ls, w1, b1, w2, qw, qb, kw, vw, vb, pw, pb, g1, be1, f1w, f1b, f2w, f2b, g2, be2) = params
+    cd = x.dtype
+    C_ = x.shape[1]
+    wqkv, w_p, w_f1, w_f2 = _swin_operands(c, params, cd, "peek")
+    dm2, dg2, dbe2 = O.layernorm_bwd(dout, m2, g2, mean2, rstd2)
+    dm_pre = O.linear_dgrad(dm2, w_f2, act=L.ACT_GELU_BWD, aux_in=m_pre)
+    df2w = O.linear_wgrad(dm2, m_act)
+    df2b = O.colsum(dm2)
+    dh = O.linear_dgrad(dm_pre, w_f1, residual=dout)                     # + residual path of the second norm
+    df1w = O.linear_wgrad(dm_pre, h)
+    df1b = O.colsum(dm_pre)
+    da, dg1, dbe1 = O.layernorm_bwd(dh, a, g1, mean1, rstd1)
+    dctx = O.linear_dgrad(da, w_p)
+    dpw = O.linear_wgrad(da, ctxt)
+    dpb = O.colsum(da)
+    dqkv = torch.empty_like(qkv)
+    q, k, v = qkv[:, :C_], qkv[:, C_:2 * C_], qkv[:, 2 * C_:]
+    lsv = ls.detach().reshape(-1)
+    dbias, dls = O.swin_attention_bwd(q, k, v, ctxt, dctx, dqkv[:, :C_], dqkv[:, C_:2 * C_], dqkv[:, 2 * C_:], c.B, c.res,
+                                      c.heads, c.hd, c.w, c.shift, lsv, bias16, lse)
+    dw1, db1, dw2 = O.swin_cpb_bwd(c.coords, c.index, w2.detach(), hidden, tab, dbias, c.heads, c.N)
+    dx = O.linear_dgrad(dqkv, wqkv, residual=dh)                          # + residual path of the first norm
+    dwqkv = O.linear_wgrad(dqkv, x)
+    dbqkv = O.colsum(dqkv)
+    return (dx, dls.view(ls.shape), dw1, db1, dw2, dwqkv[:C_], dbqkv[:C_], dwqkv[C_:2 * C_], dwqkv[2 * C_:], dbqkv[2 * C_:],
+            dpw, dpb, dg1, dbe1, df1w, df1b, df2w, df2b, dg2, dbe2)
+
+
 class SwinBlockFn(torch.autograd.Function):
     """One Swinv2Layer (:662-715) with Swinv2SelfAttention (:421-487) inlined.
     params: logit_scale, cpb_w1, cpb_b1, cpb_w2, q_w, q_b, k_w, v_w, v_b, proj_w, proj_b, ln1_w, ln1_b, fc1_w, fc1_b, fc2_w, fc2_b,
@@ -396,62 +577,31 @@ class SwinBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, c, x, *params):
-        (ls, w1, b1, w2, qw, qb, kw, vw, vb, pw, pb, g1, be1, f1w, f1b, f2w, f2b, g2, be2) = params
-        cd = x.dtype
-        cache = c.cache
-        C_ = x.shape[1]
-        wqkv = cache.get([qw, kw, vw], cd)
-        bqkv = cat_vec([(qb, C_), (None, C_), (vb, C_)], x.device)            # key has no bias (:417)
-        qkv = O.linear_fwd(x, wqkv, bias=bqkv)
-        bias16, hidden, tab = O.swin_cpb_fwd(c.coords, c.index, w1.detach(), b1.detach(), w2.detach(), c.heads, c.N)
-        lsv = ls.detach().reshape(-1)
-        q, k, v = qkv[:, :C_], qkv[:, C_:2 * C_], qkv[:, 2 * C_:]
-        ctxt, lse = O.swin_attention_fwd(q, k, v, c.B, c.res, c.heads, c.hd, c.w, c.shift, lsv, bias16)
-        a = O.linear_fwd(ctxt, cache.get([pw], cd), bias=pb)
         save = _needs_grad((x,) + tuple(params))
-        h, mean1, rstd1 = O.layernorm_fwd(a, g1, be1, c.eps, residual=x, save_stats=save)       # res-post-norm (:707-708)
-        m_pre = torch.empty(x.shape[0], 4 * C_, dtype=cd, device=x.device) if save else None
-        m_act = O.linear_fwd(h, cache.get([f1w], cd), bias=f1b, act=L.ACT_GELU, aux_out=m_pre)
-        m2 = O.linear_fwd(m_act, cache.get([f2w], cd), bias=f2b)
-        out, mean2, rstd2 = O.layernorm_fwd(m2, g2, be2, c.eps, residual=h, save_stats=save)      # :712
+        trainable = save and any(p.requires_grad for p in params)
+        if not trainable:
+            _swin_operands(c, params, x.dtype, "get")
+        x = x.contiguous()
+        outs, graphed = POOL.run(("swf", id(c), save), _swin_block_fwd_body, (x,), (c, save, trainable) + tuple(params),
+                                 allow_graph=not c.busy)
         if save:
             ctx.c = c
+            ctx.graphed = graphed
             ctx.save_for_backward(x, *params)
-            ctx.acts = (qkv, bias16, hidden, tab, ctxt, lse, a, mean1, rstd1, h, m_pre, m_act, m2, mean2, rstd2)
-        return out
+            ctx.acts = outs[1:]
+            if graphed:
+                c.busy = True
+                ctx.token = _Token(c)
+        return outs[0]
 
     @staticmethod
     def backward(ctx, dout):
         c = ctx.c
         x, *params = ctx.saved_tensors
-        (ls, w1, b1, w2, qw, qb, kw, vw, vb, pw, pb, g1, be1, f1w, f1b, f2w, f2b, g2, be2) = params
-        qkv, bias16, hidden, tab, ctxt, lse, a, mean1, rstd1, h, m_pre, m_act, m2, mean2, rstd2 = ctx.acts
-        ctx.acts = None
-        cd = x.dtype
-        cache = c.cache
-        C_ = x.shape[1]
-        dout = dout.contiguous()
-        dm2, dg2, dbe2 = O.layernorm_bwd(dout, m2, g2, mean2, rstd2)
-        w_f2, w_f1, w_p, wqkv = cache.get([f2w], cd), cache.get([f1w], cd), cache.get([pw], cd), cache.get([qw, kw, vw], cd)
-        dm_pre = O.linear_dgrad(dm2, w_f2, act=L.ACT_GELU_BWD, aux_in=m_pre)
-        df2w = O.linear_wgrad(dm2, m_act)
-        df2b = O.colsum(dm2)
-        dh = O.linear_dgrad(dm_pre, w_f1, residual=dout)                     # + residual path of the second norm
-        df1w = O.linear_wgrad(dm_pre, h)
-        df1b = O.colsum(dm_pre)
-        da, dg1, dbe1 = O.layernorm_bwd(dh, a, g1, mean1, rstd1)
-        dctx = O.linear_dgrad(da, w_p)
-        dpw = O.linear_wgrad(da, ctxt)
-        dpb = O.colsum(da)
-        dqkv = torch.empty_like(qkv)
-        q, k, v = qkv[:, :C_], qkv[:, C_:2 * C_], qkv[:, 2 * C_:]
-        lsv = ls.detach().reshape(-1)
-        dbias, dls = O.swin_attention_bwd(q, k, v, ctxt, dctx, dqkv[:, :C_], dqkv[:, C_:2 * C_], dqkv[:, 2 * C_:], c.B, c.res,
-                                          c.heads, c.hd, c.w, c.shift, lsv, bias16, lse)
-        dw1, db1, dw2 = O.swin_cpb_bwd(c.coords, c.index, w2.detach(), hidden, tab, dbias, c.heads, c.N)
-        dx = O.linear_dgrad(dqkv, wqkv, residual=dh)                          # + residual path of the first norm
-        dwqkv = O.linear_wgrad(dqkv, x)
-        dbqkv = O.colsum(dqkv)
-        grads = (dls.view(ls.shape), dw1, db1, dw2, dwqkv[:C_], dbqkv[:C_], dwqkv[C_:2 * C_], dwqkv[2 * C_:], dbqkv[2 * C_:],
-                 dpw, dpb, dg1, dbe1, df1w, df1b, df2w, df2b, dg2, dbe2)
-        return (None, dx) + grads
+        acts, ctx.acts = ctx.acts, None
+        if ctx.graphed:
+            _detach_aliased_grads(params)
+        outs, _ = POOL.run(("swb", id(c)), _swin_block_bwd_body, (dout.contiguous(), x) + tuple(acts), (c,) + tuple(params),
+                           allow_graph=ctx.graphed)
+        c.busy = False
+        return (None,) + tuple(outs)

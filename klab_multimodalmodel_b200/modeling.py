@@ -218,6 +218,9 @@ class T5Stack(nn.Module):
         self.block = nn.ModuleList([_T5Block(cfg, is_decoder, i == 0) for i in range(n)])
         self.final_layer_norm = _P(cfg.d_model)
         self._luts: dict = {}
+        self._ctxs: dict = {}
+        _STACK_COUNT[0] += 1
+        self.seed_base = _STACK_COUNT[0] * 100003               # distinct dropout streams per stack / block / site
 
     def lut(self, L_, device):
         key = (L_, device)
@@ -228,31 +231,47 @@ class T5Stack(nn.Module):
             self._luts[key] = (lut.to(device), rz)
         return self._luts[key]
 
+    def block_ctx(self, i, B, L_, Le, p, cache, device, cd):
+        """One cached Ctx per (block, shape signature): its identity keys the block's CUDA graphs."""
+        key = (i, B, L_, Le, p, device, cd)
+        c = self._ctxs.get(key)
+        if c is None:
+            cfg = self.cfg
+            lut, rz = self.lut(L_, device)
+            c = self._ctxs[key] = Ctx(cache=cache, is_decoder=self.is_decoder, B=B, L=L_, Le=Le, H=cfg.num_heads, dk=cfg.d_kv,
+                                      eps=cfg.layer_norm_epsilon, num_buckets=cfg.relative_attention_num_buckets, lut=lut, rz=rz, p=p,
+                                      seed=self.seed_base + 16 * (i + 1), seed_ptr=step_seed(device) if p > 0 else None)
+        return c
+
     def run_blocks(self, x, B, L_, cache: OperandCache, enc_out=None, Le=0):
         """x: [B*L, d] in the compute dtype -> hidden state BEFORE final_layer_norm."""
         cfg = self.cfg
         p = cfg.dropout_rate if self.training else 0.0
-        lut, rz = self.lut(L_, x.device)
         table = self.block[0].layer[0].SelfAttention.relative_attention_bias.weight
-        seed = _new_seed() if p > 0 else 0
         if p > 0:                                                       # dropout on the stack input (:734)
-            x = Fn.apply_fn(DropoutFn, x, p, seed)
+            x = Fn.apply_fn(Fn.DropoutFn, x, p, self.seed_base, step_seed(x.device))
         for i, blk in enumerate(self.block):
-            c = Ctx(cache=cache, is_decoder=self.is_decoder, B=B, L=L_, Le=Le, H=cfg.num_heads, dk=cfg.d_kv, eps=cfg.layer_norm_epsilon,
-                    num_buckets=cfg.relative_attention_num_buckets, lut=lut, rz=rz, p=p, seed=(seed + 16 * (i + 1)) & ((1 << 62) - 1))
+            c = self.block_ctx(i, B, L_, Le, p, cache, x.device, x.dtype)
             x = Fn.apply_fn(Fn.T5BlockFn, c, x, enc_out, table, *blk.flat_params())
         return x
 
 
-class DropoutFn(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, p, seed):
-        ctx.p, ctx.seed = p, seed
-        return O.dropout_apply(x, p, seed)
+_STEP_SEEDS: dict = {}
+_STACK_COUNT = [0]
 
-    @staticmethod
-    def backward(ctx, dy):
-        return O.dropout_apply(dy, ctx.p, ctx.seed), None, None
+
+def step_seed(device) -> torch.Tensor:
+    """Per-device dropout counter living on the GPU: every dropout site hashes (its own constant + this counter, element
+    index); `advance_step_seed` steps it once per training forward (klab_seed_advance), CUDA graphs replay unchanged."""
+    key = (device.type, device.index)
+    t = _STEP_SEEDS.get(key)
+    if t is None:
+        t = _STEP_SEEDS[key] = torch.tensor([random.getrandbits(62)], dtype=torch.int64, device=device)
+    return t
+
+
+def advance_step_seed(device) -> None:
+    O.seed_advance(step_seed(device))
 
 
 class T5EncoderModel(nn.Module):
@@ -314,13 +333,14 @@ class T5ForConditionalGeneration(nn.Module):
         enc = self.encoder.run_blocks(embeds, B, Le, self.cache)
         enc = Fn.apply_fn(Fn.RMSNormFn, enc, self.encoder.final_layer_norm.weight, cfg.layer_norm_epsilon)
         p = cfg.dropout_rate if self.training else 0.0
+        sp = step_seed(embeds.device) if p > 0 else None
         if p > 0:
-            enc = Fn.apply_fn(DropoutFn, enc, p, _new_seed())                 # :768
+            enc = Fn.apply_fn(Fn.DropoutFn, enc, p, self.encoder.seed_base + 7, sp)     # :768
         labels = labels.contiguous()
         dec_in = Fn.apply_fn(Fn.DecoderEmbedFn, labels, self.shared.weight, self.cache, cd, cfg.decoder_start_token_id, cfg.pad_token_id)
         dec = self.decoder.run_blocks(dec_in, B, Lt, self.cache, enc_out=enc, Le=Le)
         return Fn.apply_fn(Fn.LMHeadLossFn, dec, self.decoder.final_layer_norm.weight, self.shared.weight, labels, self.cache,
-                                     cfg.layer_norm_epsilon, p, _new_seed() if p > 0 else 0)
+                           cfg.layer_norm_epsilon, p, self.decoder.seed_base + 7, sp)
 
 
 def init_t5_(m: nn.Module, seed: int | None = None):
@@ -420,6 +440,7 @@ class Swinv2Model(nn.Module):
         self.layernorm = _P(self.num_features, bias=True)
         self.cache = OperandCache()
         self._tables: dict = {}
+        self._ctxs: dict = {}
         init_swin_(self)
 
     @classmethod
@@ -457,8 +478,11 @@ class Swinv2Model(nn.Module):
             coords, index = self.tables(w, cfg.pretrained_window_sizes[s], x.device)
             for i, blk in enumerate(stage.blocks):
                 shift = 0 if (i % 2 == 0 or res <= w) else cfg.window_size // 2
-                c = Ctx(cache=self.cache, B=B, res=res, heads=heads, hd=dim // heads, w=w, shift=shift, N=w * w, coords=coords,
-                        index=index, eps=cfg.layer_norm_eps)
+                key = (s, i, B, res, x.device, cd)
+                c = self._ctxs.get(key)
+                if c is None:
+                    c = self._ctxs[key] = Ctx(cache=self.cache, B=B, res=res, heads=heads, hd=dim // heads, w=w, shift=shift, N=w * w,
+                                              coords=coords, index=index, eps=cfg.layer_norm_eps)
                 x = Fn.apply_fn(Fn.SwinBlockFn, c, x, *blk.flat_params())
             if stage.downsample is not None:
                 d = stage.downsample

@@ -19,7 +19,7 @@ from torch import nn
 
 from .. import functional as Fn
 from ..generation import greedy_generate
-from ..modeling import Swinv2Model, T5EncoderModel, T5ForConditionalGeneration, _compute_dtype
+from ..modeling import Swinv2Model, T5EncoderModel, T5ForConditionalGeneration, _compute_dtype, advance_step_seed
 
 
 class MyModel(nn.Module):
@@ -54,6 +54,8 @@ class MyModel(nn.Module):
         return emb, B, n_img + src.shape[1]
 
     def forward(self, images, source_encoding, target_encoding=None, return_loss=True):
+        if self.transformer.training and not Fn.pending_backward():
+            advance_step_seed(images["pixel_values"].device)          # fresh dropout masks for this step (device-side counter)
         emb, B, Le = self._concat_embeddings(images, source_encoding)
         if return_loss:
             return self.transformer.loss_from_embeds(emb, B, Le, target_encoding["input_ids"])
