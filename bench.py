@@ -189,7 +189,7 @@ def run_reference(args, w):
                          "sample": f"{sample} samples/step of the same model + sequence lengths, fwd+bwd+Adam, torch fp32, {cores} threads"},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -284,7 +284,8 @@ def run_ours(args, w):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=int(os.environ.get("KLAB_NCCL_TIMEOUT_S", "600"))))
     L.check(L.lib().klab_check_device())
     model, tcfg = build_model(w, dev, args.dtype)
     model.transformer.train()                                        # train.py:52
@@ -298,7 +299,13 @@ def run_ours(args, w):
     h2d = px_h.numel() * 4 + src_h.numel() * 8 + tgt_h.numel() * 8
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)    # > 126 MB L2
 
+    wd = int(os.environ.get("KLAB_BENCH_WATCHDOG_S", "0"))          # debugging aid: dump every thread's stack if a step stalls
+    if wd:
+        import faulthandler
+
     def step(px, src, tgt, read_loss=True):
+        if wd:
+            faulthandler.dump_traceback_later(wd, exit=True)
         loss = net({"pixel_values": px}, {"input_ids": src}, {"input_ids": tgt})
         lv = loss.item() if read_loss else None                          # train.py:59 reads the loss every step
         loss.backward()
@@ -353,7 +360,17 @@ def run_ours(args, w):
     value = world * B / (ms_step * 1e-3)
     e2e_val = world * B / (ms_e2e / args.steps * 1e-3)
     pk = peaks()
-    roof = gemm_roofline(lambda: step(px_d, src_d, tgt_d), pk, verbose=args.verbose) if rank == 0 else None
+    if world > 1:                                       # collectives are over: what follows is rank-0-local reporting
+        dist.barrier()
+        dist.destroy_process_group()
+    def local_step():                                   # rank-local (no DDP collectives): only rank 0 runs the roofline probe
+        loss = model({"pixel_values": px_d}, {"input_ids": src_d}, {"input_ids": tgt_d})
+        loss.backward()
+        opt.zero_grad()
+
+    if wd:
+        faulthandler.cancel_dump_traceback_later()
+    roof = gemm_roofline(local_step, pk, verbose=args.verbose) if rank == 0 else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sb = args.cpu_sample_batch
@@ -378,9 +395,21 @@ def run_ours(args, w):
             "step_model_tflops": step_tflops, "step_frac_of_peak": step_tflops / pk["tflops"], "loss": loss_v,
             "cuda_graphs": POOL.stats(),
         }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything else written to fd 1 meanwhile (e.g. NCCL's version banner) was
+    diverted to stderr by `main`."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
 
 
 def main():
@@ -396,6 +425,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     args = ap.parse_args()
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                                  # libraries that print to stdout (NCCL banner) must not pollute the JSON line
     w = dict(WORKLOADS[args.workload])
     if args.batch:
         w["batch"] = args.batch
