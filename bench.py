@@ -214,11 +214,12 @@ def build_model(w, device, dtype):
     return model.to(device), tcfg
 
 
-def gemm_roofline(model_step, pk, verbose=False):
+def gemm_roofline(model_step, pk, verbose=False, check=False):
     """Roofline of the dominant kernel family (tcgen05 GEMM): (1) run one step eagerly and record the signature of every GEMM
-    launch (M, N, K, operand majors, output dtype); (2) launch each distinct signature back to back on the current stream,
-    rotating over operand copies that together exceed the 126 MB L2, timed with CUDA events; (3) achieved = sum of algorithmic
-    FLOPs (2 M N K) of the step's launches / sum(count x measured duration)."""
+    launch (M, N, K, operand majors, output dtype AND the fused epilogue: bias / activation / residual / aux tensors / dropout /
+    accumulate); (2) launch each distinct signature back to back on the current stream with that same epilogue, rotating over
+    operand copies that together exceed the 126 MB L2, timed with CUDA events; (3) achieved = sum of algorithmic FLOPs (2 M N K)
+    of the step's launches / sum(count x measured duration)."""
     import collections
 
     from klab_multimodalmodel_b200 import ops as O
@@ -229,7 +230,10 @@ def gemm_roofline(model_step, pk, verbose=False):
     def rec(a, b, M, N, K, **kw):
         out = orig(a, b, M, N, K, **kw)
         if a.dtype == torch.bfloat16:
-            sigs[(M, N, K, bool(kw.get("a_mn")), bool(kw.get("b_mn")), out.dtype)] += 1
+            res, ain, aout = kw.get("residual"), kw.get("aux_in"), kw.get("aux_out")
+            sigs[(M, N, K, bool(kw.get("a_mn")), bool(kw.get("b_mn")), out.dtype, kw.get("bias") is not None, int(kw.get("act", 0)),
+                  None if res is None else res.dtype, None if ain is None else ain.dtype, aout is not None,
+                  float(kw.get("dropout_p", 0.0)), bool(kw.get("accumulate", False)), out.stride(0))] += 1
         return out
 
     was = POOL.enabled
@@ -241,37 +245,75 @@ def gemm_roofline(model_step, pk, verbose=False):
         O.gemm, POOL.enabled = orig, was
     tot_ms, tot_fl, rows = 0.0, 0.0, []
     dev = torch.device("cuda", torch.cuda.current_device())
-    for (M, N, K, a_mn, b_mn, od), cnt in sigs.items():
-        per = (M * K + N * K) * 2 + M * N * (2 if od == torch.bfloat16 else 4)
+    seedp = torch.zeros(1, dtype=torch.int64, device=dev)
+    for sig, cnt in sigs.items():
+        M, N, K, a_mn, b_mn, od, has_bias, act, res_dt, ain_dt, has_aout, p_drop, acc, ldd = sig
+        esz = 2 if od == torch.bfloat16 else 4
+        per = (M * K + N * K) * 2 + M * ldd * esz * (1 + (res_dt is not None) + (ain_dt is not None) + has_aout)
         copies = max(1, min(8, (300 << 20) // max(per, 1)))
         As = [torch.randn((K, M) if a_mn else (M, K), device=dev).bfloat16() for _ in range(copies)]
         Bs = [torch.randn((K, N) if b_mn else (N, K), device=dev).bfloat16() for _ in range(copies)]
-        Ds = [torch.empty(M, N, device=dev, dtype=od) for _ in range(copies)]
+        Ds = [torch.zeros(M, ldd, device=dev, dtype=od)[:, :N] for _ in range(copies)]
+        kws = []
+        for i in range(copies):
+            kw = dict(a_mn=a_mn, b_mn=b_mn, out=Ds[i], act=act, dropout_p=p_drop, accumulate=acc, seed=5, seed_ptr=seedp if p_drop > 0 else None)
+            if has_bias:
+                kw["bias"] = torch.randn(N, device=dev)
+            if res_dt is not None:
+                kw["residual"] = torch.randn(M, N, device=dev).to(res_dt)
+            if ain_dt is not None:
+                kw["aux_in"] = torch.randn(M, N, device=dev).to(ain_dt)
+            if has_aout:
+                kw["aux_out"] = torch.empty(M, N, device=dev, dtype=od)
+            kws.append(kw)
         for i in range(3):
-            orig(As[i % copies], Bs[i % copies], M, N, K, a_mn=a_mn, b_mn=b_mn, out=Ds[i % copies])
+            orig(As[i % copies], Bs[i % copies], M, N, K, **kws[i % copies])
         iters = 8
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()                      # replay from a CUDA graph, as the step does: no host launch cost in the timing
+        with torch.cuda.graph(g):
+            for i in range(iters):
+                orig(As[i % copies], Bs[i % copies], M, N, K, **kws[i % copies])
+        g.replay()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        for i in range(iters):
-            orig(As[i % copies], Bs[i % copies], M, N, K, a_mn=a_mn, b_mn=b_mn, out=Ds[i % copies])
+        g.replay()
         e.record()
         torch.cuda.synchronize()
         ms = s.elapsed_time(e) / iters
+        del g
+        err = None
+        if check and p_drop == 0.0 and not acc and act in (0, 1, 2):
+            kw = dict(kws[0]); D = torch.zeros(M, ldd, device=dev, dtype=od)[:, :N]; kw["out"] = D
+            orig(As[0], Bs[0], M, N, K, **kw)
+            A32 = As[0].float().t() if a_mn else As[0].float()
+            B32 = Bs[0].float() if b_mn else Bs[0].float().t()
+            ref = A32 @ B32
+            if has_bias:
+                ref = ref + kw["bias"]
+            if act == 1:
+                ref = torch.relu(ref)
+            elif act == 2:
+                ref = torch.nn.functional.gelu(ref)
+            if res_dt is not None:
+                ref = ref + kw["residual"].float()
+            err = ((D.float() - ref).abs().max() / ref.abs().max().clamp_min(1e-6)).item()
         fl = 2.0 * M * N * K
         tot_ms += cnt * ms
         tot_fl += cnt * fl
-        rows.append((cnt * ms, cnt, M, N, K, int(a_mn), int(b_mn), ms, fl / ms / 1e9))
-        del As, Bs, Ds
+        rows.append((cnt * ms, cnt, M, N, K, int(a_mn), int(b_mn), ms, fl / ms / 1e9, sig[6:13], err))
+        del As, Bs, Ds, kws
     if verbose:
-        for r in sorted(rows, reverse=True)[:30]:
-            print("gemm sig: total %.2f ms  x%d  M=%d N=%d K=%d a_mn=%d b_mn=%d  %.1f us  %.0f TFLOP/s" %
-                  (r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7] * 1e3, r[8]), file=sys.stderr)
+        for r in sorted(rows, reverse=True)[:(200 if check else 40)]:
+            print("gemm sig: total %.2f ms  x%d  M=%d N=%d K=%d a_mn=%d b_mn=%d  %.1f us  %.0f TFLOP/s  epi(bias,act,res,auxin,auxout,p,acc)=%s%s" %
+                  (r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7] * 1e3, r[8], r[9], "" if r[10] is None else "  relerr %.2e" % r[10]),
+                  file=sys.stderr)
     ach = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
     return {"bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None,
             "kernel": "gemm_bf16_tc_kernel (tcgen05)", "launches_per_step": int(sum(sigs.values())), "distinct_shapes": len(sigs),
             "gemm_ms_per_step": tot_ms, "gemm_gflop_per_step": tot_fl / 1e9, "peak_source": pk["source"] + " bf16 sustained",
-            "method": "every GEMM signature of one step replayed back to back (operands rotated beyond L2), CUDA events; "
-                      "epilogue extras (bias/activation/residual reads) not replayed"}
+            "method": "every GEMM signature of one step (shape, operand majors and fused epilogue: bias / activation / residual / "
+                      "aux tensors / dropout) replayed back to back from a CUDA graph, operands rotated beyond L2, CUDA events"}
 
 
 def run_ours(args, w):
@@ -296,6 +338,15 @@ def run_ours(args, w):
     opt = torch.optim.Adam(model.transformer.parameters(), lr=1e-4)
     px_h, src_h, tgt_h = synth_batch(w, tcfg.vocab_size, 1234 + rank, pin=True)
     px_d, src_d, tgt_d = px_h.to(dev), src_h.to(dev), tgt_h.to(dev)
+    if args.gemm_probe:
+        def probe_step():
+            loss = model({"pixel_values": px_d}, {"input_ids": src_d}, {"input_ids": tgt_d})
+            loss.backward()
+            opt.zero_grad()
+        probe_step()
+        r = gemm_roofline(probe_step, peaks(), verbose=True, check=True)
+        emit(r)
+        return
     h2d = px_h.numel() * 4 + src_h.numel() * 8 + tgt_h.numel() * 8
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)    # > 126 MB L2
 
@@ -424,6 +475,7 @@ def main():
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--gemm-probe", action="store_true", help="development aid: only replay (and check) the step's GEMM signatures")
     args = ap.parse_args()
     global _REAL_STDOUT
     sys.stdout.flush()

@@ -70,29 +70,101 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// exact (erf) GELU, as HF `hidden_act="gelu"` (configuration_swinv2.py:69)
+// exact (erf) GELU, as HF `hidden_act="gelu"` (configuration_swinv2.py:69).  erfc is evaluated with the Abramowitz-Stegun
+// 7.1.26 rational form (|error| <= 1.5e-7, i.e. fp32 rounding level): erfc(z) = poly(t) exp(-z^2), t = 1 / (1 + p z), z >= 0.
+// It is branch free and costs one MUFU.RCP + one MUFU.EX2, which matters because the GEMM epilogue that applies it is
+// instruction-issue bound (libdevice erff is ~40 instructions with two divergent branches).  GELU' reuses the same
+// exponential: phi(x) = exp(-x^2 / 2) / sqrt(2 pi) and exp(-z^2) with z = |x| / sqrt(2) are the same number.
+__device__ __forceinline__ void gelu_terms(float x, float& half_erfc, float& u) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    u = __expf(-z * z);
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    half_erfc = 0.5f * poly * t * u;                       // 0.5 * erfc(|x| / sqrt 2) = 1 - Phi(|x|)
+}
+#ifdef KLAB_EXACT_GELU
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
     const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
     const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
     return cdf + x * pdf;
 }
+#else
+__device__ __forceinline__ float gelu_erf(float x) {
+    float q, u;
+    gelu_terms(x, q, u);
+    return x * (x >= 0.0f ? 1.0f - q : q);                 // x * Phi(x)
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+    float q, u;
+    gelu_terms(x, q, u);
+    const float cdf = x >= 0.0f ? 1.0f - q : q;
+    return fmaf(x * 0.39894228040143267794f, u, cdf);      // Phi(x) + x phi(x)
+}
+#endif
 
-// Counter-based dropout RNG: keep(element) is a pure function of (seed, site, element index), so the
-// backward pass regenerates the forward mask without storing it.
-__device__ __forceinline__ uint32_t hash_u32(uint64_t seed, uint64_t idx) {
-    uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+// Counter-based dropout RNG: keep(element) is a pure function of (seed, element index), so the backward pass regenerates
+// the forward mask without storing it.  The generator is cheap on purpose (the kernels that apply it are issue bound):
+// one 64-bit mix of the seed per THREAD gives two 32-bit keys; one 32-bit hash per PAIR of elements gives two 16-bit
+// uniforms.  keep probability = thr16 / 65536 and the survivors are scaled by exactly 65536 / thr16, so E[mask] = 1.
+struct DropKey {
+    uint32_t k0, k1;
+    uint32_t thr16;       // keep iff 16-bit uniform < thr16
+    float inv_keep;
+    bool on;
+};
+__host__ __device__ inline uint32_t dropout_thr16(float p) {
+    const double keep = 1.0 - static_cast<double>(p);
+    uint32_t t = static_cast<uint32_t>(keep * 65536.0 + 0.5);
+    return t > 65536u ? 65536u : (t < 1u ? 1u : t);
+}
+__device__ __forceinline__ DropKey make_drop_key(uint64_t seed, float p) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     z = z ^ (z >> 31);
-    return static_cast<uint32_t>(z >> 32);
+    DropKey k;
+    k.k0 = static_cast<uint32_t>(z);
+    k.k1 = static_cast<uint32_t>(z >> 32);
+    k.on = p > 0.0f;
+    k.thr16 = k.on ? dropout_thr16(p) : 65536u;
+    k.inv_keep = k.on ? 65536.0f / static_cast<float>(k.thr16) : 1.0f;
+    return k;
 }
-__host__ __device__ inline uint32_t make_dropout_thr(float p) {
-    return p > 0.0f ? static_cast<uint32_t>((1.0 - static_cast<double>(p)) * 4294967295.0) : 0xFFFFFFFFu;
+// 32 random bits for the element pair (2*pair, 2*pair + 1)
+__device__ __forceinline__ uint32_t drop_hash_pair(const DropKey& k, uint64_t pair) {
+    uint32_t x = static_cast<uint32_t>(pair) ^ k.k0;
+    x += static_cast<uint32_t>(pair >> 32) * 0x9E3779B9u;
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15; x *= 0x846CA68Bu;
+    x ^= x >> 16; x ^= k.k1;
+    x *= 0x9E3779B1u;
+    x ^= x >> 15;
+    return x;
 }
-// returns the multiplier to apply: 0 or 1/(1-p)
-__device__ __forceinline__ float dropout_scale(uint64_t seed, uint64_t idx, uint32_t keep_threshold, float inv_keep) {
-    return hash_u32(seed, idx) < keep_threshold ? inv_keep : 0.0f;
+// multiplier of one element: 0 or 1 / keep
+__device__ __forceinline__ float dropout_mult(const DropKey& k, uint64_t idx) {
+    const uint32_t h = drop_hash_pair(k, idx >> 1);
+    const uint32_t u = (idx & 1) ? (h >> 16) : (h & 0xFFFFu);
+    return u < k.thr16 ? k.inv_keep : 0.0f;
+}
+// v[i] *= multiplier(base + i) for CH consecutive elements (CH even); one hash per pair when base is even
+template <int CH>
+__device__ __forceinline__ void dropout_apply_run(const DropKey& k, uint64_t base, float (&v)[CH]) {
+    if ((base & 1) == 0) {
+#pragma unroll
+        for (int i = 0; i < CH; i += 2) {
+            const uint32_t h = drop_hash_pair(k, (base + i) >> 1);
+            v[i] *= (h & 0xFFFFu) < k.thr16 ? k.inv_keep : 0.0f;
+            v[i + 1] *= (h >> 16) < k.thr16 ? k.inv_keep : 0.0f;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < CH; ++i) v[i] *= dropout_mult(k, base + i);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -166,6 +238,22 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256); the address must be 32-byte aligned
+__device__ __forceinline__ void ld_global_v8(const void* p, uint32_t (&r)[8]) {
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&r)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]),
+                 "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start while its
+// predecessor is still running; it must not touch global memory the predecessor reads or writes before pdl_wait().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // --- TMEM allocation ---
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
@@ -203,6 +291,16 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
 }

@@ -194,11 +194,25 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(T* __restrict__ logits, lon
 // y[i] = x[i] * keep(seed, i) / (1 - p): regenerates the mask a GEMM epilogue applied to element (row*N + col)
 template <typename T>
 __global__ void dropout_apply_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, unsigned long long seed,
-                                     const unsigned long long* __restrict__ seed_ptr, uint32_t thr, float inv_keep) {
+                                     const unsigned long long* __restrict__ seed_ptr, float p) {
     if (seed_ptr) seed += *seed_ptr;
+    const DropKey key = make_drop_key(seed, p);
+    const long long npairs = (n + 1) / 2;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
-        y[i] = from_f32<T>(to_f32(x[i]) * dropout_scale(seed, static_cast<uint64_t>(i), thr, inv_keep));
+    for (long long pr = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; pr < npairs; pr += stride) {
+        const uint32_t h = drop_hash_pair(key, static_cast<uint64_t>(pr));
+        const long long i = 2 * pr;
+        const float m0 = (h & 0xFFFFu) < key.thr16 ? key.inv_keep : 0.0f;
+        const float m1 = (h >> 16) < key.thr16 ? key.inv_keep : 0.0f;
+        if (i + 1 < n && sizeof(T) == 2) {
+            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(x + i);
+            const float2 f = __bfloat1622float2(v);
+            *reinterpret_cast<__nv_bfloat162*>(y + i) = __floats2bfloat162_rn(f.x * m0, f.y * m1);
+        } else {
+            y[i] = from_f32<T>(to_f32(x[i]) * m0);
+            if (i + 1 < n) y[i + 1] = from_f32<T>(to_f32(x[i + 1]) * m1);
+        }
+    }
 }
 
 // Greedy decode step (HF/generation/utils.py:2762-2800): next = argmax(fp32 logits row) (first index on ties);
@@ -357,12 +371,11 @@ int klab_dropout_apply(void* stream, int dtype, long long n, const void* x, void
     if (int rc = klab_check_device()) return rc;
     KLAB_REQUIRE(n > 0 && p >= 0.0f && p < 1.0f, "dropout_apply: bad arguments n=%lld p=%f", n, p);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const uint32_t thr = make_dropout_thr(p);
-    const float inv_keep = 1.0f / (1.0f - p);
+    KLAB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 3) == 0 && (reinterpret_cast<uintptr_t>(y) & 3) == 0, "dropout_apply: pointers must be 4-byte aligned");
     if (dtype == KLAB_BF16)
-        dropout_apply_kernel<__nv_bfloat16><<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), n, seed, seed_ptr, thr, inv_keep);
+        dropout_apply_kernel<__nv_bfloat16><<<grid_for(n, 256, 2), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), n, seed, seed_ptr, p);
     else
-        dropout_apply_kernel<float><<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const float*>(x), reinterpret_cast<float*>(y), n, seed, seed_ptr, thr, inv_keep);
+        dropout_apply_kernel<float><<<grid_for(n, 256, 2), 256, 0, st>>>(reinterpret_cast<const float*>(x), reinterpret_cast<float*>(y), n, seed, seed_ptr, p);
     KLAB_LAUNCH_CHECK();
     count_launch();
     return KLAB_OK;

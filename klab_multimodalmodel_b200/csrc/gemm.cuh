@@ -6,27 +6,24 @@
 
 namespace klab {
 
-struct EpiDropout {
-    uint32_t keep_threshold;
-    float inv_keep;
-    bool on;
-};
-
-__host__ __device__ inline EpiDropout make_dropout(float p) {
-    EpiDropout d;
-    d.on = p > 0.0f;
-    const double keep = 1.0 - static_cast<double>(p);
-    d.keep_threshold = d.on ? static_cast<uint32_t>(keep * 4294967295.0) : 0xFFFFFFFFu;
-    d.inv_keep = d.on ? static_cast<float>(1.0 / keep) : 1.0f;
-    return d;
-}
-
 // Load `CH` consecutive elements of a row into fp32 registers (vector path when aligned and full).
 template <int CH>
 __device__ __forceinline__ void load_chunk(const void* base, int dt, long long idx0, int nvalid, float (&out)[CH]) {
     if (dt == KLAB_BF16) {
         const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(base) + idx0;
-        if (CH % 8 == 0 && nvalid == CH && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        if (CH % 16 == 0 && nvalid == CH && (reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+#pragma unroll
+            for (int i = 0; i < CH / 16; ++i) {
+                uint32_t q[8];
+                ld_global_v8(p + i * 16, q);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q[j]));
+                    out[i * 16 + 2 * j] = f.x;
+                    out[i * 16 + 2 * j + 1] = f.y;
+                }
+            }
+        } else if (CH % 8 == 0 && nvalid == CH && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
 #pragma unroll
             for (int i = 0; i < CH / 8; ++i) {
                 const uint4 q = reinterpret_cast<const uint4*>(p)[i];
@@ -44,7 +41,15 @@ __device__ __forceinline__ void load_chunk(const void* base, int dt, long long i
         }
     } else {
         const float* p = reinterpret_cast<const float*>(base) + idx0;
-        if (nvalid == CH && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        if (CH % 8 == 0 && nvalid == CH && (reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+#pragma unroll
+            for (int i = 0; i < CH / 8; ++i) {
+                uint32_t q[8];
+                ld_global_v8(p + i * 8, q);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) out[i * 8 + j] = __uint_as_float(q[j]);
+            }
+        } else if (nvalid == CH && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
 #pragma unroll
             for (int i = 0; i < CH / 4; ++i) {
                 const float4 q = reinterpret_cast<const float4*>(p)[i];
@@ -61,7 +66,18 @@ template <int CH>
 __device__ __forceinline__ void store_chunk(void* base, int dt, long long idx0, int nvalid, const float (&v)[CH]) {
     if (dt == KLAB_BF16) {
         __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(base) + idx0;
-        if (CH % 8 == 0 && nvalid == CH && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        if (CH % 16 == 0 && nvalid == CH && (reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+#pragma unroll
+            for (int i = 0; i < CH / 16; ++i) {
+                uint32_t q[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(v[i * 16 + 2 * j], v[i * 16 + 2 * j + 1]);
+                    q[j] = *reinterpret_cast<const uint32_t*>(&h);
+                }
+                st_global_v8(p + i * 16, q);
+            }
+        } else if (CH % 8 == 0 && nvalid == CH && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
 #pragma unroll
             for (int i = 0; i < CH / 8; ++i) {
                 uint4 q;
@@ -77,7 +93,15 @@ __device__ __forceinline__ void store_chunk(void* base, int dt, long long idx0, 
         }
     } else {
         float* p = reinterpret_cast<float*>(base) + idx0;
-        if (nvalid == CH && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+        if (CH % 8 == 0 && nvalid == CH && (reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+#pragma unroll
+            for (int i = 0; i < CH / 8; ++i) {
+                uint32_t q[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) q[j] = __float_as_uint(v[i * 8 + j]);
+                st_global_v8(p + i * 8, q);
+            }
+        } else if (nvalid == CH && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
 #pragma unroll
             for (int i = 0; i < CH / 4; ++i)
                 reinterpret_cast<float4*>(p)[i] = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
@@ -91,15 +115,24 @@ __device__ __forceinline__ void store_chunk(void* base, int dt, long long idx0, 
 
 // Apply the epilogue to CH consecutive columns [col0, col0+nvalid) of output row `row` and store.
 template <int CH>
-__device__ __forceinline__ void epilogue_apply_store(const klab_gemm_epilogue& e, const EpiDropout& dr, float (&v)[CH],
+__device__ __forceinline__ void epilogue_apply_store(const klab_gemm_epilogue& e, const DropKey& dr, float (&v)[CH],
                                                      long long row, long long col0, int nvalid, int N,
                                                      void* D, long long ldd) {
 #pragma unroll
     for (int i = 0; i < CH; ++i) v[i] *= e.alpha;
     if (e.bias) {
+        const float* bp = e.bias + col0;
+        if (CH % 4 == 0 && nvalid == CH && (reinterpret_cast<uintptr_t>(bp) & 15) == 0) {
 #pragma unroll
-        for (int i = 0; i < CH; ++i)
-            if (i < nvalid) v[i] += __ldg(e.bias + col0 + i);
+            for (int i = 0; i < CH / 4; ++i) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + i);
+                v[i * 4] += b4.x; v[i * 4 + 1] += b4.y; v[i * 4 + 2] += b4.z; v[i * 4 + 3] += b4.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < CH; ++i)
+                if (i < nvalid) v[i] += __ldg(bp + i);
+        }
     }
     if (e.aux_out) store_chunk<CH>(e.aux_out, e.out_dtype, row * e.ld_aux_out + col0, nvalid, v);
     if (e.act == KLAB_ACT_RELU) {
@@ -121,8 +154,7 @@ __device__ __forceinline__ void epilogue_apply_store(const klab_gemm_epilogue& e
     }
     if (dr.on) {
         const uint64_t base = static_cast<uint64_t>(row) * static_cast<uint64_t>(N) + static_cast<uint64_t>(col0);
-#pragma unroll
-        for (int i = 0; i < CH; ++i) v[i] *= dropout_scale(e.dropout_seed, base + i, dr.keep_threshold, dr.inv_keep);
+        dropout_apply_run<CH>(dr, base, v);
     }
     if (e.residual) {
         float r[CH];

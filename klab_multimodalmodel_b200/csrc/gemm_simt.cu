@@ -51,8 +51,8 @@ gemm_simt_kernel(const T* __restrict__ A, long long sa_m, long long sa_k, const 
         }
         __syncthreads();
     }
-    const EpiDropout dr = make_dropout(epi.dropout_p);
-    if (dr.on && epi.dropout_seed_ptr) epi.dropout_seed += *epi.dropout_seed_ptr;
+    if (epi.dropout_p > 0.0f && epi.dropout_seed_ptr) epi.dropout_seed += *epi.dropout_seed_ptr;
+    const DropKey dr = make_drop_key(epi.dropout_seed, epi.dropout_p);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const long long row = m0 + ty * 4 + i;

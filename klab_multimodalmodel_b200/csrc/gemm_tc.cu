@@ -6,11 +6,28 @@
 // path (HF/models/swinv2/modeling_swinv2.py:535,578-579,591,385; HF/models/t5/modeling_t5.py:93-102,
 // 178-181,338,1110) for forward (both operands K-major), dgrad (B MN-major) and wgrad (A and B MN-major).
 //
-// Structure (persistent, one CTA per SM, 192 threads):
-//   warp 0      : TMA producer   -- cp.async.bulk.tensor tiles into a STAGES-deep smem ring (SWIZZLE_128B)
-//   warp 1      : MMA issuer     -- one elected lane issues tcgen05.mma (128 x BN x 16), commits to mbarriers
-//   warps 2..5  : epilogue       -- tcgen05.ld the 128 x BN fp32 tile out of TMEM, fused epilogue, global stores
-// Two TMEM accumulator stages (2 x BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+// Structure (persistent, one CTA per SM, 576 threads):
+//   warp 0       : TMA producer   -- cp.async.bulk.tensor tiles into a smem ring (SWIZZLE_128B), 4..8 stages
+//   warp 1       : MMA issuer     -- one elected lane issues tcgen05.mma (128 x BN x 16), commits to mbarriers
+//   warps 2..17  : epilogue       -- tcgen05.ld the 128 x BN fp32 tile out of TMEM, fused epilogue, global stores.
+//                                    Sixteen warps (four per TMEM sub-partition, each taking every fourth 16-column
+//                                    chunk) because the fused epilogues (GELU / GELU', ReLU' + dropout, residual) are
+//                                    instruction-issue bound: with one warp per scheduler the epilogue, not the MMA,
+//                                    paced every GEMM with K <= 1024.
+// Two TMEM accumulator stages (columns 0.. and 256..) let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// The N tile BN is a RUN-TIME parameter (multiple of 16, or of 64 when B is MN-major): with 148 SMs and tile counts
+// like 48 x 4, a fixed 256-wide tile leaves the second wave 70 % empty; BN = 176 gives 288 tiles = 1.95 waves.
+// The choice is made by a small cost model that knows the two things that actually bound this kernel on B200:
+// the MMA rate (128 x 256 x 16 per 128 cycles) and the L2 -> SM operand feed (~12.4 TB/s chip-wide, i.e. a
+// 128 x BN x 64 k-block needs (16 KiB + BN * 128 B) / 84 GB/s when all SMs pull at once).
+//
+// Split-K (weight gradients of tall-skinny activations): a work item is (output tile, K range).  Partial results go to an
+// fp32 workspace [split][M_pad][N_pad] with plain stores and a second, tiny kernel sums them in split order and runs the
+// epilogue -- deterministic, no atomics and no in-kernel fences (a gpu-scope fence inside a CTA that keeps seven TMA stages
+// in flight costs ~15 us per item; fp32 red.global.add tops out at ~0.8 TB/s).
+#include <cstdlib>
+
 #include "gemm.cuh"
 
 namespace klab {
@@ -19,78 +36,91 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
-constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KiB
+constexpr int NUM_EPI_WARPS = 16;
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;     // 576
+constexpr int A_TILE_BYTES = BM * BK * 2;                // 16 KiB
+constexpr int MAX_STAGES = 8;
+constexpr int CTRL_BYTES = 1024;                         // barriers + tmem pointer + split-K flag
+constexpr int SMEM_BYTES = 227 * 1024;                   // everything an SM has: one CTA per SM
+constexpr int RING_BYTES = SMEM_BYTES - 1024 /*align slack*/ - CTRL_BYTES;
+constexpr int ACC_STRIDE = 256;                          // TMEM columns between the two accumulator stages
+constexpr int CH = 16;                                   // epilogue chunk (columns per tcgen05.ld)
 
-template <int BN> struct TileCfg {
-    static constexpr int B_TILE_BYTES = BN * BK * 2;
-    static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-    static constexpr int TMEM_COLS = 2 * BN;            // 128 / 256 / 512: powers of two
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+struct SplitK {
+    float* ws;            // [splits][m_pad][n_pad] fp32 partial results
+    long long n_pad;      // row stride of a partial matrix
+    long long split_stride;   // m_pad * n_pad
+    int splits;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    void* __restrict__ D, long long ldd, int M, int N, int K, int splits, klab_gemm_epilogue epi) {
-    using Cfg = TileCfg<BN>;
-    constexpr int STAGES = Cfg::STAGES;
+                    void* __restrict__ D, long long ldd, int M, int N, int K, int BN, int stages, SplitK sk,
+                    klab_gemm_epilogue epi) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint8_t* ctrl = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* ring = ctrl + CTRL_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
+    uint64_t* empty_bar = full_bar + MAX_STAGES;
+    uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int stage_bytes = A_TILE_BYTES + BN * BK * 2;
     const int num_m = (M + BM - 1) / BM;
     const int num_n = (N + BN - 1) / BN;
     const int num_k = (K + BK - 1) / BK;
-    // split-K (wgrad of tall-skinny activations): a work item is (output tile, K range); partial tiles are reduced with
-    // fp32 red.global.add into a zero-initialised (or accumulating) D
+    const int splits = sk.splits;
     const int kps = (num_k + splits - 1) / splits;
-    const int num_tiles = num_m * num_n * splits;
+    const int num_items = num_m * num_n * splits;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < stages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full_bar[s], 1);
-            mbar_init(&tmem_empty_bar[s], 4);
+            mbar_init(&tmem_empty_bar[s], NUM_EPI_WARPS);
         }
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+        tmem_alloc(tmem_ptr_smem, 512);
         tmem_relinquish();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail
+    // of the previous kernel; from here on this grid reads / writes global memory.  Our own dependents may be scheduled as
+    // soon as SMs free up (they block in their own pdl_wait until this grid has completed).
+    pdl_wait();
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
                 const int tile = item / splits, split = item - tile * splits;
+                // consecutive items share the m tile (and therefore A) while sweeping n: CTAs running side by side hit the same
+                // A rows in L2
                 const int m0 = (tile / num_n) * BM;
                 const int n0 = (tile % num_n) * BN;
                 const int kb0 = split * kps, kb1 = min(num_k, kb0 + kps);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sa = ring + stage * stage_bytes;
                     uint8_t* sb = sa + A_TILE_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
                     const int k0 = kb * BK;
                     if constexpr (!A_MN) {
                         tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);            // box {64 k, 128 m}
@@ -102,32 +132,31 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     if constexpr (!B_MN) {
                         tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);            // box {64 k, BN n}
                     } else {
-#pragma unroll
                         for (int i = 0; i < BN / 64; ++i)                                 // box {64 n, 64 k}
                             tma_load_2d(sb + i * 8192, &tmap_b, &full_bar[stage], n0 + i * 64, k0);
                     }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+            const uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
                 const int split = item % splits;
                 const int kb0 = split * kps, kb1 = min(num_k, kb0 + kps);
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
+                const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sa = smem_u32(ring + stage * stage_bytes);
                     const uint32_t sb = sa + A_TILE_BYTES;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
@@ -138,60 +167,66 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         umma_bf16(d_tmem, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);           // frees the smem slot once these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(&tmem_full_bar[acc]);             // accumulator complete -> epilogue
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        const int sub = warp & 3;                              // TMEM sub-partition this warp may access
-        const EpiDropout dr = make_dropout(epi.dropout_p);
-        if (dr.on && epi.dropout_seed_ptr) epi.dropout_seed += *epi.dropout_seed_ptr;
+        // ===================== epilogue (warps 2..17) =====================
+        const int sub = warp & 3;                              // TMEM sub-partition this warp may access (warp id % 4)
+        const int quarter = (warp - 2) >> 2;                   // which chunks of the tile: c % 4 == quarter
+        if (epi.dropout_p > 0.0f && epi.dropout_seed_ptr) epi.dropout_seed += *epi.dropout_seed_ptr;
+        const DropKey dr = make_drop_key(epi.dropout_seed, epi.dropout_p);
+        const int nchunks = BN / CH;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
-            const int tile = item / splits;
+        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            const int tile = item / splits, split = item - tile * splits;
             const int m0 = (tile / num_n) * BM;
             const int n0 = (tile % num_n) * BN;
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
-            const long long row = static_cast<long long>(m0) + sub * 32 + lane;
-            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * BN;
+            const int r_in = sub * 32 + lane;
+            const long long row = static_cast<long long>(m0) + r_in;
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * ACC_STRIDE;
+            if (splits == 1) {
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(t_row + c * 32, r);
-                tmem_ld_wait();
-                const int col0 = n0 + c * 32;
-                const int nvalid = min(32, N - col0);
-                if (row < M && nvalid > 0) {
-                    if (splits > 1) {
-                        float* dst = reinterpret_cast<float*>(D) + row * ldd + col0;
-                        if (nvalid == 32) {                     // 16-byte aligned (ldd % 4 == 0, col0 % 32 == 0): vector reds
+                for (int c = quarter; c < nchunks; c += 4) {
+                    uint32_t r[CH];
+                    tmem_ld_32x16(t_row + c * CH, r);
+                    tmem_ld_wait();
+                    const int col0 = n0 + c * CH;
+                    const int nvalid = min(CH, N - col0);
+                    if (row < M && nvalid > 0) {
+                        float v[CH];
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4)
-                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i),
-                                             "f"(__uint_as_float(r[i]) * epi.alpha), "f"(__uint_as_float(r[i + 1]) * epi.alpha),
-                                             "f"(__uint_as_float(r[i + 2]) * epi.alpha), "f"(__uint_as_float(r[i + 3]) * epi.alpha)
-                                             : "memory");
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (i < nvalid) atomicAdd(dst + i, __uint_as_float(r[i]) * epi.alpha);
-                        }
-                    } else {
-                        float v[32];
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                        epilogue_apply_store<32>(epi, dr, v, row, col0, nvalid, N, D, ldd);
+                        for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
+                        epilogue_apply_store<CH>(epi, dr, v, row, col0, nvalid, N, D, ldd);
                     }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            } else {
+                // split-K: park the partial tile; splitk_reduce_kernel finishes the job
+                float* part = sk.ws + split * sk.split_stride + row * sk.n_pad + n0;
+#pragma unroll 1
+                for (int c = quarter; c < nchunks; c += 4) {
+                    uint32_t r[CH];
+                    tmem_ld_32x16(t_row + c * CH, r);
+                    tmem_ld_wait();
+                    uint32_t lo[8], hi[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { lo[i] = r[i]; hi[i] = r[8 + i]; }
+                    st_global_v8(part + c * CH, lo);
+                    st_global_v8(part + c * CH + 8, hi);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -200,14 +235,135 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        tmem_dealloc(tmem_base, 512);
     }
 }
 
-template <int BN, bool A_MN, bool B_MN>
-int launch_cfg(cudaStream_t stream, int M, int N, int K, int splits, const void* A, long long lda, const void* B, long long ldb,
-               void* D, long long ldd, const klab_gemm_epilogue& epi) {
-    using Cfg = TileCfg<BN>;
+// D = epilogue(sum_s ws[s]) over an [M, N] output; one float4 per thread, coalesced
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(SplitK sk, void* __restrict__ D, long long ldd, int M, int N,
+                                                            klab_gemm_epilogue epi) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int n4 = (N + 3) >> 2;
+    const long long total = static_cast<long long>(M) * n4;
+    const DropKey dr = make_drop_key(0, 0.0f);
+    for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = idx / n4;
+        const int c0 = static_cast<int>(idx - r * n4) * 4;
+        const float4* p = reinterpret_cast<const float4*>(sk.ws + r * sk.n_pad + c0);
+        const long long stride4 = sk.split_stride >> 2;
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+        int s = 0;
+        for (; s + 4 <= sk.splits; s += 4) {
+            const float4 q0 = __ldcg(p + s * stride4), q1 = __ldcg(p + (s + 1) * stride4);
+            const float4 q2 = __ldcg(p + (s + 2) * stride4), q3 = __ldcg(p + (s + 3) * stride4);
+            a0.x += q0.x; a0.y += q0.y; a0.z += q0.z; a0.w += q0.w;
+            a1.x += q1.x; a1.y += q1.y; a1.z += q1.z; a1.w += q1.w;
+            a2.x += q2.x; a2.y += q2.y; a2.z += q2.z; a2.w += q2.w;
+            a3.x += q3.x; a3.y += q3.y; a3.z += q3.z; a3.w += q3.w;
+        }
+        for (; s < sk.splits; ++s) {
+            const float4 q0 = __ldcg(p + s * stride4);
+            a0.x += q0.x; a0.y += q0.y; a0.z += q0.z; a0.w += q0.w;
+        }
+        float v[4] = {(a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y), (a0.z + a1.z) + (a2.z + a3.z),
+                      (a0.w + a1.w) + (a2.w + a3.w)};
+        epilogue_apply_store<4>(epi, dr, v, r, c0, min(4, N - c0), N, D, ldd);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+constexpr size_t WS_BYTES = 128ull << 20;      // split-K partial results (fp32)
+
+struct Workspace {
+    float* ws = nullptr;
+};
+Workspace g_ws[16];
+
+// One workspace per device, allocated on first use (never while a stream is capturing: cudaMalloc is illegal there; the
+// caller then runs without split-K).  All GEMMs of a process are issued on one stream at a time (torch's current stream);
+// two split-K GEMMs running CONCURRENTLY on different streams would share it and are not supported.
+Workspace* get_workspace(cudaStream_t stream) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    Workspace& w = g_ws[dev];
+    if (w.ws) return &w;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;
+    if (cudaMalloc(&w.ws, WS_BYTES) != cudaSuccess) { w.ws = nullptr; cudaGetLastError(); return nullptr; }
+    return &w;
+}
+
+int stages_for(int bn) {
+    const int s = RING_BYTES / (A_TILE_BYTES + bn * BK * 2);
+    return s > MAX_STAGES ? MAX_STAGES : s;
+}
+
+// Epilogue cost in instructions per output element (issue-bound estimate), see pick_config.
+double epilogue_instr(const klab_gemm_epilogue& e) {
+    double i = e.out_dtype == KLAB_BF16 ? 3.0 : 2.5;
+    if (e.bias) i += 1.3;
+    if (e.aux_out) i += 2.0;
+    if (e.act == KLAB_ACT_RELU) i += 1.0;
+    if (e.act == KLAB_ACT_GELU) i += 16.0;
+    if (e.act == KLAB_ACT_RELU_BWD) i += 3.0;
+    if (e.act == KLAB_ACT_GELU_BWD) i += 19.0;
+    if (e.dropout_p > 0.0f) i += 8.0;
+    if (e.residual) i += 2.5;
+    if (e.accumulate) i += 2.5;
+    return i;
+}
+
+// Choose the N tile and the K split with a small time model (microseconds), calibrated on B200 (profiles/):
+//   k-block (64 deep) of a 128 x BN tile: max(MMA: BN/256 * 0.26 us, operand feed: (16 KiB + BN * 128 B) / rate) where the
+//   L2 -> SM rate is ~12.4 TB/s shared by the SMs that are pulling (capped per SM);
+//   epilogue: 128 * BN * instr / (96 thread-instructions per clock per SM); it overlaps the next tile's MMAs, so a CTA pays
+//   max(mainloop, epilogue) per tile plus ~2.5 us of fill / drain once;
+//   split-K adds the partial round trip through L2 (write + read by the last CTA).
+void pick_config(int M, int N, int K, bool b_mn, bool can_split, size_t ws_bytes, const klab_gemm_epilogue& epi, int* bn_out,
+                 int* splits_out) {
+    const int sms = sm_count();
+    const int num_m = (M + BM - 1) / BM, num_k = (K + BK - 1) / BK;
+    const double instr = epilogue_instr(epi);
+    double best = 1e30;
+    *bn_out = b_mn ? 64 : 16;
+    *splits_out = 1;
+    const int step = b_mn ? 64 : 16;
+    for (int bn = 256; bn >= step; bn -= step) {
+        const int num_n = (N + bn - 1) / bn;
+        if (num_n > 1 && bn < 64) break;                       // tiles narrower than 64 only when one tile covers N
+        const long long tiles = 1ll * num_m * num_n;
+        const double t_epi = 128.0 * bn * instr / 96.0 / 1965.0;                 // us per tile
+        for (int s = 1; s <= (can_split ? 128 : 1); s *= 2) {
+            if (s > 1 && (num_k / s < 2 || static_cast<size_t>(tiles) * s * BM * bn * 4 > ws_bytes)) break;
+            const int kps = (num_k + s - 1) / s;
+            const long long items = tiles * s;
+            const long long waves = (items + sms - 1) / sms;
+            const double active = items < sms ? double(items) : double(sms);
+            double rate = 12.4e6 / active;                                       // bytes per us per SM
+            if (rate > 100e3) rate = 100e3;                                      // one SM pulls at most ~100 GB/s through TMA
+            const double t_k = fmax(bn / 256.0 * 0.26, (A_TILE_BYTES + bn * 128.0) / rate);
+            const double t_main = kps * t_k;
+            double t = waves * fmax(t_main, s > 1 ? 0.5 : t_epi) + 4.0 + (s > 1 ? 0.0 : fmin(t_epi, 1.5));
+            if (s > 1) {
+                const double bytes = double(tiles) * s * BM * bn * 4.0;
+                t += 3.0 + 2.0 * bytes / 5.0e6;                                  // reduce kernel: launch + partials out and back
+            }
+            if (t < best * 0.97) { best = t; *bn_out = bn; *splits_out = s; }   // prefer wider tiles on near ties (less L2 traffic)
+        }
+    }
+    if (*splits_out > 1) {                                                       // no empty K ranges
+        const int kps = (num_k + *splits_out - 1) / *splits_out;
+        *splits_out = (num_k + kps - 1) / kps;
+    }
+}
+
+template <bool A_MN, bool B_MN>
+int launch_cfg(cudaStream_t stream, int M, int N, int K, int bn, int splits, Workspace* w, const void* A, long long lda, const void* B,
+               long long ldb, void* D, long long ldd, const klab_gemm_epilogue& epi) {
     CUtensorMap ta, tb;
     int rc;
     // A: K-major -> tensor [M rows, K cols], box [128, 64];  MN-major -> tensor [K rows, M cols], box [64, 64]
@@ -215,65 +371,48 @@ int launch_cfg(cudaStream_t stream, int M, int N, int K, int splits, const void*
               : make_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, 64);
     if (rc) return rc;
     rc = B_MN ? make_tmap_2d_bf16(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, 64)
-              : make_tmap_2d_bf16(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN, 64);
+              : make_tmap_2d_bf16(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, bn, 64);
     if (rc) return rc;
-    auto kern = gemm_bf16_tc_kernel<BN, A_MN, B_MN>;
+    auto kern = gemm_bf16_tc_kernel<A_MN, B_MN>;
     static bool attr_set = false;   // per instantiation
     if (!attr_set) {
-        KLAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        KLAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
-    const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-    if (splits > 1 && !epi.accumulate) {
-        if (ldd == N) KLAB_CHECK_CUDA(cudaMemsetAsync(D, 0, sizeof(float) * static_cast<size_t>(M) * N, stream));
-        else KLAB_CHECK_CUDA(cudaMemset2DAsync(D, sizeof(float) * ldd, 0, sizeof(float) * N, M, stream));
+    const int tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
+    SplitK sk{nullptr, 0, 0, splits};
+    if (splits > 1) {
+        const long long m_pad = 1ll * ((M + BM - 1) / BM) * BM, n_pad = 1ll * ((N + bn - 1) / bn) * bn;
+        sk.ws = w->ws; sk.n_pad = n_pad; sk.split_stride = m_pad * n_pad;
     }
     const int items = tiles * splits;
     const int grid = items < sm_count() ? items : sm_count();
-    kern<<<grid, NUM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, D, ldd, M, N, K, splits, epi);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool pdl = []() { const char* e = getenv("KLAB_PDL"); return !(e && e[0] == '0'); }();
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    KLAB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, D, ldd, M, N, K, bn, stages_for(bn), sk, epi));
     KLAB_LAUNCH_CHECK();
     count_launch();
+    if (splits > 1) {
+        const long long total = 1ll * M * ((N + 3) / 4);
+        long long blocks = (total + 255) / 256;
+        if (blocks > 8ll * sm_count()) blocks = 8ll * sm_count();
+        cfg.gridDim = dim3(static_cast<unsigned>(blocks));
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = 0;
+        KLAB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, splitk_reduce_kernel, sk, D, ldd, M, N, epi));
+        KLAB_LAUNCH_CHECK();
+        count_launch();
+    }
     return KLAB_OK;
-}
-
-template <int BN>
-int launch_major(cudaStream_t stream, int M, int N, int K, int splits, const void* A, long long lda, int a_mn, const void* B,
-                 long long ldb, int b_mn, void* D, long long ldd, const klab_gemm_epilogue& epi) {
-    if (!a_mn && !b_mn) return launch_cfg<BN, false, false>(stream, M, N, K, splits, A, lda, B, ldb, D, ldd, epi);
-    if (!a_mn && b_mn) return launch_cfg<BN, false, true>(stream, M, N, K, splits, A, lda, B, ldb, D, ldd, epi);
-    if (a_mn && !b_mn) return launch_cfg<BN, true, false>(stream, M, N, K, splits, A, lda, B, ldb, D, ldd, epi);
-    return launch_cfg<BN, true, true>(stream, M, N, K, splits, A, lda, B, ldb, D, ldd, epi);
-}
-
-// Choose the N tile and the K split with a small time model (microseconds), calibrated on B200:
-//   per k-block (64 deep) MMA time of a 128 x BN tile: BN/256 * 0.27 us (128 x 256 x 16 UMMA = 128 cycles), narrower tiles
-//   lose a little to shared-memory bandwidth; ~2 us of prologue / epilogue per tile; split-K adds M*N*splits fp32 reds
-//   (~0.2 elements/ns measured with red.global.add.v4.f32) and a memset.
-void pick_config(int M, int N, int K, bool can_split, int* bn_out, int* splits_out) {
-    const int sms = sm_count();
-    const int num_m = (M + BM - 1) / BM, num_k = (K + BK - 1) / BK;
-    const int cand[3] = {256, 128, 64};
-    const double t_k[3] = {0.27, 0.145, 0.09};
-    double best = 1e30;
-    *bn_out = 64;
-    *splits_out = 1;
-    for (int i = 0; i < 3; ++i) {
-        const int num_n = (N + cand[i] - 1) / cand[i];
-        const long long tiles = 1ll * num_m * num_n;
-        const double waste = double(num_n * cand[i]) / double(N);            // MMA work on padding columns is still paid
-        for (int s = 1; s <= (can_split ? 128 : 1); s *= 2) {
-            if (s > 1 && num_k / s < 8) break;
-            const int kps = (num_k + s - 1) / s;
-            const long long waves = (tiles * s + sms - 1) / sms;
-            double t = waves * (kps * t_k[i] * (waste > 1.5 ? 1.0 : 1.0) + 2.0);
-            if (s > 1) t += double(M) * N * s / 200.0e3 + 2.0;
-            if (t < best - 1e-9) { best = t; *bn_out = cand[i]; *splits_out = s; }
-        }
-    }
-    if (*splits_out > 1) {                                                   // no empty K ranges
-        const int kps = (num_k + *splits_out - 1) / *splits_out;
-        *splits_out = (num_k + kps - 1) / kps;
-    }
 }
 
 }  // namespace
@@ -284,16 +423,29 @@ int gemm_tc_launch(cudaStream_t stream, int M, int N, int K, const void* A, long
     KLAB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm(bf16): lda=%lld / ldb=%lld must be multiples of 8", lda, ldb);
     KLAB_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
                  "gemm(bf16): operand base pointers must be 16-byte aligned");
-    // split-K needs a linear epilogue into an fp32 output (weight gradients)
-    const bool can_split = epi.act == KLAB_ACT_NONE && !epi.bias && !epi.residual && !epi.aux_out && epi.dropout_p == 0.0f &&
-                           epi.out_dtype == KLAB_F32 && ldd % 4 == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0;
+    // split-K is used for weight gradients: an fp32 output and a linear epilogue
+    Workspace* w = nullptr;
+    const bool splittable = epi.act == KLAB_ACT_NONE && !epi.bias && !epi.residual && !epi.aux_out && epi.dropout_p == 0.0f &&
+                            epi.out_dtype == KLAB_F32;
+    if (splittable) w = get_workspace(stream);
     int bn, splits;
-    pick_config(M, N, K, can_split, &bn, &splits);
-    switch (bn) {
-        case 256: return launch_major<256>(stream, M, N, K, splits, A, lda, a_mn, B, ldb, b_mn, D, ldd, epi);
-        case 128: return launch_major<128>(stream, M, N, K, splits, A, lda, a_mn, B, ldb, b_mn, D, ldd, epi);
-        default: return launch_major<64>(stream, M, N, K, splits, A, lda, a_mn, B, ldb, b_mn, D, ldd, epi);
+    pick_config(M, N, K, b_mn != 0, w != nullptr, WS_BYTES, epi, &bn, &splits);
+    if (const char* f = getenv("KLAB_GEMM_FORCE_BN")) {          // development aid: pin the N tile (and disable split-K)
+        const int v = atoi(f);
+        if (v >= 16 && v <= 256 && v % (b_mn ? 64 : 16) == 0) { bn = v; splits = 1; }
     }
+    if (const char* f = getenv("KLAB_GEMM_FORCE_SPLITS")) {
+        const int v = atoi(f), num_k = (K + BK - 1) / BK;
+        const size_t tiles = static_cast<size_t>((M + BM - 1) / BM) * ((N + bn - 1) / bn);
+        if (w && v >= 1 && v <= num_k && tiles * v * BM * bn * 4 <= WS_BYTES) {
+            const int kps = (num_k + v - 1) / v;
+            splits = (num_k + kps - 1) / kps;
+        }
+    }
+    if (!a_mn && !b_mn) return launch_cfg<false, false>(stream, M, N, K, bn, splits, w, A, lda, B, ldb, D, ldd, epi);
+    if (!a_mn && b_mn) return launch_cfg<false, true>(stream, M, N, K, bn, splits, w, A, lda, B, ldb, D, ldd, epi);
+    if (a_mn && !b_mn) return launch_cfg<true, false>(stream, M, N, K, bn, splits, w, A, lda, B, ldb, D, ldd, epi);
+    return launch_cfg<true, true>(stream, M, N, K, bn, splits, w, A, lda, B, ldb, D, ldd, epi);
 }
 
 }  // namespace klab

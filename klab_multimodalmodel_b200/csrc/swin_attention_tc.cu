@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(128) swin_attn_bwd_tc_kernel(SwinTcArgs a, int
         const int bw = pair * 2 + g;
         int region;
         const int tok = window_token(a, bw, n, region);
-        float qn = 1.0f, kn = 1.0f, Di = 0.0f, lse = 0.0f;
+        float qn = 1.0f, kn = 1.0f, lse = 0.0f;
         {
             float q[HD], k[HD], v[HD], go[HD];
             if (tok >= 0) {
@@ -294,10 +294,6 @@ __global__ void __launch_bounds__(128) swin_attn_bwd_tc_kernel(SwinTcArgs a, int
                 load_row32(a.k, a.ld, tok, h, k);
                 load_row32(a.v, a.ld, tok, h, v);
                 load_row32(a.dctx, a.ldc, tok, h, go);
-                float o[HD];
-                load_row32(a.ctx, a.ldc, tok, h, o);
-#pragma unroll
-                for (int c = 0; c < HD; ++c) Di = fmaf(go[c], o[c], Di);
                 const float iq = inv_norm32(q, qn), ik = inv_norm32(k, kn);
 #pragma unroll
                 for (int c = 0; c < HD; ++c) { q[c] *= iq; k[c] *= ik; }
@@ -330,6 +326,30 @@ __global__ void __launch_bounds__(128) swin_attn_bwd_tc_kernel(SwinTcArgs a, int
 
         const float* brow = a.bias + (static_cast<long long>(h) * N + (tok >= 0 ? n : 0)) * N;
         float* dbrow = dbias_s + (static_cast<long long>(g) * N + (tok >= 0 ? n : 0)) * N;
+        // pass 1: probabilities of the whole row (kept in registers) and D_i = sum_j P_ij dP_ij.  D is taken from the SAME
+        // P and dP that form dS = P (dP - D) -- not from dO . O with the bf16-rounded O -- so the cancellation in (dP - D) is
+        // exact to fp32 rounding; with O rounded to 8 bits the q / k / bias gradients of peaked rows were rounding noise.
+        float pall[SLOT];
+        float Di = 0.0f;
+#pragma unroll
+        for (int c0 = 0; c0 < SLOT; c0 += 32) {
+            uint32_t rs[32], rp[32];
+            tmem_ld_32x32(trow + TM_S + g * SLOT + c0, rs);
+            tmem_ld_32x32(trow + TM_DP + g * SLOT + c0, rp);
+            tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+                const int j = c0 + t;
+                float p = 0.0f;
+                if (tok >= 0 && j < N) {
+                    float s = __uint_as_float(rs[t]) * scale + brow[j];
+                    if (sreg[g * SLOT + j] != region) s += -200.0f;
+                    p = __expf(s - lse);
+                    Di = fmaf(p, __uint_as_float(rp[t]), Di);
+                }
+                pall[j] = p;
+            }
+        }
 #pragma unroll
         for (int c0 = 0; c0 < SLOT; c0 += 32) {
             uint32_t rs[32], rp[32];
@@ -340,15 +360,12 @@ __global__ void __launch_bounds__(128) swin_attn_bwd_tc_kernel(SwinTcArgs a, int
 #pragma unroll
             for (int t = 0; t < 32; ++t) {
                 const int j = c0 + t;
-                float p = 0.0f, ds = 0.0f;
+                const float p = pall[j];
+                float ds = 0.0f;
                 if (tok >= 0 && j < N) {
-                    const float cs = __uint_as_float(rs[t]);
-                    float s = cs * scale + brow[j];
-                    if (sreg[g * SLOT + j] != region) s += -200.0f;
-                    p = __expf(s - lse);
                     ds = p * (__uint_as_float(rp[t]) - Di);
                     dbrow[j] += ds;                       // row (slot g, token n) is owned by this thread: no race
-                    dscale_acc = fmaf(ds, cs, dscale_acc);
+                    dscale_acc = fmaf(ds, __uint_as_float(rs[t]), dscale_acc);
                 }
                 pv[t] = p;
                 dsv[t] = ds;

@@ -35,10 +35,10 @@ struct AttnArgs {
     const unsigned long long* seed_ptr;
 };
 
-__device__ __forceinline__ float drop_mult(const AttnArgs& a, uint32_t thr, float inv_keep, int bh, int i, int j) {
-    if (a.dropout_p <= 0.0f) return 1.0f;
+__device__ __forceinline__ float drop_mult(const AttnArgs& a, const DropKey& key, int bh, int i, int j) {
+    if (!key.on) return 1.0f;
     const uint64_t idx = (static_cast<uint64_t>(bh) * a.Lq + i) * a.Lk + j;
-    return dropout_scale(a.seed, idx, thr, inv_keep);
+    return dropout_mult(key, idx);
 }
 
 template <typename T>
@@ -67,8 +67,7 @@ __global__ void __launch_bounds__(NW * 32) t5_attn_fwd_kernel(AttnArgs a) {
             brel[r] = a.bias_table[a.rel_bucket[rel + a.rel_zero] * a.H + h];
         }
     __syncthreads();
-    const uint32_t thr = make_dropout_thr(a.dropout_p);
-    const float inv_keep = a.dropout_p > 0.0f ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
+    const DropKey dkey = make_drop_key(a.seed, a.dropout_p);
     float* pw = pbuf + warp * Lk;
     float* qw = qbuf + warp * dk;
     const int i_end = min(Lq, (static_cast<int>(blockIdx.y) + 1) * RPC);
@@ -96,7 +95,7 @@ __global__ void __launch_bounds__(NW * 32) t5_attn_fwd_kernel(AttnArgs a) {
         }
         sum = warp_sum(sum);
         const float inv = 1.0f / sum;
-        for (int j = lane; j < jmax; j += 32) pw[j] = pw[j] * inv * drop_mult(a, thr, inv_keep, bh, i, j);
+        for (int j = lane; j < jmax; j += 32) pw[j] = pw[j] * inv * drop_mult(a, dkey, bh, i, j);
         __syncwarp();
         if (lane == 0) a.lse[(static_cast<long long>(bh)) * Lq + i] = mx + __logf(sum);
         T* op = reinterpret_cast<T*>(a.out) + (static_cast<long long>(b) * Lq + i) * a.ldo + h * dk;
@@ -142,8 +141,7 @@ __global__ void __launch_bounds__(NW * 32) t5_attn_bwd_dq_kernel(AttnArgs a) {
         for (int r = threadIdx.x; r < a.num_buckets; r += blockDim.x) s_dbias[r] = 0.0f;
     }
     __syncthreads();
-    const uint32_t thr = make_dropout_thr(a.dropout_p);
-    const float inv_keep = a.dropout_p > 0.0f ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
+    const DropKey dkey = make_drop_key(a.seed, a.dropout_p);
     float* pw = pbuf + warp * Lk;
     float* qw = qbuf + warp * dk;
     float* dow = dobuf + warp * dk;
@@ -175,7 +173,7 @@ __global__ void __launch_bounds__(NW * 32) t5_attn_bwd_dq_kernel(AttnArgs a) {
             }
             if (a.bias_table) s += brel[j - i + Lq - 1];
             const float p = __expf(s - lse);
-            const float ds = p * (dpv * drop_mult(a, thr, inv_keep, bh, i, j) - Di);
+            const float ds = p * (dpv * drop_mult(a, dkey, bh, i, j) - Di);
             pw[j] = ds;
             if (a.bias_table) atomicAdd(&s_dbias[relb[j - i + Lq - 1]], ds);
         }
@@ -230,8 +228,7 @@ __global__ void __launch_bounds__(NW * 32) t5_attn_bwd_dkv_kernel(AttnArgs a) {
             brel[r] = a.bias_table[a.rel_bucket[rel + a.rel_zero] * a.H + h];
         }
     __syncthreads();
-    const uint32_t thr = make_dropout_thr(a.dropout_p);
-    const float inv_keep = a.dropout_p > 0.0f ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
+    const DropKey dkey = make_drop_key(a.seed, a.dropout_p);
     float* pw = pbuf + warp * Lq;
     float* dsw = dsbuf + warp * Lq;
     float* kw = kbuf + warp * dk;
@@ -258,7 +255,7 @@ __global__ void __launch_bounds__(NW * 32) t5_attn_bwd_dkv_kernel(AttnArgs a) {
             }
             if (a.bias_table) s += brel[j - i + Lq - 1];
             const float p = __expf(s - lse_s[i]);
-            const float m = drop_mult(a, thr, inv_keep, bh, i, j);
+            const float m = drop_mult(a, dkey, bh, i, j);
             pw[i] = p * m;
             dsw[i] = p * (dpv * m - d_s[i]);
         }

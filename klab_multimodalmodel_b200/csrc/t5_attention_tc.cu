@@ -52,9 +52,9 @@ __device__ __forceinline__ void st_tile8(uint8_t* tile, int row, int col8, const
     *reinterpret_cast<uint4*>(tile + row * 128 + ((col8 ^ (row & 7)) << 4)) = q;
 }
 
-__device__ __forceinline__ float drop_mult(const TcArgs& a, uint64_t seed, uint32_t thr, float inv_keep, int bh, int i, int j) {
+__device__ __forceinline__ float drop_mult(const TcArgs& a, const DropKey& key, int bh, int i, int j) {
     const uint64_t idx = (static_cast<uint64_t>(bh) * a.Lq + i) * a.Lk + j;
-    return dropout_scale(seed, idx, thr, inv_keep);
+    return dropout_mult(key, idx);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -121,8 +121,7 @@ __global__ void __launch_bounds__(128) t5_attn_fwd_tc_kernel(const __grid_consta
     const int jmax = a.causal ? min(Lk, i + a.q_offset + 1) : Lk;
     const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
     const uint64_t seed = a.seed + (a.seed_ptr ? *a.seed_ptr : 0ull);
-    const uint32_t thr = make_dropout_thr(a.dropout_p);
-    const float inv_keep = a.dropout_p > 0.0f ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
+    const DropKey dkey = make_drop_key(seed, a.dropout_p);
     const float* br = brel + (Lq - 1 - i);                     // br[j] = bias(j - i)
     const bool has_bias = a.bias_table != nullptr && i < Lq;
 
@@ -152,7 +151,7 @@ __global__ void __launch_bounds__(128) t5_attn_fwd_tc_kernel(const __grid_consta
             if (j < jmax) {
                 e = __expf(__uint_as_float(r[t]) + (has_bias ? br[j] : 0.0f) - mx);
                 sum += e;
-                if (a.dropout_p > 0.0f) e *= drop_mult(a, seed, thr, inv_keep, bh, i, j);
+                if (a.dropout_p > 0.0f) e *= drop_mult(a, dkey, bh, i, j);
             }
             p[t] = e;
         }
@@ -270,8 +269,7 @@ __global__ void __launch_bounds__(128) t5_attn_bwd_tc_kernel(const __grid_consta
     const uint32_t tmem = *tmem_ptr;
     const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
     const uint64_t seed = a.seed + (a.seed_ptr ? *a.seed_ptr : 0ull);
-    const uint32_t thr = make_dropout_thr(a.dropout_p);
-    const float inv_keep = a.dropout_p > 0.0f ? 1.0f / (1.0f - a.dropout_p) : 1.0f;
+    const DropKey dkey = make_drop_key(seed, a.dropout_p);
 
     // per query tile: D_i = dO_i . O_i and lse_i of the row this thread owns (global loads, overlapped with the TMA)
     float Dv[2] = {0.0f, 0.0f}, lsev[2] = {0.0f, 0.0f};
@@ -342,7 +340,7 @@ __global__ void __launch_bounds__(128) t5_attn_bwd_tc_kernel(const __grid_consta
                     float p = 0.0f, ds = 0.0f;
                     if (row_ok && j < jmax) {
                         const float pr = __expf(__uint_as_float(rs[t]) + (has_bias ? br[j] : 0.0f) - lsev[qt]);
-                        const float m = a.dropout_p > 0.0f ? drop_mult(a, seed, thr, inv_keep, bh, i, j) : 1.0f;
+                        const float m = a.dropout_p > 0.0f ? drop_mult(a, dkey, bh, i, j) : 1.0f;
                         p = pr * m;
                         ds = pr * (__uint_as_float(rp[t]) * m - Dv[qt]);
                     }
