@@ -335,7 +335,11 @@ def run_ours(args, w):
     if world > 1:
         from torch.nn.parallel import DistributedDataParallel as DDP
         net = DDP(model, device_ids=[local])
-    opt = torch.optim.Adam(model.transformer.parameters(), lr=1e-4)
+    if args.optimizer == "klab":                                      # N1: fused multi-tensor Adam, same semantics as train.py:28
+        from klab_multimodalmodel_b200.optim import Adam
+        opt = Adam(model.transformer.parameters(), lr=1e-4)
+    else:
+        opt = torch.optim.Adam(model.transformer.parameters(), lr=1e-4)
     px_h, src_h, tgt_h = synth_batch(w, tcfg.vocab_size, 1234 + rank, pin=True)
     px_d, src_d, tgt_d = px_h.to(dev), src_h.to(dev), tgt_h.to(dev)
     if args.gemm_probe:
@@ -436,7 +440,8 @@ def run_ours(args, w):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.dtype == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": w["desc"], "name": args.workload, "batch_per_gpu": B, "global_batch": B * world, "l_src": w["l_src"],
-                       "l_tgt": w["l_tgt"], "parallelism": f"dp{world}", "optimizer": "torch.optim.Adam over transformer params (train.py:28)",
+                       "l_tgt": w["l_tgt"], "parallelism": f"dp{world}", "optimizer": ("klab_multimodalmodel_b200.optim.Adam (fused multi-tensor kernel, torch.optim.Adam semantics)" if args.optimizer == "klab"
+                                     else "torch.optim.Adam") + " over transformer params (train.py:28)",
                        "dropout": "T5 p=0.1 active (train.py:52)", "l2_flush": "256 MiB buffer zeroed between timed iterations"},
             "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches),
@@ -473,6 +478,8 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
+    ap.add_argument("--optimizer", default="klab", choices=["klab", "torch"],
+                    help="klab = fused multi-tensor Adam (SURVEY 8f N1, same update rule); torch = stock torch.optim.Adam")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--gemm-probe", action="store_true", help="development aid: only replay (and check) the step's GEMM signatures")

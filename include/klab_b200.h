@@ -187,6 +187,16 @@ int klab_dropout_apply(void* stream, int dtype, long long n, const void* x, void
  * with fresh masks and without a host round trip. */
 int klab_seed_advance(void* stream, unsigned long long* seed_counter);
 
+/* ---- N1: fused multi-tensor Adam (the optimizer step that follows the path: /root/reference/train.py:28,66,
+ * torch.optim.Adam over model.transformer.parameters(); semantics of torch/optim/adam.py with amsgrad = False).
+ * table (DEVICE, int64 [n_tensors][6]) = {param fp32*, grad fp32*, exp_avg fp32*, exp_avg_sq fp32*, bf16 operand copy* or 0,
+ * numel}; blockmap (DEVICE, int32 [n_blocks][2]) = {tensor index, chunk index}, one CTA per chunk of klab_adam_chunk_elems()
+ * elements.  `step` is the 1-based step count (bias corrections); grad_scale multiplies the gradient first.
+ * When the bf16 pointer is non-zero the refreshed parameter is also written there (the operand the tensor cores read). */
+int klab_adam_chunk_elems(void);
+int klab_adam_step(void* stream, const long long* table_dev, const int* blockmap_dev, int n_blocks, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, long long step, float grad_scale);
+
 /* dtype conversion (fp32 master weights -> bf16 operand copies). */
 int klab_cast(void* stream, int src_dtype, int dst_dtype, long long n, const void* src, void* dst);
 

@@ -81,6 +81,8 @@ SIGNATURES = {
     "klab_greedy_step": [_vp, _i, _i, _vp, _ll, _vp, _ll, _i, _vp, _i, _i],
     "klab_dropout_apply": [_vp, _i, _ll, _vp, _vp, _f, _ull, _vp],
     "klab_seed_advance": [_vp, _vp],
+    "klab_adam_chunk_elems": [],
+    "klab_adam_step": [_vp, _vp, _vp, _i, _f, _f, _f, _f, _f, _ll, _f],
 }
 _RESTYPES = {"klab_last_error": C.c_char_p, "klab_launch_count": C.c_longlong,
              "klab_norm_bwd_workspace_bytes": C.c_longlong, "klab_colsum_workspace_bytes": C.c_longlong,

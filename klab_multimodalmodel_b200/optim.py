@@ -1,0 +1,96 @@
+"""N1: fused multi-tensor Adam -- the optimizer step that follows the hot path every iteration
+(/root/reference/train.py:28 `torch.optim.Adam(model.module.transformer.parameters(), lr=args.lr)`, :66 `optimizer.step()`).
+
+Drop-in for `torch.optim.Adam` (same constructor arguments for the features the reference uses: lr, betas, eps, weight_decay;
+same state keys `step`, `exp_avg`, `exp_avg_sq`, so `state_dict()` round-trips with torch's and LR schedulers work unchanged).
+One CUDA launch (csrc/optim.cu) updates every parameter tensor instead of torch's ~250 multi_tensor_apply launches:
+the step is pure HBM traffic (28 B per parameter) and runs at memory speed.  No CPU path: parameters must live on an
+sm_100 device.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+
+
+class Adam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=False, *, maximize=False,
+                 grad_scale=1.0):
+        if amsgrad or maximize:
+            raise NotImplementedError("klab Adam: amsgrad / maximize are not used by the reference and not implemented")
+        if not 0.0 <= lr or not 0.0 <= eps or not 0.0 <= betas[0] < 1.0 or not 0.0 <= betas[1] < 1.0 or not 0.0 <= weight_decay:
+            raise ValueError("klab Adam: invalid hyper-parameter")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False, maximize=False,
+                                      grad_scale=grad_scale))
+        self._tables: dict = {}
+
+    def _table(self, key, items):
+        """items: list of (p, g, m, v).  Device tables are rebuilt only when a pointer changed (with CUDA graphs the gradient
+        buffers are static, so this happens once).  Rebuilds go through two alternating pinned staging buffers and an event, so
+        they never synchronise the device."""
+        sig = tuple((p.data_ptr(), g.data_ptr(), m.data_ptr()) for p, g, m, v in items)
+        ent = self._tables.get(key)
+        if ent is not None and ent["sig"] == sig:
+            return ent["table"], ent["blockmap"], ent["nblocks"]
+        chunk = int(L.lib().klab_adam_chunk_elems())
+        dev = items[0][0].device
+        shape_sig = tuple(p.numel() for p, _, _, _ in items)
+        if ent is None or ent["shape_sig"] != shape_sig:
+            bm = []
+            for ti, n in enumerate(shape_sig):
+                bm.extend([ti, c] for c in range((n + chunk - 1) // chunk))
+            ent = {"shape_sig": shape_sig, "nblocks": len(bm),
+                   "blockmap": torch.tensor(bm, dtype=torch.int32).to(dev),
+                   "table": torch.empty(len(items), 6, dtype=torch.int64, device=dev),
+                   "host": [torch.empty(len(items), 6, dtype=torch.int64).pin_memory() for _ in range(2)],
+                   "events": [None, None], "flip": 0}
+            self._tables[key] = ent
+        i = ent["flip"]
+        ent["flip"] = 1 - i
+        if ent["events"][i] is not None:
+            ent["events"][i].synchronize()                     # the copy that last used this staging buffer (two rebuilds ago)
+        host = ent["host"][i]
+        host.copy_(torch.tensor([[p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), 0, p.numel()] for p, g, m, v in items],
+                                dtype=torch.int64))
+        ent["table"].copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        ent["events"][i] = ev
+        ent["sig"] = sig
+        self.rebuilds = getattr(self, "rebuilds", 0) + 1
+        return ent["table"], ent["blockmap"], ent["nblocks"]
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for gi, group in enumerate(self.param_groups):
+            by_step: dict = {}
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if not p.is_cuda or p.dtype != torch.float32 or p.grad.dtype != torch.float32:
+                    raise RuntimeError("klab Adam: fp32 CUDA parameters and gradients only (there is no CPU path)")
+                if p.grad.is_sparse:
+                    raise RuntimeError("klab Adam does not support sparse gradients")
+                st = self.state[p]
+                if len(st) == 0:
+                    st["step"] = 0                      # python int (torch.optim.Adam.__setstate__ accepts it on load_state_dict)
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                if not p.is_contiguous() or not p.grad.is_contiguous():
+                    raise RuntimeError("klab Adam: parameters and gradients must be contiguous")
+                t = int(st["step"]) + 1
+                st["step"] = t
+                by_step.setdefault(t, []).append((p, p.grad, st["exp_avg"], st["exp_avg_sq"]))
+            b1, b2 = group["betas"]
+            for t, items in by_step.items():
+                table, blockmap, nblocks = self._table((gi, len(by_step) > 1 and t), items)
+                stream = torch.cuda.current_stream(items[0][0].device).cuda_stream
+                L.check(L.lib().klab_adam_step(stream, table.data_ptr(), blockmap.data_ptr(), nblocks, float(group["lr"]), float(b1),
+                                               float(b2), float(group["eps"]), float(group["weight_decay"]), t,
+                                               float(group.get("grad_scale", 1.0))))
+        return loss

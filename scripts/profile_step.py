@@ -37,7 +37,8 @@ def main():
     dev = torch.device("cuda", 0)
     model, tcfg = bench.build_model(w, dev, "bf16")
     model.transformer.train()
-    opt = torch.optim.Adam(model.transformer.parameters(), lr=1e-4)
+    from klab_multimodalmodel_b200.optim import Adam
+    opt = Adam(model.transformer.parameters(), lr=1e-4)
     px, src, tgt = [t.to(dev) for t in bench.synth_batch(w, tcfg.vocab_size, 1234, pin=False)]
 
     def step():
@@ -70,6 +71,7 @@ def main():
     tot = sum(t for _, t in agg.values())
     print(f"workload {a.workload} batch {w['batch']}: wall {t_wall * 1e3:.1f} ms/step, host enqueue {t_cpu * 1e3:.1f} ms/step, "
           f"sum of kernel time {tot / 1e3:.1f} ms over {sum(c for c, _ in agg.values())} launches")
+    print("adam table rebuilds:", getattr(opt, "rebuilds", None))
     for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:a.top]:
         print(f"{k:70s} {c:6d} {t / 1e3:9.2f} ms {100 * t / tot:5.1f}%")
 

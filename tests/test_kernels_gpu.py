@@ -335,3 +335,39 @@ def test_embedding_patch_ce(dtype):
     close(LG[:, :Vv], 0.5 * lr.grad, dtype, "ce bwd")
     assert (LG[:, Vv:] == 0).all()
     o.check_err_flag(LG.device)
+
+
+def test_fused_adam_matches_torch_adam():
+    """N1: klab Adam == torch.optim.Adam (train.py:28) over several steps, odd sizes, an unaligned view, weight decay and an
+    LR scheduler; state_dict keys are torch's."""
+    from klab_multimodalmodel_b200.optim import Adam
+    torch.manual_seed(0)
+    flat = torch.randn(70000, device="cuda")
+    shapes = [(1024, 1024), (33, 7), (1,), (16385,), (513, 129)]
+    ps_a = [torch.randn(s, device="cuda").requires_grad_() for s in shapes] + [flat[1:50001].detach().clone().requires_grad_()]
+    ps_b = [p.detach().clone().requires_grad_() for p in ps_a]
+    for wd in (0.0, 0.01):
+        oa = Adam(ps_a, lr=3e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=wd)
+        ob = torch.optim.Adam(ps_b, lr=3e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=wd)
+        sa = torch.optim.lr_scheduler.CosineAnnealingLR(oa, T_max=10)
+        sb = torch.optim.lr_scheduler.CosineAnnealingLR(ob, T_max=10)
+        for step in range(6):
+            for pa, pb in zip(ps_a, ps_b):
+                g = torch.randn_like(pa) * (10.0 ** (step - 3))
+                pa.grad = g.clone()
+                pb.grad = g.clone()
+            if step == 3:                      # a parameter without a gradient is skipped (and its step count does not advance)
+                ps_a[1].grad = None
+                ps_b[1].grad = None
+            oa.step(); ob.step(); sa.step(); sb.step()
+        for pa, pb in zip(ps_a, ps_b):
+            torch.testing.assert_close(pa, pb, rtol=2e-6, atol=2e-7)
+            ma, mb = oa.state[pa]["exp_avg"], ob.state[pb]["exp_avg"]
+            va, vb = oa.state[pa]["exp_avg_sq"], ob.state[pb]["exp_avg_sq"]
+            torch.testing.assert_close(ma, mb, rtol=2e-6, atol=2e-6 * mb.abs().max().item())     # torch forms m with lerp: fp32 rounding differs
+            torch.testing.assert_close(va, vb, rtol=2e-6, atol=2e-6 * vb.abs().max().item())
+        sd = oa.state_dict()
+        assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
+        ob2 = torch.optim.Adam(ps_b, lr=1e-3)
+        ob2.load_state_dict(sd)                 # torch's Adam accepts our state (python-int step counts included)
+        assert all(torch.is_tensor(st["step"]) or isinstance(st["step"], (int, float)) for st in ob2.state.values())
