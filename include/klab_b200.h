@@ -194,8 +194,8 @@ int klab_seed_advance(void* stream, unsigned long long* seed_counter);
  * elements.  `step` is the 1-based step count (bias corrections); grad_scale multiplies the gradient first.
  * When the bf16 pointer is non-zero the refreshed parameter is also written there (the operand the tensor cores read). */
 int klab_adam_chunk_elems(void);
-int klab_adam_step(void* stream, const long long* table_dev, const int* blockmap_dev, int n_blocks, float lr, float beta1,
-                   float beta2, float eps, float weight_decay, long long step, float grad_scale);
+int klab_adam_step(void* stream, const long long* table_dev, const int* blockmap_dev, int n_blocks, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, long long step, double grad_scale);
 
 /* dtype conversion (fp32 master weights -> bf16 operand copies). */
 int klab_cast(void* stream, int src_dtype, int dst_dtype, long long n, const void* src, void* dst);

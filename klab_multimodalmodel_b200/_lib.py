@@ -46,7 +46,7 @@ def check(rc: int) -> None:
         raise RuntimeError(f"libklab_b200: {lib().klab_last_error().decode()} (status {rc})")
 
 
-_vp, _i, _ll, _f, _ull = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulonglong
+_vp, _i, _ll, _f, _ull, _d = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_ulonglong, C.c_double
 
 # name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/klab_b200.h
 SIGNATURES = {
@@ -82,7 +82,7 @@ SIGNATURES = {
     "klab_dropout_apply": [_vp, _i, _ll, _vp, _vp, _f, _ull, _vp],
     "klab_seed_advance": [_vp, _vp],
     "klab_adam_chunk_elems": [],
-    "klab_adam_step": [_vp, _vp, _vp, _i, _f, _f, _f, _f, _f, _ll, _f],
+    "klab_adam_step": [_vp, _vp, _vp, _i, _d, _d, _d, _d, _d, _ll, _d],
 }
 _RESTYPES = {"klab_last_error": C.c_char_p, "klab_launch_count": C.c_longlong,
              "klab_norm_bwd_workspace_bytes": C.c_longlong, "klab_colsum_workspace_bytes": C.c_longlong,

@@ -20,6 +20,7 @@ constexpr int ADAM_THREADS = 256;
 
 struct AdamArgs {
     float lr, beta1, beta2, eps, weight_decay;
+    float omb1, omb2;     // 1 - beta, rounded from the DOUBLE difference (1.0f - 0.98f is off by 1e-6 relative)
     float inv_bc1;        // 1 / (1 - beta1^t)
     float inv_sqrt_bc2;   // 1 / sqrt(1 - beta2^t)
     float grad_scale;     // multiplies g first (1 = off): gradient-accumulation averaging without a separate pass
@@ -28,8 +29,8 @@ struct AdamArgs {
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamArgs& a) {
     g *= a.grad_scale;
     g = fmaf(a.weight_decay, p, g);
-    m = fmaf(a.beta1, m, (1.0f - a.beta1) * g);
-    v = fmaf(a.beta2, v, (1.0f - a.beta2) * g * g);
+    m = fmaf(a.beta1, m, a.omb1 * g);
+    v = fmaf(a.beta2, v, a.omb2 * g * g);
     const float denom = fmaf(sqrtf(v), a.inv_sqrt_bc2, a.eps);
     p -= (a.lr * a.inv_bc1) * (m / denom);
 }
@@ -93,15 +94,18 @@ extern "C" {
 
 int klab_adam_chunk_elems(void) { return klab::ADAM_CHUNK; }
 
-int klab_adam_step(void* stream, const long long* table_dev, const int* blockmap_dev, int n_blocks, float lr, float beta1,
-                   float beta2, float eps, float weight_decay, long long step, float grad_scale) {
+int klab_adam_step(void* stream, const long long* table_dev, const int* blockmap_dev, int n_blocks, double lr, double beta1,
+                   double beta2, double eps, double weight_decay, long long step, double grad_scale) {
     using namespace klab;
     if (int rc = klab_check_device()) return rc;
     KLAB_REQUIRE(n_blocks > 0 && step >= 1 && table_dev && blockmap_dev, "adam_step: bad arguments (n_blocks=%d step=%lld)", n_blocks, step);
     AdamArgs a;
-    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.grad_scale = grad_scale;
-    a.inv_bc1 = static_cast<float>(1.0 / (1.0 - pow(static_cast<double>(beta1), static_cast<double>(step))));
-    a.inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(1.0 - pow(static_cast<double>(beta2), static_cast<double>(step))));
+    a.beta1 = static_cast<float>(beta1); a.beta2 = static_cast<float>(beta2); a.eps = static_cast<float>(eps);
+    a.weight_decay = static_cast<float>(weight_decay); a.grad_scale = static_cast<float>(grad_scale);
+    a.omb1 = static_cast<float>(1.0 - beta1); a.omb2 = static_cast<float>(1.0 - beta2);
+    a.lr = static_cast<float>(lr / (1.0 - pow(beta1, static_cast<double>(step))));      // step size lr / (1 - b1^t), formed in double
+    a.inv_bc1 = 1.0f;
+    a.inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(1.0 - pow(beta2, static_cast<double>(step))));
     adam_multi_kernel<<<n_blocks, ADAM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(table_dev, blockmap_dev, a);
     KLAB_LAUNCH_CHECK();
     count_launch();

@@ -234,10 +234,19 @@ __global__ void __launch_bounds__(128) swin_attn_fwd_tc_kernel(SwinTcArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// backward: grid (nchunks, heads), 128 threads; the CTA walks window pairs pair = blockIdx.x, blockIdx.x + nchunks, ...
+// backward: grid (nchunks, heads), 512 threads; the CTA walks window pairs pair = blockIdx.x, blockIdx.x + nchunks, ...
 // TMEM: S 0..127 | dP 128..255 | dV 256..287 | dK 288..351 | dQ 352..415
+//
+// One window pair is a serial chain (stage operands -> S, dP MMAs -> softmax backward -> dV, dK, dQ MMAs -> write out) and
+// the operands of a pair fill most of the SM's shared memory, so a second resident CTA is not an option.  The kernel is
+// latency bound, not throughput bound; it therefore (1) spreads every SIMT phase over 16 warps -- staging: 4 threads per
+// token row, 16 bytes of q / k / v / dO each; softmax backward: 4 threads per row, 16 keys each; write-out: dq / dk / dv rows
+// by different warps -- and (2) prefetches the rows of the NEXT pair into registers while the tensor core and the softmax
+// phase work on the current one.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) swin_attn_bwd_tc_kernel(SwinTcArgs a, int npairs) {
+constexpr int BWD_THREADS = 512;
+
+__global__ void __launch_bounds__(BWD_THREADS, 1) swin_attn_bwd_tc_kernel(SwinTcArgs a, int npairs) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
@@ -247,16 +256,23 @@ __global__ void __launch_bounds__(128) swin_attn_bwd_tc_kernel(SwinTcArgs a, int
     uint8_t* sP = sdO + TB;
     uint8_t* sdS = sP + 2 * TB;
     uint8_t* sdSl = sdS + 2 * TB;                                  // low-order bf16 part of dS
-    float* dbias_s = reinterpret_cast<float*>(sdSl + 2 * TB);      // [2 slots][N][N]
+    float* dbias_s = reinterpret_cast<float*>(sdSl + 2 * TB);      // [N][N + 1] (padded: conflict-free), used by the final flush only
     const int N = a.N;
-    int* sreg = reinterpret_cast<int*>(dbias_s + 2 * N * N);
-    float* red = reinterpret_cast<float*>(sreg + TILE);            // [4]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 4);
+    int* sreg = reinterpret_cast<int*>(dbias_s + N * (N + 1));     // [128] shift-mask region of the row's token, -1 = padding row
+    float* sqn = reinterpret_cast<float*>(sreg + TILE);            // [128] |q|
+    float* skn = sqn + TILE;                                       // [128] |k|
+    float* sD = skn + TILE;                                        // [4][128] partial D_i
+    float* red = sD + 4 * TILE;                                    // [16]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 16);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
     constexpr int TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 288, TM_DQ = 352;      // dK / dQ: 64 columns ([hi | lo] of B)
 
-    const int tid = threadIdx.x, warp = tid >> 5, h = blockIdx.y;
-    const int g = tid >> 6, n = tid & 63;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, h = blockIdx.y;
+    // staging view: 4 consecutive threads share token row srow, each moves the 16-byte chunk `part` (8 channels) of q, k, v, dO
+    const int srow = tid >> 2, part = tid & 3, sg = srow >> 6, sn = srow & 63;
+    // TMEM view: TMEM lane = row; the four warps with the same (warp & 3) split the row's 64 keys into quarters
+    const int r = (warp & 3) * 32 + lane, g = r >> 6, n = r & 63, cq = warp >> 2;
+
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         fence_barrier_init();
@@ -266,12 +282,21 @@ __global__ void __launch_bounds__(128) swin_attn_bwd_tc_kernel(SwinTcArgs a, int
         tmem_alloc(tmem_ptr, 512);
         tmem_relinquish();
     }
-    for (int idx = tid; idx < 2 * N * N; idx += blockDim.x) dbias_s[idx] = 0.0f;
+    for (int idx = tid; idx < N * (N + 1); idx += BWD_THREADS) dbias_s[idx] = 0.0f;
+    // the bias gradient of element (n, j) is owned by the thread with TMEM row n (either window slot) and key quarter j / 16 for
+    // EVERY window pair this CTA visits, so it accumulates in registers (a shared-memory row per thread would put the 32 lanes
+    // of a warp on one bank: rows are 64 floats apart) and is combined once at the end
+    float dbacc[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) dbacc[t] = 0.0f;
+    // P / dS / dSl hold, per row, the keys of the row's OWN window in key block g; the other block stays zero for the whole
+    // kernel (it is the cross-window half of the 128 x 128 product), so it is cleared once, not once per pair
+    for (int idx = tid; idx < 6 * TB / 16; idx += BWD_THREADS) reinterpret_cast<uint4*>(sP)[idx] = make_uint4(0, 0, 0, 0);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
-    const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint32_t trow = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const float raw_ls = a.logit_scale[h];
     const float scale = __expf(fminf(raw_ls, LOGIT_MAX));
     const uint32_t id_s = umma_idesc_bf16(TILE, TILE, false, false);   // S / dP
@@ -282,32 +307,56 @@ __global__ void __launch_bounds__(128) swin_attn_bwd_tc_kernel(SwinTcArgs a, int
     float dscale_acc = 0.0f;
     uint32_t phase = 0;
 
-    for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
-        const int bw = pair * 2 + g;
-        int region;
-        const int tok = window_token(a, bw, n, region);
-        float qn = 1.0f, kn = 1.0f, lse = 0.0f;
-        {
-            float q[HD], k[HD], v[HD], go[HD];
-            if (tok >= 0) {
-                load_row32(a.q, a.ld, tok, h, q);
-                load_row32(a.k, a.ld, tok, h, k);
-                load_row32(a.v, a.ld, tok, h, v);
-                load_row32(a.dctx, a.ldc, tok, h, go);
-                const float iq = inv_norm32(q, qn), ik = inv_norm32(k, kn);
-#pragma unroll
-                for (int c = 0; c < HD; ++c) { q[c] *= iq; k[c] *= ik; }
-                lse = a.lse[(static_cast<long long>(bw) * a.heads + h) * N + n];
-            } else {
-#pragma unroll
-                for (int c = 0; c < HD; ++c) { q[c] = 0.0f; k[c] = 0.0f; v[c] = 0.0f; go[c] = 0.0f; }
-            }
-            stage_row32_hilo(sQ, tid, q);
-            stage_row32_hilo(sK, tid, k);
-            stage_row32(sV, tid, v);
-            stage_row32(sdO, tid, go);
+    // prefetch registers (rows of the pair about to be staged)
+    uint4 pq = make_uint4(0, 0, 0, 0), pk = pq, pv = pq, pdo = pq;
+    int ptok = -1, pregion = 0;
+    auto prefetch = [&](int pair) {
+        ptok = window_token(a, pair * 2 + sg, sn, pregion);
+        if (ptok >= 0) {
+            const long long o = static_cast<long long>(ptok) * a.ld + h * HD;
+            const long long oc = static_cast<long long>(ptok) * a.ldc + h * HD;
+            pq = __ldg(reinterpret_cast<const uint4*>(a.q + o) + part);
+            pk = __ldg(reinterpret_cast<const uint4*>(a.k + o) + part);
+            pv = __ldg(reinterpret_cast<const uint4*>(a.v + o) + part);
+            pdo = __ldg(reinterpret_cast<const uint4*>(a.dctx + oc) + part);
+        } else {
+            pq = pk = pv = pdo = make_uint4(0, 0, 0, 0);
         }
-        sreg[tid] = region;
+    };
+    if (static_cast<int>(blockIdx.x) < npairs) prefetch(blockIdx.x);
+
+    for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+        // ---- stage the pair: L2-normalise q, k (fp32), split into bf16 hi | lo, copy v and dO ----
+        {
+            float q[8], k[8];
+            unpack8(pq, q);
+            unpack8(pk, k);
+            float sq = 0.0f, sk = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) { sq = fmaf(q[c], q[c], sq); sk = fmaf(k[c], k[c], sk); }
+            sq += __shfl_xor_sync(0xffffffffu, sq, 1); sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+            sk += __shfl_xor_sync(0xffffffffu, sk, 1); sk += __shfl_xor_sync(0xffffffffu, sk, 2);
+            const float qn = fmaxf(sqrtf(sq), NORM_EPS), kn = fmaxf(sqrtf(sk), NORM_EPS);
+            const float iq = ptok >= 0 ? 1.0f / qn : 0.0f, ik = ptok >= 0 ? 1.0f / kn : 0.0f;
+            float ql[8], kl[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                q[c] *= iq; k[c] *= ik;
+                ql[c] = q[c] - __bfloat162float(__float2bfloat16_rn(q[c]));
+                kl[c] = k[c] - __bfloat162float(__float2bfloat16_rn(k[c]));
+            }
+            st_tile8(sQ, srow, part, q);
+            st_tile8(sQ, srow, 4 + part, ql);
+            st_tile8(sK, srow, part, k);
+            st_tile8(sK, srow, 4 + part, kl);
+            st_tile8_raw(sV, srow, part, pv);
+            st_tile8_raw(sdO, srow, part, pdo);
+            if (part == 0) {
+                sreg[srow] = ptok >= 0 ? pregion : -1;
+                sqn[srow] = qn;
+                skn[srow] = kn;
+            }
+        }
         fence_proxy_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -320,71 +369,65 @@ __global__ void __launch_bounds__(128) swin_attn_bwd_tc_kernel(SwinTcArgs a, int
                 umma_bf16(tmem + TM_DP, umma_smem_desc_sw128(doa + k * 32, 16, 1024), umma_smem_desc_sw128(va + k * 32, 16, 1024), id_s, k != 0);
             umma_commit(&bars[0]);
         }
+        // rows of the next pair travel while the tensor core and the softmax phase work on this one
+        if (pair + static_cast<int>(gridDim.x) < npairs) prefetch(pair + gridDim.x);
+
+        const int region = sreg[r];
+        const bool valid = region >= 0;
+        const int bw = pair * 2 + g;
+        const float lse = valid ? a.lse[(static_cast<long long>(bw) * a.heads + h) * N + n] : 0.0f;
+        const float* brow = a.bias + (static_cast<long long>(h) * N + (valid ? n : 0)) * N + cq * 16;
+        int kreg[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) kreg[t] = sreg[g * SLOT + cq * 16 + t];
         mbar_wait(&bars[0], phase);
         phase ^= 1;
         tc_fence_after();
 
-        const float* brow = a.bias + (static_cast<long long>(h) * N + (tok >= 0 ? n : 0)) * N;
-        float* dbrow = dbias_s + (static_cast<long long>(g) * N + (tok >= 0 ? n : 0)) * N;
-        // pass 1: probabilities of the whole row (kept in registers) and D_i = sum_j P_ij dP_ij.  D is taken from the SAME
-        // P and dP that form dS = P (dP - D) -- not from dO . O with the bf16-rounded O -- so the cancellation in (dP - D) is
-        // exact to fp32 rounding; with O rounded to 8 bits the q / k / bias gradients of peaked rows were rounding noise.
-        float pall[SLOT];
-        float Di = 0.0f;
+        // pass 1: probabilities of this thread's 16 keys and the partial D_i = sum_j P_ij dP_ij.  D is taken from the SAME P
+        // and dP that form dS = P (dP - D) -- not from dO . O with the bf16-rounded O -- so the cancellation in (dP - D) is exact
+        // to fp32 rounding; with O rounded to 8 bits the q / k / bias gradients of peaked rows were rounding noise.
+        uint32_t rs[16], rp[16];
+        tmem_ld_32x16(trow + TM_S + g * SLOT + cq * 16, rs);
+        tmem_ld_32x16(trow + TM_DP + g * SLOT + cq * 16, rp);
+        tmem_ld_wait();
+        float pv16[16];
+        float Dp = 0.0f;
 #pragma unroll
-        for (int c0 = 0; c0 < SLOT; c0 += 32) {
-            uint32_t rs[32], rp[32];
-            tmem_ld_32x32(trow + TM_S + g * SLOT + c0, rs);
-            tmem_ld_32x32(trow + TM_DP + g * SLOT + c0, rp);
-            tmem_ld_wait();
-#pragma unroll
-            for (int t = 0; t < 32; ++t) {
-                const int j = c0 + t;
-                float p = 0.0f;
-                if (tok >= 0 && j < N) {
-                    float s = __uint_as_float(rs[t]) * scale + brow[j];
-                    if (sreg[g * SLOT + j] != region) s += -200.0f;
-                    p = __expf(s - lse);
-                    Di = fmaf(p, __uint_as_float(rp[t]), Di);
-                }
-                pall[j] = p;
+        for (int t = 0; t < 16; ++t) {
+            const int j = cq * 16 + t;
+            float p = 0.0f;
+            if (valid && j < N) {
+                float sc = __uint_as_float(rs[t]) * scale + __ldg(brow + t);
+                if (kreg[t] != region) sc += -200.0f;
+                p = __expf(sc - lse);
+                Dp = fmaf(p, __uint_as_float(rp[t]), Dp);
             }
+            pv16[t] = p;
         }
+        sD[cq * TILE + r] = Dp;
+        __syncthreads();
+        const float Di = (sD[r] + sD[TILE + r]) + (sD[2 * TILE + r] + sD[3 * TILE + r]);
+        {
+            float dsv[16], dlo[16];
 #pragma unroll
-        for (int c0 = 0; c0 < SLOT; c0 += 32) {
-            uint32_t rs[32], rp[32];
-            tmem_ld_32x32(trow + TM_S + g * SLOT + c0, rs);
-            tmem_ld_32x32(trow + TM_DP + g * SLOT + c0, rp);
-            tmem_ld_wait();
-            float pv[32], dsv[32];
-#pragma unroll
-            for (int t = 0; t < 32; ++t) {
-                const int j = c0 + t;
-                const float p = pall[j];
+            for (int t = 0; t < 16; ++t) {
+                const int j = cq * 16 + t;
                 float ds = 0.0f;
-                if (tok >= 0 && j < N) {
-                    ds = p * (__uint_as_float(rp[t]) - Di);
-                    dbrow[j] += ds;                       // row (slot g, token n) is owned by this thread: no race
+                if (valid && j < N) {
+                    ds = pv16[t] * (__uint_as_float(rp[t]) - Di);
+                    dbacc[t] += ds;
                     dscale_acc = fmaf(ds, __uint_as_float(rs[t]), dscale_acc);
                 }
-                pv[t] = p;
                 dsv[t] = ds;
+                dlo[t] = ds - __bfloat162float(__float2bfloat16_rn(ds));   // dS = hi + lo (both bf16): see the dQ / dK passes below
             }
-            float dlo[32];                                   // dS = hi + lo (both bf16): see the dQ / dK passes below
 #pragma unroll
-            for (int t = 0; t < 32; ++t) dlo[t] = dsv[t] - __bfloat162float(__float2bfloat16_rn(dsv[t]));
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                st_tile8(sP + g * TB, tid, (c0 >> 3) + c, pv + 8 * c);
-                st_tile8(sdS + g * TB, tid, (c0 >> 3) + c, dsv + 8 * c);
-                st_tile8(sdSl + g * TB, tid, (c0 >> 3) + c, dlo + 8 * c);
+            for (int c = 0; c < 2; ++c) {
+                st_tile8(sP + g * TB, r, cq * 2 + c, pv16 + 8 * c);
+                st_tile8(sdS + g * TB, r, cq * 2 + c, dsv + 8 * c);
+                st_tile8(sdSl + g * TB, r, cq * 2 + c, dlo + 8 * c);
             }
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            st_tile8_raw(sP + (1 - g) * TB, tid, c, make_uint4(0, 0, 0, 0));
-            st_tile8_raw(sdS + (1 - g) * TB, tid, c, make_uint4(0, 0, 0, 0));
-            st_tile8_raw(sdSl + (1 - g) * TB, tid, c, make_uint4(0, 0, 0, 0));
         }
         fence_proxy_async_smem();
         tc_fence_before();
@@ -414,48 +457,42 @@ __global__ void __launch_bounds__(128) swin_attn_bwd_tc_kernel(SwinTcArgs a, int
         mbar_wait(&bars[0], phase);
         phase ^= 1;
         tc_fence_after();
-        {
-            uint32_t rq[32], rk[32], rv[32];
-            {
-                uint32_t lo[32];
-                tmem_ld_32x32(trow + TM_DQ, rq);
-                tmem_ld_32x32(trow + TM_DQ + HD, lo);
+        // ---- write out: warps 0-3 dq, warps 4-7 dk, warps 8-11 dv (token row = TMEM lane) ----
+        if (cq < 3) {
+            int rg;
+            const int tok = window_token(a, bw, n, rg);
+            if (cq == 2) {
+                uint32_t rv[32];
+                tmem_ld_32x32(trow + TM_DV, rv);
                 tmem_ld_wait();
+                if (tok >= 0) {
+                    float o[HD];
 #pragma unroll
-                for (int c = 0; c < HD; ++c) rq[c] = __float_as_uint(__uint_as_float(rq[c]) + __uint_as_float(lo[c]));
-                tmem_ld_32x32(trow + TM_DK, rk);
-                tmem_ld_32x32(trow + TM_DK + HD, lo);
-                tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < HD; ++c) rk[c] = __float_as_uint(__uint_as_float(rk[c]) + __uint_as_float(lo[c]));
-            }
-            tmem_ld_32x32(trow + TM_DV, rv);
-            tmem_ld_wait();
-            if (tok >= 0) {
-                float qh[HD], kh[HD], o[HD];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    unpack8(ld_tile8_raw(sQ, tid, c), qh + 8 * c);
-                    unpack8(ld_tile8_raw(sK, tid, c), kh + 8 * c);
+                    for (int c = 0; c < HD; ++c) o[c] = __uint_as_float(rv[c]);
+                    store_row32(a.dv, a.ld, tok, h, o);
                 }
-                // d q = (d qh - qh (qh . d qh)) / |q| with d qh = scale * (dS Kh)   (normalisation backward)
-                float dot = 0.0f;
+            } else {
+                // d q = (d qh - qh (qh . d qh)) / |q| with d qh = scale * (dS Kh)   (normalisation backward); same for k
+                uint32_t hi[32], lo[32];
+                tmem_ld_32x32(trow + (cq == 0 ? TM_DQ : TM_DK), hi);
+                tmem_ld_32x32(trow + (cq == 0 ? TM_DQ : TM_DK) + HD, lo);
+                tmem_ld_wait();
+                if (tok >= 0) {
+                    const uint8_t* tile = cq == 0 ? sQ : sK;
+                    float xh[HD], o[HD];
 #pragma unroll
-                for (int c = 0; c < HD; ++c) dot = fmaf(__uint_as_float(rq[c]) * scale, qh[c], dot);
-                const float iq = 1.0f / qn;
+                    for (int c = 0; c < 4; ++c) unpack8(ld_tile8_raw(tile, r, c), xh + 8 * c);
+                    float dot = 0.0f;
 #pragma unroll
-                for (int c = 0; c < HD; ++c) o[c] = (__uint_as_float(rq[c]) * scale - qh[c] * dot) * iq;
-                store_row32(a.dq, a.ld, tok, h, o);
-                dot = 0.0f;
+                    for (int c = 0; c < HD; ++c) {
+                        o[c] = (__uint_as_float(hi[c]) + __uint_as_float(lo[c])) * scale;
+                        dot = fmaf(o[c], xh[c], dot);
+                    }
+                    const float inv = 1.0f / (cq == 0 ? sqn[r] : skn[r]);
 #pragma unroll
-                for (int c = 0; c < HD; ++c) dot = fmaf(__uint_as_float(rk[c]) * scale, kh[c], dot);
-                const float ik = 1.0f / kn;
-#pragma unroll
-                for (int c = 0; c < HD; ++c) o[c] = (__uint_as_float(rk[c]) * scale - kh[c] * dot) * ik;
-                store_row32(a.dk, a.ld, tok, h, o);
-#pragma unroll
-                for (int c = 0; c < HD; ++c) o[c] = __uint_as_float(rv[c]);
-                store_row32(a.dv, a.ld, tok, h, o);
+                    for (int c = 0; c < HD; ++c) o[c] = (o[c] - xh[c] * dot) * inv;
+                    store_row32(cq == 0 ? a.dq : a.dk, a.ld, tok, h, o);
+                }
             }
         }
         tc_fence_before();
@@ -463,17 +500,26 @@ __global__ void __launch_bounds__(128) swin_attn_bwd_tc_kernel(SwinTcArgs a, int
         tc_fence_after();
     }
 
-    // flush: bias gradient of every window this CTA visited, and d(logit_scale)
+    // flush: bias gradient of every window this CTA visited (the two window slots are combined in shared memory first), and
+    // d(logit_scale)
+    if (n < N) {
+#pragma unroll
+        for (int t = 0; t < 16; ++t)
+            if (cq * 16 + t < N && dbacc[t] != 0.0f) atomicAdd(&dbias_s[n * (N + 1) + cq * 16 + t], dbacc[t]);
+    }
+    __syncthreads();
     float* dbias = a.dbias + static_cast<long long>(h) * N * N;
-    for (int idx = tid; idx < N * N; idx += blockDim.x) {
-        const float v = dbias_s[idx] + dbias_s[N * N + idx];
+    for (int idx = tid; idx < N * N; idx += BWD_THREADS) {
+        const float v = dbias_s[(idx / N) * (N + 1) + idx % N];
         if (v != 0.0f) atomicAdd(&dbias[idx], v);
     }
     dscale_acc = warp_sum(dscale_acc);
-    if ((tid & 31) == 0) red[warp] = dscale_acc;
+    if (lane == 0) red[warp] = dscale_acc;
     __syncthreads();
     if (tid == 0) {
-        const float t = red[0] + red[1] + red[2] + red[3];
+        float t = 0.0f;
+#pragma unroll
+        for (int w = 0; w < BWD_THREADS / 32; ++w) t += red[w];
         atomicAdd(&a.dlogit_scale[h], raw_ls <= LOGIT_MAX ? t * scale : 0.0f);
     }
     tc_fence_before();
@@ -528,7 +574,7 @@ int swin_attention_bwd_tc(cudaStream_t st, int B, int res, int heads, int window
     a.dq = static_cast<__nv_bfloat16*>(dq); a.dk = static_cast<__nv_bfloat16*>(dk); a.dv = static_cast<__nv_bfloat16*>(dv);
     a.dbias = dbias; a.dlogit_scale = dlogit_scale;
     const int N = a.N;
-    const size_t smem = 1024 + 10 * TB + sizeof(float) * 2 * N * N + sizeof(int) * TILE + 64;
+    const size_t smem = 1024 + 10 * TB + sizeof(float) * N * (N + 1) + sizeof(int) * TILE + sizeof(float) * (6 * TILE + 16) + 64;
     static size_t set = 0;
     if (smem > set) {
         KLAB_CHECK_CUDA(cudaFuncSetAttribute(swin_attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -541,7 +587,7 @@ int swin_attention_bwd_tc(cudaStream_t st, int B, int res, int heads, int window
     if (nchunks > npairs) nchunks = npairs;
     if (nchunks < 1) nchunks = 1;
     const dim3 grid(nchunks, heads);
-    swin_attn_bwd_tc_kernel<<<grid, 128, smem, st>>>(a, npairs);
+    swin_attn_bwd_tc_kernel<<<grid, BWD_THREADS, smem, st>>>(a, npairs);
     KLAB_LAUNCH_CHECK();
     count_launch();
     return KLAB_OK;

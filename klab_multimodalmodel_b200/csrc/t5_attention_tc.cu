@@ -8,10 +8,13 @@
 //     one smem tile serves both as a K-major and as an MN-major operand (P as A of P V and as A^T of P^T dO, ...);
 //   * softmax / dS run one-thread-per-row out of TMEM (tcgen05.ld), so S, P and dS never touch HBM.
 // Limits: d_kv == 64, Lq <= 256, Lk <= 256 (the reference's sequences are <= 176); anything else takes the generic kernel.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace klab {
 void count_launch(int n = 1);
+int sm_count();
 namespace {
 
 constexpr int DK = 64;
@@ -472,6 +475,437 @@ __global__ void __launch_bounds__(128) t5_attn_bwd_tc_kernel(const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Single-tile kernels (Lq <= 128 and Lk <= 128: every sequence of workloads 1-3): PERSISTENT, 512 threads.
+//
+// One (batch, head) problem is a short serial chain (TMA -> S [, dP] MMAs -> softmax -> P V / dV dK dQ MMAs -> write-out), so
+// the kernels above -- one problem per CTA, 128 threads, one CTA per SM because of shared memory / TMEM -- are pure latency:
+// ~22 us per backward problem for ~1 us of tensor work.  Here a CTA walks problems bh = blockIdx.x, + gridDim.x, ...:
+//   * the operands of problem i+1 are fetched by TMA into a second buffer set while problem i computes;
+//   * every SIMT phase is spread over 16 warps: 4 threads per query row (TMEM lane), 32 keys each; row statistics are
+//     combined through shared memory;
+//   * backward takes D_i = sum_j P~_ij dP_ij from the same P~ and dP that form dS (no dO . O re-read, exact cancellation).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int ST_THREADS = 512;
+
+__device__ __forceinline__ void st_tile16(uint8_t* tile, int row, int col16, const float* v) {        // 16 consecutive columns
+    st_tile8(tile, row, col16 * 2, v);
+    st_tile8(tile, row, col16 * 2 + 1, v + 8);
+}
+
+// smem: [Q 16K | K 16K | V 16K] x 2 | P 32K | brel | stats | barriers
+__global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_fwd_tc1_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
+                                                                        const __grid_constant__ CUtensorMap tmv, TcArgs a, int lk_pad) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int T = TILE * 128;
+    uint8_t* sIn = smem;                          // 2 x (Q, K, V)
+    uint8_t* sP = sIn + 6 * T;                    // 2 key blocks of 64
+    float* brel = reinterpret_cast<float*>(sP + 2 * T);          // [256]
+    float* sred = brel + 256;                                    // [4][128] row max / row sum partials
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sred + 4 * TILE);   // full[2], mma
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r = (warp & 3) * 32 + lane, cq = warp >> 2;       // TMEM lane = query row; key quarter
+    const int Lq = a.Lq, Lk = a.Lk, nprob = a.B * a.H;
+    constexpr int O_COL = 128;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_init(&bars[2], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tmem_alloc(tmem_ptr, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+    const uint32_t trow = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const uint64_t seed = a.seed + (a.seed_ptr ? *a.seed_ptr : 0ull);
+    const DropKey dkey = make_drop_key(seed, a.dropout_p);
+    const uint32_t id_s = umma_idesc_bf16(TILE, TILE, false, false);
+    const uint32_t id_o = umma_idesc_bf16(TILE, DK, false, true);
+    const int nks = lk_pad / 16;
+
+    auto issue_loads = [&](int bh, int buf) {
+        const int b = bh / a.H, h = bh - b * a.H;
+        uint8_t* base = sIn + buf * 3 * T;
+        mbar_arrive_expect_tx(&bars[buf], 3 * T);
+        tma_load_2d(base, &tmq, &bars[buf], h * DK, b * Lq);
+        tma_load_2d(base + T, &tmk, &bars[buf], h * DK, b * Lk);
+        tma_load_2d(base + 2 * T, &tmv, &bars[buf], h * DK, b * Lk);
+    };
+    if (tid == 0 && static_cast<int>(blockIdx.x) < nprob) issue_loads(blockIdx.x, 0);
+
+    uint32_t mma_phase = 0;
+    int it = 0;
+    for (int bh = blockIdx.x; bh < nprob; bh += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int h = bh % a.H, b = bh / a.H;
+        uint8_t* sQ = sIn + buf * 3 * T;
+        uint8_t* sK = sQ + T;
+        uint8_t* sV = sK + T;
+        if (tid == 0 && bh + static_cast<int>(gridDim.x) < nprob) issue_loads(bh + gridDim.x, buf ^ 1);
+        const bool has_bias = a.bias_table != nullptr;
+        if (has_bias && tid < Lq + Lk - 1) {
+            const int rel = tid - (Lq - 1) - a.q_offset;
+            brel[tid] = a.bias_table[a.rel_bucket[rel + a.rel_zero] * a.H + h];
+        }
+        if (tid == 0) {
+            mbar_wait(&bars[buf], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK);
+#pragma unroll
+            for (int k = 0; k < DK / 16; ++k)
+                umma_bf16(tmem, umma_smem_desc_sw128(qa + k * 32, 16, 1024), umma_smem_desc_sw128(ka + k * 32, 16, 1024), id_s, k != 0);
+            umma_commit(&bars[2]);
+        }
+        __syncthreads();                                   // brel visible
+        mbar_wait(&bars[2], mma_phase);
+        mma_phase ^= 1;
+        tc_fence_after();
+
+        const int i = r;
+        const int jmax = a.causal ? min(Lk, i + a.q_offset + 1) : Lk;
+        const int j0 = cq * 32;
+        const float* br = brel + (Lq - 1 - i) + j0;
+        const bool bias_on = has_bias && i < Lq;
+        const bool active = j0 < lk_pad;                   // warp-uniform
+        float sv[32];
+        float mx = -INFINITY;
+        if (active) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t rr[16];
+                tmem_ld_32x16(trow + j0 + hf * 16, rr);
+                tmem_ld_wait();
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const int j = j0 + hf * 16 + t;
+                    float sc = -INFINITY;
+                    if (j < jmax) {
+                        sc = __uint_as_float(rr[t]) + (bias_on ? br[hf * 16 + t] : 0.0f);
+                        mx = fmaxf(mx, sc);
+                    }
+                    sv[hf * 16 + t] = sc;
+                }
+            }
+        }
+        sred[cq * TILE + r] = mx;
+        __syncthreads();
+        mx = fmaxf(fmaxf(sred[r], sred[TILE + r]), fmaxf(sred[2 * TILE + r], sred[3 * TILE + r]));
+        __syncthreads();                                   // sred is reused for the sums
+        float sum = 0.0f;
+        if (active) {
+            const uint64_t base = (static_cast<uint64_t>(bh) * Lq + i) * Lk + j0;
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+                const float e = sv[t] > -INFINITY ? __expf(sv[t] - mx) : 0.0f;
+                sum += e;
+                sv[t] = e;
+            }
+            if (dkey.on && i < Lq) dropout_apply_run<32>(dkey, base, sv);     // elements past jmax are zero already
+            uint8_t* blk = sP + (j0 >> 6) * T;
+            st_tile16(blk, r, (j0 & 63) >> 4, sv);
+            st_tile16(blk, r, ((j0 & 63) >> 4) + 1, sv + 16);
+        }
+        sred[cq * TILE + r] = sum;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (tid == 0) {
+            const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
+            for (int ks = 0; ks < nks; ++ks)
+                umma_bf16(tmem + O_COL, umma_smem_desc_sw128(pa + (ks >> 2) * T + (ks & 3) * 32, 16, 1024),
+                          umma_smem_desc_sw128(va + ks * 2048, 8192, 1024), id_o, ks != 0);
+            umma_commit(&bars[2]);
+        }
+        sum = (sred[r] + sred[TILE + r]) + (sred[2 * TILE + r] + sred[3 * TILE + r]);
+        mbar_wait(&bars[2], mma_phase);
+        mma_phase ^= 1;
+        tc_fence_after();
+        if (cq < 2) {                                      // warps 0-3: output columns 0-31, warps 4-7: 32-63
+            uint32_t ro[32];
+            tmem_ld_32x32(trow + O_COL + cq * 32, ro);
+            tmem_ld_wait();
+            if (i < Lq) {
+                const float inv = 1.0f / sum;
+                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + (static_cast<long long>(b) * Lq + i) * a.ldo + h * DK + cq * 32;
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq) {
+                    uint4 q;
+                    q.x = pack_bf16(__uint_as_float(ro[8 * gq]) * inv, __uint_as_float(ro[8 * gq + 1]) * inv);
+                    q.y = pack_bf16(__uint_as_float(ro[8 * gq + 2]) * inv, __uint_as_float(ro[8 * gq + 3]) * inv);
+                    q.z = pack_bf16(__uint_as_float(ro[8 * gq + 4]) * inv, __uint_as_float(ro[8 * gq + 5]) * inv);
+                    q.w = pack_bf16(__uint_as_float(ro[8 * gq + 6]) * inv, __uint_as_float(ro[8 * gq + 7]) * inv);
+                    reinterpret_cast<uint4*>(op)[gq] = q;
+                }
+            }
+        } else if (cq == 2 && i < Lq) {
+            a.lse[static_cast<long long>(bh) * Lq + i] = mx + __logf(sum);
+        }
+        tc_fence_before();
+        __syncthreads();                                   // TMEM, sP, brel, sred are reused by the next problem
+        tc_fence_after();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 256);
+    }
+}
+
+// smem: [Q | dO | K | V] x 2 (16K each) | P 32K | dS 32K | brel | drel | bins | stats | barriers   (~197 KB)
+// TMEM: S 0..127 | dP 128..255 | dV 256..319 | dK 320..383 | dQ 384..447
+__global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_bwd_tc1_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
+                                                                        const __grid_constant__ CUtensorMap tmv, const __grid_constant__ CUtensorMap tmdo,
+                                                                        TcArgs a, int lq_pad, int lk_pad) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int T = TILE * 128;
+    uint8_t* sIn = smem;                          // 2 x (Q, dO, K, V)
+    uint8_t* sP = sIn + 8 * T;                    // 2 key blocks of 64
+    uint8_t* sdS = sP + 2 * T;
+    float* brel = reinterpret_cast<float*>(sdS + 2 * T);         // [256] bias per relative position
+    float* drel = brel + 256;                                    // [256] dS summed per relative position
+    float* bins = drel + 256;                                    // [64]
+    float* sred = bins + 64;                                     // [4][128] partial D_i
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sred + 4 * TILE);   // full[2], mma
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
+    constexpr int TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r = (warp & 3) * 32 + lane, cq = warp >> 2;
+    const int Lq = a.Lq, Lk = a.Lk, nprob = a.B * a.H;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_init(&bars[2], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tmem_alloc(tmem_ptr, 512);
+        tmem_relinquish();
+    }
+    // rows of P / dS at and beyond lq_pad are never written and never read (the contraction over queries stops at lq_pad);
+    // rows in [Lq, lq_pad) are written as zeros below
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+    const uint32_t trow = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const uint64_t seed = a.seed + (a.seed_ptr ? *a.seed_ptr : 0ull);
+    const DropKey dkey = make_drop_key(seed, a.dropout_p);
+    const uint32_t id_s = umma_idesc_bf16(TILE, TILE, false, false);     // S / dP : A K-major, B K-major, N = 128
+    const uint32_t id_t = umma_idesc_bf16(TILE, DK, true, true);         // dV / dK: A MN-major (P^T), B MN-major, N = 64
+    const uint32_t id_q = umma_idesc_bf16(TILE, DK, false, true);        // dQ     : A K-major (dS), B MN-major (K), N = 64
+    const int nqs = lq_pad / 16, nks = lk_pad / 16;
+    const bool has_bias = a.bias_table != nullptr;
+
+    auto issue_loads = [&](int bh, int buf) {
+        const int b = bh / a.H, h = bh - b * a.H;
+        uint8_t* base = sIn + buf * 4 * T;
+        mbar_arrive_expect_tx(&bars[buf], 4 * T);
+        tma_load_2d(base, &tmq, &bars[buf], h * DK, b * Lq);
+        tma_load_2d(base + T, &tmdo, &bars[buf], h * DK, b * Lq);
+        tma_load_2d(base + 2 * T, &tmk, &bars[buf], h * DK, b * Lk);
+        tma_load_2d(base + 3 * T, &tmv, &bars[buf], h * DK, b * Lk);
+    };
+    if (tid == 0 && static_cast<int>(blockIdx.x) < nprob) issue_loads(blockIdx.x, 0);
+
+    uint32_t mma_phase = 0;
+    int it = 0;
+    for (int bh = blockIdx.x; bh < nprob; bh += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int h = bh % a.H, b = bh / a.H;
+        uint8_t* sQ = sIn + buf * 4 * T;
+        uint8_t* sdO = sQ + T;
+        uint8_t* sK = sdO + T;
+        uint8_t* sV = sK + T;
+        if (tid == 0 && bh + static_cast<int>(gridDim.x) < nprob) issue_loads(bh + gridDim.x, buf ^ 1);
+        if (has_bias && tid < Lq + Lk - 1) {
+            const int rel = tid - (Lq - 1) - a.q_offset;
+            brel[tid] = a.bias_table[a.rel_bucket[rel + a.rel_zero] * a.H + h];
+            drel[tid] = 0.0f;
+        }
+        if (tid < 64) bins[tid] = 0.0f;
+        const int i = r;
+        const bool row_ok = i < Lq;
+        const float lse = row_ok ? a.lse[static_cast<long long>(bh) * Lq + i] : 0.0f;
+        if (tid == 0) {
+            mbar_wait(&bars[buf], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t qa = smem_u32(sQ), doa = smem_u32(sdO), ka = smem_u32(sK), va = smem_u32(sV);
+#pragma unroll
+            for (int k = 0; k < DK / 16; ++k)
+                umma_bf16(tmem + TM_S, umma_smem_desc_sw128(qa + k * 32, 16, 1024), umma_smem_desc_sw128(ka + k * 32, 16, 1024), id_s, k != 0);
+#pragma unroll
+            for (int k = 0; k < DK / 16; ++k)
+                umma_bf16(tmem + TM_DP, umma_smem_desc_sw128(doa + k * 32, 16, 1024), umma_smem_desc_sw128(va + k * 32, 16, 1024), id_s, k != 0);
+            umma_commit(&bars[2]);
+        }
+        __syncthreads();                                   // brel / drel / bins visible
+        mbar_wait(&bars[2], mma_phase);
+        mma_phase ^= 1;
+        tc_fence_after();
+
+        const int jmax = a.causal ? min(Lk, i + a.q_offset + 1) : Lk;
+        const int j0 = cq * 32;
+        const float* br = brel + (Lq - 1 - i) + j0;
+        const bool active = j0 < lk_pad;                   // warp-uniform
+        // pass 1: P~ = P * dropout multiplier (what the forward multiplied into V) and the partial D_i = sum_j P~_ij dP_ij
+        uint32_t keep = 0xFFFFFFFFu;                       // dropout keep bits of the 32 keys
+        uint8_t* pb = sP + (j0 >> 6) * T;
+        uint8_t* db = sdS + (j0 >> 6) * T;
+        const int c16 = (j0 & 63) >> 4;
+        float Dp = 0.0f;
+        if (active) {
+            if (dkey.on) {
+                const uint64_t base = (static_cast<uint64_t>(bh) * Lq + i) * Lk + j0;
+                keep = 0;
+                if ((base & 1) == 0) {
+#pragma unroll
+                    for (int t = 0; t < 32; t += 2) {
+                        const uint32_t hsh = drop_hash_pair(dkey, (base + t) >> 1);
+                        keep |= ((hsh & 0xFFFFu) < dkey.thr16 ? 1u : 0u) << t;
+                        keep |= ((hsh >> 16) < dkey.thr16 ? 1u : 0u) << (t + 1);
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 32; ++t) keep |= (dropout_mult(dkey, base + t) != 0.0f ? 1u : 0u) << t;
+                }
+            }
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t rs[16], rp[16];
+                tmem_ld_32x16(trow + TM_S + j0 + hf * 16, rs);
+                tmem_ld_32x16(trow + TM_DP + j0 + hf * 16, rp);
+                tmem_ld_wait();
+                float pm[16];                              // P~
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const int j = j0 + hf * 16 + t;
+                    float p = 0.0f;
+                    if (row_ok && j < jmax) {
+                        p = __expf(__uint_as_float(rs[t]) + (has_bias ? br[hf * 16 + t] : 0.0f) - lse);
+                        p = (keep >> (hf * 16 + t)) & 1u ? p * dkey.inv_keep : 0.0f;
+                        Dp = fmaf(p, __uint_as_float(rp[t]), Dp);
+                    }
+                    pm[t] = p;
+                }
+                if (r < lq_pad) st_tile16(pb, r, c16 + hf, pm);
+            }
+        }
+        sred[cq * TILE + r] = Dp;
+        __syncthreads();
+        const float Di = (sred[r] + sred[TILE + r]) + (sred[2 * TILE + r] + sred[3 * TILE + r]);
+        // pass 2: dS_ij = P_ij (m_ij dP_ij - D_i) with P = P~ / m on kept elements; dropped elements keep P_ij D_i, which needs the
+        // un-dropped probability -> recompute it from S for those (rare: p = 0.1)
+        if (active && (warp & 3) * 32 < lq_pad) {           // warp-uniform (tcgen05.ld is warp-collective); stores are per lane
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                float dsv[16];
+                uint32_t rs[16], rp[16];
+                tmem_ld_32x16(trow + TM_S + j0 + hf * 16, rs);
+                tmem_ld_32x16(trow + TM_DP + j0 + hf * 16, rp);
+                tmem_ld_wait();
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const int j = j0 + hf * 16 + t;
+                    float ds = 0.0f;
+                    if (row_ok && j < jmax) {
+                        const bool kept = (keep >> (hf * 16 + t)) & 1u;
+                        const float pr = __expf(__uint_as_float(rs[t]) + (has_bias ? br[hf * 16 + t] : 0.0f) - lse);
+                        ds = pr * ((kept ? __uint_as_float(rp[t]) * dkey.inv_keep : 0.0f) - Di);
+                    }
+                    dsv[t] = ds;
+                }
+                if (r < lq_pad) st_tile16(db, r, c16 + hf, dsv);
+            }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (tid == 0) {
+            const uint32_t pa = smem_u32(sP), dsa = smem_u32(sdS);
+            const uint32_t qa = smem_u32(sQ), doa = smem_u32(sdO), ka = smem_u32(sK);
+            // dV = P~^T dO ; dK = dS^T Q : M = 128 keys (MN-major A: atoms of 64 keys are T bytes apart), contraction over lq_pad queries
+            for (int ks = 0; ks < nqs; ++ks) {
+                umma_bf16(tmem + TM_DV, umma_smem_desc_sw128(pa + ks * 2048, T, 1024), umma_smem_desc_sw128(doa + ks * 2048, 8192, 1024), id_t, ks != 0);
+                umma_bf16(tmem + TM_DK, umma_smem_desc_sw128(dsa + ks * 2048, T, 1024), umma_smem_desc_sw128(qa + ks * 2048, 8192, 1024), id_t, ks != 0);
+            }
+            // dQ = dS K : A K-major (k-blocks of 64 keys are T bytes apart), B = K MN-major, contraction over lk_pad keys
+            for (int ks = 0; ks < nks; ++ks)
+                umma_bf16(tmem + TM_DQ, umma_smem_desc_sw128(dsa + (ks >> 2) * T + (ks & 3) * 32, 16, 1024),
+                          umma_smem_desc_sw128(ka + ks * 2048, 8192, 1024), id_q, ks != 0);
+            umma_commit(&bars[2]);
+        }
+        // bias gradient, overlapped with the MMAs: sum the dS tile along its diagonals (j - i = const); thread t owns diagonal t.
+        // At a fixed row the lanes of a warp read consecutive bf16 of that row (no bank conflicts).
+        if (has_bias && tid < 2 * TILE - 1) {
+            const int dd = tid;                               // j - i + 127
+            const int lo = max(0, TILE - 1 - dd), hi = min(min(TILE - 1, 2 * TILE - 2 - dd), Lq - 1);
+            float acc = 0.0f;
+            for (int il = lo; il <= hi; ++il) {
+                const int jl = il + dd - (TILE - 1);
+                if (jl < lk_pad)
+                    acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sdS + (jl >> 6) * T + sw128(il, jl & 63)));
+            }
+            const int rr = dd - (TILE - 1) + (Lq - 1);
+            if (rr >= 0 && rr < Lq + Lk - 1) atomicAdd(&bins[a.rel_bucket[rr - (Lq - 1) - a.q_offset + a.rel_zero]], acc);
+        }
+        mbar_wait(&bars[2], mma_phase);
+        mma_phase ^= 1;
+        tc_fence_after();
+        // write-out: warps 0-3 dq, 4-7 dk, 8-11 dv (row = TMEM lane)
+        if (cq < 3) {
+            const int rows = cq == 0 ? Lq : Lk;
+            const uint32_t col = cq == 0 ? TM_DQ : (cq == 1 ? TM_DK : TM_DV);
+            __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(cq == 0 ? a.dq : (cq == 1 ? a.dk : a.dv));
+            const long long ld = cq == 0 ? a.ldq : (cq == 1 ? a.ldk : a.ldv);
+#pragma unroll
+            for (int c0 = 0; c0 < DK; c0 += 32) {
+                uint32_t ro[32];
+                tmem_ld_32x32(trow + col + c0, ro);
+                tmem_ld_wait();
+                if (r < rows) {
+                    uint4* dst = reinterpret_cast<uint4*>(base + (static_cast<long long>(b) * rows + r) * ld + h * DK + c0);
+#pragma unroll
+                    for (int gq = 0; gq < 4; ++gq) {
+                        uint4 q;
+                        q.x = pack_bf16(__uint_as_float(ro[8 * gq]), __uint_as_float(ro[8 * gq + 1]));
+                        q.y = pack_bf16(__uint_as_float(ro[8 * gq + 2]), __uint_as_float(ro[8 * gq + 3]));
+                        q.z = pack_bf16(__uint_as_float(ro[8 * gq + 4]), __uint_as_float(ro[8 * gq + 5]));
+                        q.w = pack_bf16(__uint_as_float(ro[8 * gq + 6]), __uint_as_float(ro[8 * gq + 7]));
+                        dst[gq] = q;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();                                   // TMEM, sP / sdS, brel / bins are reused by the next problem
+        tc_fence_after();
+        if (has_bias && tid < a.num_buckets) a.dbias_partial[static_cast<long long>(bh) * a.num_buckets + tid] = bins[tid];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
 // dtable[bucket, h] += sum_b partial[(b*H + h), bucket]      (one thread per (bucket, h); B is small)
 __global__ void t5_dbias_reduce_tc_kernel(const float* __restrict__ part, int B, int H, int nb, float* __restrict__ dtable) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -499,6 +933,28 @@ int t5_attention_fwd_tc(cudaStream_t st, int B, int H, int Lq, int Lk, const voi
                         const void* v, long long ldv, void* out, long long ldo, const float* bias_table, const int* rel_bucket,
                         int rel_zero, int num_buckets, int causal, int q_offset, float* lse, float dropout_p, unsigned long long seed,
                         const unsigned long long* seed_ptr) {
+    if (Lq <= TILE && Lk <= TILE && !getenv("KLAB_T5_ATTN_MULTI")) {          // persistent single-tile kernel
+        const int lkp = (Lk + 15) / 16 * 16;
+        CUtensorMap tq, tk, tv;
+        if (int rc = make_head_map(&tq, q, 1ll * B * Lq, H, ldq, TILE)) return rc;
+        if (int rc = make_head_map(&tk, k, 1ll * B * Lk, H, ldk, TILE)) return rc;
+        if (int rc = make_head_map(&tv, v, 1ll * B * Lk, H, ldv, TILE)) return rc;
+        TcArgs a{};
+        a.out = out; a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo; a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk;
+        a.bias_table = bias_table; a.rel_bucket = rel_bucket; a.rel_zero = rel_zero; a.num_buckets = num_buckets; a.causal = causal;
+        a.q_offset = q_offset; a.lse = lse; a.dropout_p = dropout_p; a.seed = seed; a.seed_ptr = seed_ptr;
+        const size_t smem1 = 1024 + 8 * TILE * 128 + sizeof(float) * (256 + 4 * TILE) + 64;
+        static bool set1 = false;
+        if (!set1) {
+            KLAB_CHECK_CUDA(cudaFuncSetAttribute(t5_attn_fwd_tc1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+            set1 = true;
+        }
+        const int nprob = B * H;
+        t5_attn_fwd_tc1_kernel<<<nprob < sm_count() ? nprob : sm_count(), ST_THREADS, smem1, st>>>(tq, tk, tv, a, lkp);
+        KLAB_LAUNCH_CHECK();
+        count_launch();
+        return KLAB_OK;
+    }
     const int lk_pad = (Lk + 15) / 16 * 16;
     const int o_col = lk_pad <= 64 ? 64 : (lk_pad <= 192 ? 192 : 256);
     const int tmem_cols = o_col + 64 <= 128 ? 128 : (o_col + 64 <= 256 ? 256 : 512);
@@ -542,6 +998,26 @@ int t5_attention_bwd_tc(cudaStream_t st, int B, int H, int Lq, int Lk, const voi
     a.bias_table = bias_table; a.rel_bucket = rel_bucket; a.rel_zero = rel_zero; a.num_buckets = num_buckets; a.causal = causal;
     a.q_offset = q_offset; a.lse = const_cast<float*>(lse); a.dropout_p = dropout_p; a.seed = seed; a.seed_ptr = seed_ptr;
     a.dbias_partial = static_cast<float*>(workspace);
+    if (Lq <= TILE && Lk <= TILE && num_buckets <= 64 && !getenv("KLAB_T5_ATTN_MULTI")) {      // persistent single-tile kernel
+        const size_t smem1 = 1024 + 12 * TILE * 128 + sizeof(float) * (256 + 256 + 64 + 4 * TILE) + 64;
+        static bool set1 = false;
+        if (!set1) {
+            KLAB_CHECK_CUDA(cudaFuncSetAttribute(t5_attn_bwd_tc1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+            set1 = true;
+        }
+        const int nprob = B * H;
+        t5_attn_bwd_tc1_kernel<<<nprob < sm_count() ? nprob : sm_count(), ST_THREADS, smem1, st>>>(tq, tk, tv, tdo, a, (Lq + 15) / 16 * 16,
+                                                                                                   (Lk + 15) / 16 * 16);
+        KLAB_LAUNCH_CHECK();
+        count_launch();
+        if (bias_table && dbias_table) {
+            const int n = num_buckets * H;
+            t5_dbias_reduce_tc_kernel<<<(n + 127) / 128, 128, 0, st>>>(a.dbias_partial, B, H, num_buckets, dbias_table);
+            KLAB_LAUNCH_CHECK();
+            count_launch();
+        }
+        return KLAB_OK;
+    }
     const int nq = (Lq + TILE - 1) / TILE, nk = (Lk + TILE - 1) / TILE;
     const size_t smem = 1024 + static_cast<size_t>(2 * nq + 2 * nk + 4) * TILE * 128 + 2 * sizeof(float) * ((Lq + Lk + 3) & ~3) +
                         sizeof(float) * ((num_buckets + 3) & ~3) + 64;

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_ctypes_argument_types_match_header():
     from klab_multimodalmodel_b200 import _lib as L
-    scalar = {"int": C.c_int, "long long": C.c_longlong, "float": C.c_float, "unsigned long long": C.c_ulonglong}
+    scalar = {"int": C.c_int, "long long": C.c_longlong, "float": C.c_float, "unsigned long long": C.c_ulonglong, "double": C.c_double}
     for name, args in header_prototypes():
         if args.strip() in ("void", ""):
             continue

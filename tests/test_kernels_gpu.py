@@ -339,7 +339,8 @@ def test_embedding_patch_ce(dtype):
 
 def test_fused_adam_matches_torch_adam():
     """N1: klab Adam == torch.optim.Adam (train.py:28) over several steps, odd sizes, an unaligned view, weight decay and an
-    LR scheduler; state_dict keys are torch's."""
+    LR scheduler; state_dict keys are torch's.  Both are fp32 implementations of the same recurrence, so the yardstick is a
+    float64 evaluation of it: our distance to it may not exceed torch's (x4, plus one fp32 ulp of slack)."""
     from klab_multimodalmodel_b200.optim import Adam
     torch.manual_seed(0)
     flat = torch.randn(70000, device="cuda")
@@ -347,27 +348,41 @@ def test_fused_adam_matches_torch_adam():
     ps_a = [torch.randn(s, device="cuda").requires_grad_() for s in shapes] + [flat[1:50001].detach().clone().requires_grad_()]
     ps_b = [p.detach().clone().requires_grad_() for p in ps_a]
     for wd in (0.0, 0.01):
-        oa = Adam(ps_a, lr=3e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=wd)
-        ob = torch.optim.Adam(ps_b, lr=3e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=wd)
+        lr0, b1, b2, eps = 3e-3, 0.9, 0.98, 1e-8
+        oa = Adam(ps_a, lr=lr0, betas=(b1, b2), eps=eps, weight_decay=wd)
+        ob = torch.optim.Adam(ps_b, lr=lr0, betas=(b1, b2), eps=eps, weight_decay=wd)
         sa = torch.optim.lr_scheduler.CosineAnnealingLR(oa, T_max=10)
         sb = torch.optim.lr_scheduler.CosineAnnealingLR(ob, T_max=10)
+        ex = [dict(p=p.detach().double(), m=torch.zeros_like(p, dtype=torch.float64), v=torch.zeros_like(p, dtype=torch.float64), t=0)
+              for p in ps_b]
         for step in range(6):
-            for pa, pb in zip(ps_a, ps_b):
+            lr = oa.param_groups[0]["lr"]
+            assert abs(lr - ob.param_groups[0]["lr"]) < 1e-12
+            for k, (pa, pb) in enumerate(zip(ps_a, ps_b)):
                 g = torch.randn_like(pa) * (10.0 ** (step - 3))
                 pa.grad = g.clone()
                 pb.grad = g.clone()
-            if step == 3:                      # a parameter without a gradient is skipped (and its step count does not advance)
-                ps_a[1].grad = None
-                ps_b[1].grad = None
+                if step == 3 and k == 1:           # a parameter without a gradient is skipped (and its step count does not advance)
+                    pa.grad = None
+                    pb.grad = None
+                    continue
+                e = ex[k]
+                e["t"] += 1
+                gd = g.double() + wd * e["p"]
+                e["m"] = b1 * e["m"] + (1 - b1) * gd
+                e["v"] = b2 * e["v"] + (1 - b2) * gd * gd
+                e["p"] = e["p"] - (lr / (1 - b1 ** e["t"])) * e["m"] / (e["v"].sqrt() / (1 - b2 ** e["t"]) ** 0.5 + eps)
             oa.step(); ob.step(); sa.step(); sb.step()
-        for pa, pb in zip(ps_a, ps_b):
-            torch.testing.assert_close(pa, pb, rtol=2e-6, atol=2e-7)
-            ma, mb = oa.state[pa]["exp_avg"], ob.state[pb]["exp_avg"]
-            va, vb = oa.state[pa]["exp_avg_sq"], ob.state[pb]["exp_avg_sq"]
-            torch.testing.assert_close(ma, mb, rtol=2e-6, atol=2e-6 * mb.abs().max().item())     # torch forms m with lerp: fp32 rounding differs
-            torch.testing.assert_close(va, vb, rtol=2e-6, atol=2e-6 * vb.abs().max().item())
+        for k, (pa, pb) in enumerate(zip(ps_a, ps_b)):
+            for name, xa, xb, xe in (("param", pa, pb, ex[k]["p"]), ("exp_avg", oa.state[pa]["exp_avg"], ob.state[pb]["exp_avg"], ex[k]["m"]),
+                                     ("exp_avg_sq", oa.state[pa]["exp_avg_sq"], ob.state[pb]["exp_avg_sq"], ex[k]["v"])):
+                ea = (xa.detach().double() - xe).abs().max().item()
+                eb = (xb.detach().double() - xe).abs().max().item()
+                ulp = 1.2e-7 * xe.abs().max().item()
+                assert ea <= 4.0 * eb + ulp, f"tensor {k} {name}: klab error {ea:.3e} vs torch error {eb:.3e} against float64"
         sd = oa.state_dict()
         assert set(sd["state"][0]) == {"step", "exp_avg", "exp_avg_sq"}
         ob2 = torch.optim.Adam(ps_b, lr=1e-3)
         ob2.load_state_dict(sd)                 # torch's Adam accepts our state (python-int step counts included)
-        assert all(torch.is_tensor(st["step"]) or isinstance(st["step"], (int, float)) for st in ob2.state.values())
+        for pa, pb in zip(ps_a, ps_b):          # keep the two trajectories identical for the next round
+            pb.data.copy_(pa.data)
