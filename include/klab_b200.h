@@ -173,6 +173,21 @@ int klab_ce_fwd(void* stream, int dtype, long long rows, int V, const void* logi
 int klab_ce_bwd(void* stream, int dtype, long long rows, int V, void* logits, long long ld, int ld_pad, const long long* labels,
                 const float* lse, const float* stats, const float* gscale);
 
+/* ---- K10 (hot path): LM head fused with the cross entropy, vocab-tiled, logits never written
+ * (HF/models/t5/modeling_t5.py:1105-1117: logits = (h * d^-0.5) E^T with the tied embedding, CrossEntropyLoss(ignore_index=-100)).
+ * bf16 tcgen05 path only.  fwd: the LM-head GEMM's epilogue keeps, per (row, vocab tile), an online-softmax partial
+ * (max, sum exp) and the label's logit in fp32 straight out of TMEM; a second kernel combines them into lse[rows] and
+ * stats = {mean loss over non-ignored rows, #non-ignored rows}.  workspace: klab_lmhead_ce_workspace_bytes(rows, V).
+ * bwd is vocab-chunked by the caller: klab_lmhead_ce_bwd_chunk recomputes the logits of vocabulary columns [v0, v0 + vc)
+ * (E_chunk = E + v0 * lde) and writes d loss / d logits * (*gscale) as bf16 into dlogits [rows, vc] (a chunk-sized scratch that
+ * stays in L2); the caller then runs dH += dlogits E_chunk and dE[v0:v0+vc] = dlogits^T H with klab_gemm. */
+long long klab_lmhead_ce_workspace_bytes(long long rows, int V);
+int klab_lmhead_ce_fwd(void* stream, long long rows, int V, int d, const void* h, long long ldh, const void* E, long long lde, float alpha,
+                       const long long* labels, float* lse, float* stats, void* workspace, int* err_flag);
+int klab_lmhead_ce_bwd_chunk(void* stream, long long rows, int d, const void* h, long long ldh, const void* E_chunk, long long lde, float alpha,
+                             const long long* labels, const float* lse, const float* stats, const float* gscale, int v0, int vc,
+                             void* dlogits, long long ldd);
+
 /* ---- K14 (part): greedy decode step (HF/generation/utils.py:2762-2800): ids[b,t] = unfinished[b] ? argmax(logits[b,:]) : pad;
  * unfinished[b] &= ids[b,t] != eos.  logits are fp32 [B,V]; ties resolve to the lowest index. */
 int klab_greedy_step(void* stream, int B, int V, const float* logits, long long ld, long long* ids, long long ld_ids, int t,

@@ -77,6 +77,9 @@ SIGNATURES = {
     "klab_patch_merge": [_vp, _i, _i, _i, _i, _vp, _vp, _i],
     "klab_ce_fwd": [_vp, _i, _ll, _i, _vp, _ll, _vp, _vp, _vp, _vp, _vp],
     "klab_ce_bwd": [_vp, _i, _ll, _i, _vp, _ll, _i, _vp, _vp, _vp, _vp],
+    "klab_lmhead_ce_workspace_bytes": [_ll, _i],
+    "klab_lmhead_ce_fwd": [_vp, _ll, _i, _i, _vp, _ll, _vp, _ll, _f, _vp, _vp, _vp, _vp, _vp],
+    "klab_lmhead_ce_bwd_chunk": [_vp, _ll, _i, _vp, _ll, _vp, _ll, _f, _vp, _vp, _vp, _vp, _i, _i, _vp, _ll],
     "klab_cast": [_vp, _i, _i, _ll, _vp, _vp],
     "klab_greedy_step": [_vp, _i, _i, _vp, _ll, _vp, _ll, _i, _vp, _i, _i],
     "klab_dropout_apply": [_vp, _i, _ll, _vp, _vp, _f, _ull, _vp],
@@ -86,7 +89,7 @@ SIGNATURES = {
 }
 _RESTYPES = {"klab_last_error": C.c_char_p, "klab_launch_count": C.c_longlong,
              "klab_norm_bwd_workspace_bytes": C.c_longlong, "klab_colsum_workspace_bytes": C.c_longlong,
-             "klab_t5_attention_bwd_workspace_bytes": C.c_longlong}
+             "klab_t5_attention_bwd_workspace_bytes": C.c_longlong, "klab_lmhead_ce_workspace_bytes": C.c_longlong}
 
 
 def _declare(l: C.CDLL) -> None:

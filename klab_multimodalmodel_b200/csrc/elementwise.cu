@@ -1,10 +1,9 @@
 // Bandwidth-bound helpers around the GEMMs: dtype casts, embedding gather / scatter-add (K11 + T8),
 // patch-embedding im2col (K1), patch-merging gather / scatter (K7), cross-entropy over materialised logits
 // (K10, generic path) and small vector utilities.
-#include "common.cuh"
+#include "gemm.cuh"
 
 namespace klab {
-void count_launch(int n = 1);
 namespace {
 
 template <typename TI, typename TO>
@@ -144,6 +143,37 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const T* __restrict__ logit
         if (lab != -100) {
             if (lab < 0 || lab >= V) atomicExch(err, 2);
             else loss = l - to_f32(lr[lab]);
+        }
+        row_loss[row] = loss;
+    }
+}
+
+// Fused LM-head CE, second half: combine the per-tile online-softmax partials of a row (one warp per row, fixed order):
+// lse = m + log(sum_i s_i exp(m_i - m)), row_loss = lse - logit[label] (0 for ignored rows)
+__global__ void __launch_bounds__(256) lmhead_ce_finalize_kernel(const float2* __restrict__ partials, int num_parts, const float* __restrict__ label_logit,
+                                                                 const long long* __restrict__ labels, long long rows, int V,
+                                                                 float* __restrict__ lse, float* __restrict__ row_loss, int* __restrict__ err) {
+    const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float2* p = partials + row * num_parts;
+    float m = -INFINITY;
+    for (int i = lane; i < num_parts; i += 32) m = fmaxf(m, p[i].x);
+    m = warp_max(m);
+    float s = 0.0f;
+    for (int i = lane; i < num_parts; i += 32) {
+        const float2 q = p[i];
+        if (q.x > -INFINITY) s += q.y * __expf(q.x - m);
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+        const float l = m + __logf(s);
+        lse[row] = l;
+        const long long lab = labels[row];
+        float loss = 0.0f;
+        if (lab != -100) {
+            if (lab < 0 || lab >= V) atomicExch(err, 2);
+            else loss = l - label_logit[row];
         }
         row_loss[row] = loss;
     }
@@ -396,6 +426,41 @@ int klab_ce_fwd(void* stream, int dtype, long long rows, int V, const void* logi
     KLAB_LAUNCH_CHECK();
     count_launch(2);
     return KLAB_OK;
+}
+
+long long klab_lmhead_ce_workspace_bytes(long long rows, int V) {
+    return static_cast<long long>(sizeof(float2)) * rows * klab::lmhead_ce_num_parts(V) + static_cast<long long>(sizeof(float)) * 2 * rows;
+}
+
+int klab_lmhead_ce_fwd(void* stream, long long rows, int V, int d, const void* h, long long ldh, const void* E, long long lde, float alpha,
+                       const long long* labels, float* lse, float* stats, void* workspace, int* err_flag) {
+    using namespace klab;
+    if (int rc = klab_check_device()) return rc;
+    KLAB_REQUIRE(rows > 0 && rows < (1ll << 31) && V > 0 && d > 0 && workspace, "lmhead_ce_fwd: bad arguments rows=%lld V=%d d=%d", rows, V, d);
+    KLAB_REQUIRE(((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(E)) & 15) == 0, "lmhead_ce_fwd: operands must be 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int parts = lmhead_ce_num_parts(V);
+    float2* partials = static_cast<float2*>(workspace);
+    float* label_logit = reinterpret_cast<float*>(partials + rows * parts);
+    float* row_loss = label_logit + rows;
+    if (int rc = lmhead_ce_fwd_launch(st, static_cast<int>(rows), V, d, h, ldh, E, lde, alpha, labels, partials, label_logit)) return rc;
+    lmhead_ce_finalize_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(partials, parts, label_logit, labels, rows, V, lse, row_loss, err_flag);
+    KLAB_LAUNCH_CHECK();
+    ce_reduce_kernel<<<1, 256, 0, st>>>(row_loss, labels, rows, stats);
+    KLAB_LAUNCH_CHECK();
+    count_launch(2);
+    return KLAB_OK;
+}
+
+int klab_lmhead_ce_bwd_chunk(void* stream, long long rows, int d, const void* h, long long ldh, const void* E_chunk, long long lde, float alpha,
+                             const long long* labels, const float* lse, const float* stats, const float* gscale, int v0, int vc,
+                             void* dlogits, long long ldd) {
+    using namespace klab;
+    if (int rc = klab_check_device()) return rc;
+    KLAB_REQUIRE(rows > 0 && rows < (1ll << 31) && vc > 0 && v0 >= 0 && ldd >= vc, "lmhead_ce_bwd_chunk: bad arguments rows=%lld v0=%d vc=%d ldd=%lld", rows, v0, vc, ldd);
+    KLAB_REQUIRE(((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(E_chunk)) & 15) == 0, "lmhead_ce_bwd_chunk: operands must be 16-byte aligned");
+    return lmhead_ce_bwd_launch(static_cast<cudaStream_t>(stream), static_cast<int>(rows), vc, d, h, ldh, E_chunk, lde, alpha, labels, lse,
+                                stats, gscale, v0, dlogits, ldd);
 }
 
 // Overwrites logits[:, 0:ld_pad) with d(loss)/d(logits) * (*gscale); columns [V, ld_pad) are zeroed.

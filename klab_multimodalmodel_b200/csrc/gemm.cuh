@@ -177,6 +177,13 @@ int gemm_tc_launch(cudaStream_t stream, int M, int N, int K, const void* A, long
 int gemm_simt_launch(cudaStream_t stream, int in_dtype, int M, int N, int K, const void* A, long long lda, int a_mn,
                      const void* B, long long ldb, int b_mn, void* D, long long ldd, const klab_gemm_epilogue& epi);
 
+int lmhead_ce_num_parts(int V);
+int lmhead_ce_fwd_launch(cudaStream_t stream, int M, int V, int d, const void* h, long long ldh, const void* E, long long lde, float alpha,
+                         const long long* labels, float2* partials, float* label_logit);
+int lmhead_ce_bwd_launch(cudaStream_t stream, int M, int vc, int d, const void* h, long long ldh, const void* E_chunk, long long lde,
+                         float alpha, const long long* labels, const float* lse, const float* stats, const float* gscale, int v0,
+                         void* dlogits, long long ldd);
+
 void count_launch(int n = 1);
 
 }  // namespace klab

@@ -53,11 +53,28 @@ struct SplitK {
     int splits;
 };
 
-template <bool A_MN, bool B_MN>
+// Epilogue modes of the kernel.  EPI_STORE is the generic fused epilogue (gemm.cuh).  The two CE modes turn the LM-head GEMM
+// into a vocab-tiled cross entropy that never writes the logits (K10; HF/models/t5/modeling_t5.py:1105-1117):
+//   EPI_CE_FWD : per (row, vocab tile, warp quarter) an online-softmax partial (running max, sum of exp) and the label's logit;
+//   EPI_CE_BWD : d loss / d logits = (exp(logit - lse) - onehot) * g / n_valid for one vocab chunk, written as bf16.
+enum { EPI_STORE = 0, EPI_CE_FWD = 1, EPI_CE_BWD = 2 };
+
+struct CeArgs {
+    const long long* labels;   // [M] int64, -100 = ignore
+    float2* partials;          // fwd: [M][num_parts] (max, sum exp)
+    float* label_logit;        // fwd: [M]
+    const float* lse;          // bwd: [M]
+    const float* stats;        // bwd: {mean loss, n_valid}
+    const float* gscale;       // bwd: upstream gradient of the loss (device scalar) or null
+    int col_offset;            // vocabulary index of column 0 of this GEMM (chunked backward)
+    int num_parts;             // fwd: partials per row = 4 * number of N tiles
+};
+
+template <bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     void* __restrict__ D, long long ldd, int M, int N, int K, int BN, int stages, SplitK sk,
-                    klab_gemm_epilogue epi) {
+                    klab_gemm_epilogue epi, CeArgs ce) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* ctrl = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* ring = ctrl + CTRL_BYTES;
@@ -191,7 +208,66 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int r_in = sub * 32 + lane;
             const long long row = static_cast<long long>(m0) + r_in;
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * ACC_STRIDE;
-            if (splits == 1) {
+            if constexpr (EPI == EPI_CE_FWD) {
+                const long long lab = row < M ? ce.labels[row] - ce.col_offset : -1;
+                float m_run = -INFINITY, s_run = 0.0f;
+#pragma unroll 1
+                for (int c = quarter; c < nchunks; c += 4) {
+                    uint32_t r[CH];
+                    tmem_ld_32x16(t_row + c * CH, r);
+                    tmem_ld_wait();
+                    const int col0 = n0 + c * CH;
+                    const int nvalid = min(CH, N - col0);
+                    if (row < M && nvalid > 0) {
+                        float x[CH];
+                        float cmax = -INFINITY;
+#pragma unroll
+                        for (int i = 0; i < CH; ++i) {
+                            x[i] = i < nvalid ? __uint_as_float(r[i]) * epi.alpha : -INFINITY;
+                            cmax = fmaxf(cmax, x[i]);
+                        }
+                        if (lab >= col0 && lab < col0 + nvalid) {
+                            float sel = 0.0f;
+#pragma unroll
+                            for (int i = 0; i < CH; ++i) sel = (lab - col0 == i) ? x[i] : sel;
+                            ce.label_logit[row] = sel;
+                        }
+                        const float m_new = fmaxf(m_run, cmax);
+                        float acc_s = s_run * __expf(m_run - m_new);          // m_run = -inf: exp(-inf) = 0 (m_new is finite here)
+#pragma unroll
+                        for (int i = 0; i < CH; ++i) acc_s += __expf(x[i] - m_new);
+                        s_run = acc_s;
+                        m_run = m_new;
+                    }
+                }
+                if (row < M) ce.partials[row * ce.num_parts + (tile % num_n) * 4 + quarter] = make_float2(m_run, s_run);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            } else if constexpr (EPI == EPI_CE_BWD) {
+                const long long lab_raw = row < M ? ce.labels[row] : -100;
+                const long long lab = lab_raw - ce.col_offset;
+                const float l = row < M ? ce.lse[row] : 0.0f;
+                const float g = lab_raw == -100 ? 0.0f : (ce.gscale ? *ce.gscale : 1.0f) / ce.stats[1];
+#pragma unroll 1
+                for (int c = quarter; c < nchunks; c += 4) {
+                    uint32_t r[CH];
+                    tmem_ld_32x16(t_row + c * CH, r);
+                    tmem_ld_wait();
+                    const int col0 = n0 + c * CH;
+                    const int nvalid = min(CH, N - col0);
+                    if (row < M && nvalid > 0) {
+                        float v[CH];
+#pragma unroll
+                        for (int i = 0; i < CH; ++i)
+                            v[i] = (__expf(__uint_as_float(r[i]) * epi.alpha - l) - (lab - col0 == i ? 1.0f : 0.0f)) * g;
+                        store_chunk<CH>(D, KLAB_BF16, row * ldd + col0, nvalid, v);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            } else if (splits == 1) {
 #pragma unroll 1
                 for (int c = quarter; c < nchunks; c += 4) {
                     uint32_t r[CH];
@@ -361,9 +437,9 @@ void pick_config(int M, int N, int K, bool b_mn, bool can_split, size_t ws_bytes
     }
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int EPI = EPI_STORE>
 int launch_cfg(cudaStream_t stream, int M, int N, int K, int bn, int splits, Workspace* w, const void* A, long long lda, const void* B,
-               long long ldb, void* D, long long ldd, const klab_gemm_epilogue& epi) {
+               long long ldb, void* D, long long ldd, const klab_gemm_epilogue& epi, const CeArgs& ce = CeArgs{}) {
     CUtensorMap ta, tb;
     int rc;
     // A: K-major -> tensor [M rows, K cols], box [128, 64];  MN-major -> tensor [K rows, M cols], box [64, 64]
@@ -373,7 +449,7 @@ int launch_cfg(cudaStream_t stream, int M, int N, int K, int bn, int splits, Wor
     rc = B_MN ? make_tmap_2d_bf16(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, 64)
               : make_tmap_2d_bf16(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, bn, 64);
     if (rc) return rc;
-    auto kern = gemm_bf16_tc_kernel<A_MN, B_MN>;
+    auto kern = gemm_bf16_tc_kernel<A_MN, B_MN, EPI>;
     static bool attr_set = false;   // per instantiation
     if (!attr_set) {
         KLAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -398,7 +474,7 @@ int launch_cfg(cudaStream_t stream, int M, int N, int K, int bn, int splits, Wor
     static const bool pdl = []() { const char* e = getenv("KLAB_PDL"); return !(e && e[0] == '0'); }();
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    KLAB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, D, ldd, M, N, K, bn, stages_for(bn), sk, epi));
+    KLAB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, D, ldd, M, N, K, bn, stages_for(bn), sk, epi, ce));
     KLAB_LAUNCH_CHECK();
     count_launch();
     if (splits > 1) {
@@ -446,6 +522,38 @@ int gemm_tc_launch(cudaStream_t stream, int M, int N, int K, const void* A, long
     if (!a_mn && b_mn) return launch_cfg<false, true>(stream, M, N, K, bn, splits, w, A, lda, B, ldb, D, ldd, epi);
     if (a_mn && !b_mn) return launch_cfg<true, false>(stream, M, N, K, bn, splits, w, A, lda, B, ldb, D, ldd, epi);
     return launch_cfg<true, true>(stream, M, N, K, bn, splits, w, A, lda, B, ldb, D, ldd, epi);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K10 (hot path): LM head fused with the cross entropy, vocab-tiled, logits never written
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int CE_BN = 256;
+
+int lmhead_ce_num_parts(int V) { return 4 * ((V + CE_BN - 1) / CE_BN); }
+
+// partials[row][tile * 4 + quarter] = (max, sum exp) of alpha * h[row] . E[col] over the tile's columns; label_logit[row]
+int lmhead_ce_fwd_launch(cudaStream_t stream, int M, int V, int d, const void* h, long long ldh, const void* E, long long lde, float alpha,
+                         const long long* labels, float2* partials, float* label_logit) {
+    KLAB_REQUIRE(M > 0 && V > 0 && d > 0 && ldh % 8 == 0 && lde % 8 == 0, "lmhead_ce_fwd: bad shape M=%d V=%d d=%d", M, V, d);
+    klab_gemm_epilogue epi{};
+    epi.alpha = alpha;
+    epi.out_dtype = KLAB_BF16;
+    CeArgs ce{};
+    ce.labels = labels; ce.partials = partials; ce.label_logit = label_logit; ce.col_offset = 0; ce.num_parts = lmhead_ce_num_parts(V);
+    return launch_cfg<false, false, EPI_CE_FWD>(stream, M, V, d, CE_BN, 1, nullptr, h, ldh, E, lde, nullptr, 0, epi, ce);
+}
+
+// dlogits[:, 0:vc) = d loss / d logits of vocabulary columns [v0, v0 + vc), bf16
+int lmhead_ce_bwd_launch(cudaStream_t stream, int M, int vc, int d, const void* h, long long ldh, const void* E_chunk, long long lde,
+                         float alpha, const long long* labels, const float* lse, const float* stats, const float* gscale, int v0,
+                         void* dlogits, long long ldd) {
+    KLAB_REQUIRE(M > 0 && vc > 0 && d > 0 && ldh % 8 == 0 && lde % 8 == 0, "lmhead_ce_bwd: bad shape M=%d vc=%d d=%d", M, vc, d);
+    klab_gemm_epilogue epi{};
+    epi.alpha = alpha;
+    epi.out_dtype = KLAB_BF16;
+    CeArgs ce{};
+    ce.labels = labels; ce.lse = lse; ce.stats = stats; ce.gscale = gscale; ce.col_offset = v0;
+    return launch_cfg<false, false, EPI_CE_BWD>(stream, M, vc, d, CE_BN, 1, nullptr, h, ldh, E_chunk, lde, dlogits, ldd, epi, ce);
 }
 
 }  // namespace klab

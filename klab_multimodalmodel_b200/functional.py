@@ -419,9 +419,18 @@ class DecoderEmbedFn(torch.autograd.Function):
         return None, dtab, None, None, None, None
 
 
+LMHEAD_VOCAB_CHUNK = 8192      # backward recomputes the logits this many vocabulary columns at a time (scratch stays in L2)
+
+
 class LMHeadLossFn(torch.autograd.Function):
     """final RMSNorm -> dropout (training) -> * d_model**-0.5 -> tied LM head -> CrossEntropyLoss(ignore_index=-100),
-    HF/models/t5/modeling_t5.py:767-768,1105-1117."""
+    HF/models/t5/modeling_t5.py:767-768,1105-1117.
+
+    bf16 (hot path): the LM-head GEMM is fused with the cross entropy and vocab-tiled -- its epilogue reduces every 128 x 256
+    logits tile to online-softmax partials straight out of TMEM, so the [rows, 32128] logits are never written; backward
+    recomputes them one vocabulary chunk at a time into a chunk-sized scratch of d loss / d logits and feeds the two gradient
+    GEMMs from it (dH accumulates in fp32, dE rows of the chunk are written once).
+    fp32 (strict parity path): materialised logits + klab_ce_fwd / klab_ce_bwd."""
 
     @staticmethod
     def forward(ctx, x, ln_w, table, labels, cache, eps, p, seed, seed_ptr):
@@ -431,13 +440,18 @@ class LMHeadLossFn(torch.autograd.Function):
         n, rstd = O.rmsnorm_fwd(x, ln_w, eps)
         if p > 0.0:
             n = O.dropout_apply(n, p, seed, seed_ptr)
-        vpad = (V + 7) // 8 * 8
-        logits = O.linear_fwd(n, tab, alpha=d ** -0.5, ldd_pad=vpad)
         lab = labels.reshape(-1).contiguous()
-        lse, stats = O.ce_fwd(logits, V, lab)
+        fused = cd == torch.bfloat16
+        if fused:
+            logits, vpad = None, 0
+            lse, stats = O.lmhead_ce_fwd(n, tab, d ** -0.5, lab)
+        else:
+            vpad = (V + 7) // 8 * 8
+            logits = O.linear_fwd(n, tab, alpha=d ** -0.5, ldd_pad=vpad)
+            lse, stats = O.ce_fwd(logits, V, lab)
         if _needs_grad((x, ln_w, table)):
             ctx.save_for_backward(x, ln_w, table, lab, rstd, n, logits, lse, stats)
-            ctx.cache, ctx.vpad, ctx.p, ctx.seed, ctx.seed_ptr = cache, vpad, p, seed, seed_ptr
+            ctx.cache, ctx.vpad, ctx.p, ctx.seed, ctx.seed_ptr, ctx.fused = cache, vpad, p, seed, seed_ptr, fused
             ctx.step_token = _StepToken()
         return stats[0].clone()
 
@@ -448,9 +462,23 @@ class LMHeadLossFn(torch.autograd.Function):
         V, d = table.shape
         tab = ctx.cache.get([table], x.dtype)
         g = gloss.reshape(1).to(torch.float32).contiguous()
-        O.ce_bwd(logits, V, ctx.vpad, lab, lse, stats, g)            # logits now hold d loss / d logits
-        dn = O.linear_dgrad(logits, tab, alpha=d ** -0.5)
-        dtab = O.linear_wgrad(logits, n, alpha=d ** -0.5)
+        alpha = d ** -0.5
+        if ctx.fused:
+            rows = n.shape[0]
+            chunk = min(LMHEAD_VOCAB_CHUNK, (V + 7) // 8 * 8)
+            scratch = torch.empty(rows, chunk, dtype=torch.bfloat16, device=n.device)
+            dn32 = torch.empty(rows, d, dtype=torch.float32, device=n.device)
+            dtab = torch.empty(V, d, dtype=torch.float32, device=n.device)
+            for v0 in range(0, V, chunk):
+                vc = min(chunk, V - v0)
+                dl = O.lmhead_ce_bwd_chunk(n, tab, alpha, lab, lse, stats, g, v0, vc, scratch)
+                O.gemm(dl, tab[v0:v0 + vc], rows, d, vc, b_mn=True, out=dn32, alpha=alpha, accumulate=v0 > 0)      # dH (+)= dlogits E_chunk
+                O.gemm(dl, n, vc, d, rows, a_mn=True, b_mn=True, out=dtab[v0:v0 + vc], alpha=alpha)                 # dE_chunk = dlogits^T H
+            dn = O.cast(dn32, x.dtype)
+        else:
+            O.ce_bwd(logits, V, ctx.vpad, lab, lse, stats, g)            # logits now hold d loss / d logits
+            dn = O.linear_dgrad(logits, tab, alpha=alpha)
+            dtab = O.linear_wgrad(logits, n, alpha=alpha)
         if ctx.p > 0.0:
             dn = O.dropout_apply(dn, ctx.p, ctx.seed, ctx.seed_ptr)
         dx, dln = O.rmsnorm_bwd(dn, x, ln_w, rstd)

@@ -389,6 +389,31 @@ def ce_bwd(logits, V, ld_pad, labels, lse, stats, gscale):
                                 labels.data_ptr(), lse.data_ptr(), stats.data_ptr(), _p(gscale)))
 
 
+def lmhead_ce_fwd(h, table, alpha, labels):
+    """Fused LM head + cross entropy forward (bf16 tcgen05 path): the logits (alpha * h table^T) are never written.
+    Returns (lse [rows] fp32, stats [2] fp32 = {mean loss over non-ignored rows, #non-ignored rows})."""
+    rows, d = h.shape
+    V = table.shape[0]
+    assert h.dtype == torch.bfloat16 and table.dtype == torch.bfloat16 and h.stride(1) == 1 and table.stride(1) == 1
+    dev = h.device
+    lse = torch.empty(rows, dtype=torch.float32, device=dev)
+    stats = torch.empty(2, dtype=torch.float32, device=dev)
+    ws = _bytes(L.lib().klab_lmhead_ce_workspace_bytes(rows, V), dev)
+    L.check(L.lib().klab_lmhead_ce_fwd(_stream(), rows, V, d, h.data_ptr(), h.stride(0), table.data_ptr(), table.stride(0), alpha,
+                                       labels.data_ptr(), lse.data_ptr(), stats.data_ptr(), ws.data_ptr(), err_flag(dev).data_ptr()))
+    return lse, stats
+
+
+def lmhead_ce_bwd_chunk(h, table, alpha, labels, lse, stats, gscale, v0, vc, out):
+    """d loss / d logits (times *gscale) of vocabulary columns [v0, v0 + vc), recomputed from h and table, bf16 into out[:, :vc]."""
+    rows, d = h.shape
+    chunk = table[v0:v0 + vc]
+    L.check(L.lib().klab_lmhead_ce_bwd_chunk(_stream(), rows, d, h.data_ptr(), h.stride(0), chunk.data_ptr(), chunk.stride(0), alpha,
+                                             labels.data_ptr(), lse.data_ptr(), stats.data_ptr(), _p(gscale), v0, vc, out.data_ptr(),
+                                             out.stride(0)))
+    return out[:, :vc]
+
+
 def cast(x, dtype, out=None):
     x = x.contiguous()
     y = torch.empty(x.shape, dtype=dtype, device=x.device) if out is None else out

@@ -386,3 +386,46 @@ def test_fused_adam_matches_torch_adam():
         ob2.load_state_dict(sd)                 # torch's Adam accepts our state (python-int step counts included)
         for pa, pb in zip(ps_a, ps_b):          # keep the two trajectories identical for the next round
             pb.data.copy_(pa.data)
+
+
+@pytest.mark.parametrize("rows,V,d", [(300, 1000, 128), (64, 32128, 256), (2048, 520, 64)])
+def test_fused_lmhead_cross_entropy(rows, V, d):
+    """K10 hot path: LM head fused with the cross entropy (logits never written) against fp32 torch on the same bf16 operands:
+    lse / mean loss with ignore_index, an out-of-range label raises, and the chunked d loss / d logits."""
+    from klab_multimodalmodel_b200 import ops as o
+    torch.manual_seed(rows + V)
+    h = (torch.randn(rows, d, device="cuda") * 2.0).bfloat16()
+    E = (torch.randn(V, d, device="cuda") * 1.5).bfloat16()
+    labels = torch.randint(0, V, (rows,), device="cuda")
+    labels[::7] = -100
+    labels[1] = V - 1
+    labels[2] = 0
+    alpha = d ** -0.5
+    ref_logits = (h.float() @ E.float().t()) * alpha
+    ref_lse = torch.logsumexp(ref_logits, dim=-1)
+    ref_loss = torch.nn.functional.cross_entropy(ref_logits, labels, ignore_index=-100)
+    lse, stats = o.lmhead_ce_fwd(h, E, alpha, labels)
+    o.check_err_flag(h.device)
+    torch.testing.assert_close(lse, ref_lse, rtol=1e-4, atol=1e-3)
+    assert abs(stats[0].item() - ref_loss.item()) <= 1e-4 * abs(ref_loss.item()) + 1e-4
+    assert stats[1].item() == float((labels != -100).sum().item())
+    # backward, chunked: (softmax - onehot) * g / n_valid, zero rows for ignored labels
+    g = torch.tensor([0.37], device="cuda")
+    ref_d = torch.softmax(ref_logits, dim=-1)
+    valid = labels != -100
+    ref_d[valid, labels[valid]] -= 1.0
+    ref_d = ref_d * (0.37 / valid.sum().item())
+    ref_d[~valid] = 0.0
+    chunk = 512 if V > 512 else 264
+    scratch = torch.empty(rows, chunk, dtype=torch.bfloat16, device="cuda")
+    for v0 in range(0, V, chunk):
+        vc = min(chunk, V - v0)
+        dl = o.lmhead_ce_bwd_chunk(h, E, alpha, labels, lse, stats, g, v0, vc, scratch)
+        ref = ref_d[:, v0:v0 + vc]
+        err = (dl.float() - ref).abs().max().item()
+        assert err <= 1e-2 * ref.abs().max().item() + 1e-7, (v0, err)
+    bad = labels.clone()
+    bad[5] = V + 3
+    o.lmhead_ce_fwd(h, E, alpha, bad)
+    with pytest.raises(IndexError):
+        o.check_err_flag(h.device)
