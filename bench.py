@@ -398,6 +398,13 @@ def run_ours(args, w):
     for _ in range(max(args.warmup, 3)):
         resident_step()
     torch.cuda.synchronize()
+    if args.profile_range:                                # ncu --profile-from-start off: exactly the timed steps are profiled
+        torch.cuda.profiler.start()
+        for _ in range(args.steps):
+            resident_step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     sampler = ClockSampler(local) if rank == 0 else None
     time.sleep(0.3)
     lo = sampler.mark() if sampler else 0
@@ -482,6 +489,8 @@ def main():
                     help="klab = fused multi-tensor Adam (SURVEY 8f N1, same update rule); torch = stock torch.optim.Adam")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verbose", action="store_true")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="for ncu --profile-from-start off: cudaProfilerStart/Stop around the K steps after warm-up, then exit (no JSON line)")
     ap.add_argument("--gemm-probe", action="store_true", help="development aid: only replay (and check) the step's GEMM signatures")
     args = ap.parse_args()
     global _REAL_STDOUT

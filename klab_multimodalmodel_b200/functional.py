@@ -150,6 +150,16 @@ def _needs_grad(tensors) -> bool:
     return _OUTER_GRAD[0] and any(t is not None and t.requires_grad for t in tensors)
 
 
+def _grad_outputs(outs, graphed):
+    """Gradients handed back to autograd.  A captured region returns the SAME static tensors on every replay, and its tuple
+    keeps a reference to them, so AccumulateGrad (which only adopts a gradient nobody else holds) would clone every parameter
+    gradient every step -- ~3 GB of device copies for T5-large.  Fresh aliases of the static storage are adopted as .grad
+    without a copy; `_detach_aliased_grads` moves an accumulated value out of the way before the next replay overwrites it."""
+    if not graphed:
+        return tuple(outs)
+    return tuple(o.detach() if torch.is_tensor(o) else o for o in outs)
+
+
 def _detach_aliased_grads(params):
     """Gradient accumulation: if a parameter's .grad still IS the static gradient buffer of a captured backward region, the
     replay about to run would overwrite it -- move the accumulated value out first."""
@@ -327,10 +337,10 @@ class T5BlockFn(torch.autograd.Function):
         acts, ctx.acts = ctx.acts, None
         if ctx.graphed:
             _detach_aliased_grads(params if table is None else params + [table])
-        outs, _ = POOL.run(("t5b", id(c)), _t5_block_bwd_body, (dout.contiguous(), x, enc_out) + tuple(acts),
-                           (c, table) + tuple(params), allow_graph=ctx.graphed)
+        outs, graphed = POOL.run(("t5b", id(c)), _t5_block_bwd_body, (dout.contiguous(), x, enc_out) + tuple(acts),
+                                 (c, table) + tuple(params), allow_graph=ctx.graphed)
         c.busy = False
-        return (None,) + tuple(outs)
+        return (None,) + _grad_outputs(outs, graphed)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -629,7 +639,7 @@ class SwinBlockFn(torch.autograd.Function):
         acts, ctx.acts = ctx.acts, None
         if ctx.graphed:
             _detach_aliased_grads(params)
-        outs, _ = POOL.run(("swb", id(c)), _swin_block_bwd_body, (dout.contiguous(), x) + tuple(acts), (c,) + tuple(params),
-                           allow_graph=ctx.graphed)
+        outs, graphed = POOL.run(("swb", id(c)), _swin_block_bwd_body, (dout.contiguous(), x) + tuple(acts), (c,) + tuple(params),
+                                 allow_graph=ctx.graphed)
         c.busy = False
-        return (None,) + tuple(outs)
+        return (None,) + _grad_outputs(outs, graphed)
