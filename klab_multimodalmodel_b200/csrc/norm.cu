@@ -279,23 +279,34 @@ norm_bwd_kernel(const T* __restrict__ dy, RowMap dym, const T* __restrict__ x, R
     }
 }
 
-// out[a][c] (+)= sum_p part[a][p, c] for a in {0 (, 1)}: blockDim = (32 cols, 8 part lanes), grid = (ceil(d/32), arrays)
-__global__ void __launch_bounds__(256)
+// out[a][c] (+)= sum_p part[a][p, c] for a in {0 (, 1)}: blockDim = (32 cols, 32 part lanes), grid = (ceil(d/32), arrays).
+// Launched ~270 times per training step behind every norm backward / bias gradient, so it is sized for latency: 1024 threads
+// keep nparts/32 independent loads in flight per thread (it used to be 8 lanes and ~10 us per launch).
+constexpr int FIN_LANES = 32;
+__global__ void __launch_bounds__(32 * FIN_LANES)
 colsum_finalize_kernel(const float* __restrict__ part0, const float* __restrict__ part1, int nparts, int d, float* __restrict__ out0,
                        float* __restrict__ out1, int accumulate) {
-    __shared__ float red[8][33];
+    __shared__ float red[FIN_LANES][33];
     const float* part = blockIdx.y ? part1 : part0;
     float* out = blockIdx.y ? out1 : out0;
     const int c = blockIdx.x * 32 + threadIdx.x;
-    float s = 0.0f;
-    if (c < d)
-        for (int p = threadIdx.y; p < nparts; p += 8) s += part[static_cast<long long>(p) * d + c];
-    red[threadIdx.y][threadIdx.x] = s;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    if (c < d) {
+        int p = threadIdx.y;
+        for (; p + 3 * FIN_LANES < nparts; p += 4 * FIN_LANES) {
+            s0 += part[static_cast<long long>(p) * d + c];
+            s1 += part[static_cast<long long>(p + FIN_LANES) * d + c];
+            s2 += part[static_cast<long long>(p + 2 * FIN_LANES) * d + c];
+            s3 += part[static_cast<long long>(p + 3 * FIN_LANES) * d + c];
+        }
+        for (; p < nparts; p += FIN_LANES) s0 += part[static_cast<long long>(p) * d + c];
+    }
+    red[threadIdx.y][threadIdx.x] = (s0 + s1) + (s2 + s3);
     __syncthreads();
     if (threadIdx.y == 0 && c < d) {
         float t = 0.0f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+        for (int i = 0; i < FIN_LANES; ++i) t += red[i][threadIdx.x];
         out[c] = accumulate ? out[c] + t : t;
     }
 }
@@ -319,6 +330,60 @@ colsum_partial_kernel(const T* __restrict__ x, long long ld, long long rows, int
         for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
         part[static_cast<long long>(blockIdx.y) * d + c] = t;
     }
+}
+
+// bf16 fast path (d % 8 == 0, 16-byte aligned rows): every thread owns 8 adjacent columns and streams rows with 16-byte loads,
+// four rows in flight; blockDim = (32 column vectors, 8 row lanes), grid = (ceil(d/256), row_chunks).  HBM/L2-bound.
+__global__ void __launch_bounds__(256)
+colsum_partial_bf16x8_kernel(const __nv_bfloat16* __restrict__ x, long long ld, long long rows, int d, float* __restrict__ part) {
+    __shared__ float red[8][32][9];
+    const int c0 = (blockIdx.x * 32 + threadIdx.x) * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+    if (c0 < d) {
+        const long long step = static_cast<long long>(gridDim.y) * 8;
+        long long r = static_cast<long long>(blockIdx.y) * 8 + threadIdx.y;
+        const __nv_bfloat16* px = x + c0;
+        auto add = [&](const uint4& q) {
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                acc[2 * j] += __uint_as_float(w[j] << 16);
+                acc[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+            }
+        };
+        for (; r + 3 * step < rows; r += 4 * step) {
+            const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(px + r * ld));
+            const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(px + (r + step) * ld));
+            const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(px + (r + 2 * step) * ld));
+            const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(px + (r + 3 * step) * ld));
+            add(q0); add(q1); add(q2); add(q3);
+        }
+        for (; r < rows; r += step) add(__ldg(reinterpret_cast<const uint4*>(px + r * ld)));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.y][threadIdx.x][j] = acc[j];
+    __syncthreads();
+    // 256 threads finish the 32 x 8 columns of this block: thread -> (column vector, element)
+    const int tid = threadIdx.y * 32 + threadIdx.x, cv = tid >> 3, j = tid & 7;
+    const int c = (blockIdx.x * 32 + cv) * 8 + j;
+    if (c < d) {
+        float t = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][cv][j];
+        part[static_cast<long long>(blockIdx.y) * d + c] = t;
+    }
+}
+
+inline long long colsum_chunks(long long rows, int d, bool vec) {
+    const long long col_blocks = vec ? (d + 255) / 256 : (d + 31) / 32;
+    long long chunks = (8ll * sm_count() + col_blocks - 1) / col_blocks;       // ~8 CTAs per SM in total
+    const long long by_rows = (rows + 31) / 32;                                 // at least 4 rows per row lane
+    if (chunks > by_rows) chunks = by_rows;
+    if (chunks > 1024) chunks = 1024;
+    if (chunks < 1) chunks = 1;
+    return chunks;
 }
 
 template <typename T>
@@ -381,7 +446,7 @@ int norm_bwd_t(cudaStream_t st, const void* dy, RowMap dym, const void* x, RowMa
     }
 #undef KLAB_NORM_BWD_ARGS
     KLAB_LAUNCH_CHECK();
-    colsum_finalize_kernel<<<dim3((d + 31) / 32, IS_LN ? 2 : 1), dim3(32, 8), 0, st>>>(part_dg, part_db, grid, d, dgamma, dbeta, accumulate);
+    colsum_finalize_kernel<<<dim3((d + 31) / 32, IS_LN ? 2 : 1), dim3(32, FIN_LANES), 0, st>>>(part_dg, part_db, grid, d, dgamma, dbeta, accumulate);
     KLAB_LAUNCH_CHECK();
     count_launch(2);
     return KLAB_OK;
@@ -452,10 +517,7 @@ int klab_layernorm_bwd(void* stream, int dtype, long long rows, int d, const voi
 }
 
 long long klab_colsum_workspace_bytes(long long rows, int d) {
-    long long chunks = (rows + 255) / 256;
-    if (chunks > 64) chunks = 64;
-    if (chunks < 1) chunks = 1;
-    return chunks * d * static_cast<long long>(sizeof(float));
+    return 1024ll * d * static_cast<long long>(sizeof(float));          // upper bound of colsum_chunks() partial rows
 }
 
 // out[c] (+)= sum_r x[r, c]   (bias gradients of the Swin linears, SURVEY.md K5 backward)
@@ -463,17 +525,22 @@ int klab_colsum(void* stream, int dtype, long long rows, int d, const void* x, l
                 void* workspace) {
     if (int rc = klab_check_device()) return rc;
     KLAB_REQUIRE(rows > 0 && d > 0, "colsum: empty input rows=%lld d=%d", rows, d);
-    long long chunks = (rows + 255) / 256;
-    if (chunks > 64) chunks = 64;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const dim3 grid((d + 31) / 32, static_cast<unsigned>(chunks)), block(32, 8);
     float* part = static_cast<float*>(workspace);
-    if (dtype == KLAB_BF16)
-        colsum_partial_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows, d, part);
-    else
-        colsum_partial_kernel<float><<<grid, block, 0, st>>>(reinterpret_cast<const float*>(x), ldx, rows, d, part);
+    const bool vec = dtype == KLAB_BF16 && d % 8 == 0 && ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    const long long chunks = colsum_chunks(rows, d, vec);
+    if (vec) {
+        colsum_partial_bf16x8_kernel<<<dim3((d + 255) / 256, static_cast<unsigned>(chunks)), dim3(32, 8), 0, st>>>(
+            reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows, d, part);
+    } else {
+        const dim3 grid((d + 31) / 32, static_cast<unsigned>(chunks)), block(32, 8);
+        if (dtype == KLAB_BF16)
+            colsum_partial_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), ldx, rows, d, part);
+        else
+            colsum_partial_kernel<float><<<grid, block, 0, st>>>(reinterpret_cast<const float*>(x), ldx, rows, d, part);
+    }
     KLAB_LAUNCH_CHECK();
-    colsum_finalize_kernel<<<dim3((d + 31) / 32, 1), dim3(32, 8), 0, st>>>(part, nullptr, static_cast<int>(chunks), d, out, nullptr, accumulate);
+    colsum_finalize_kernel<<<dim3((d + 31) / 32, 1), dim3(32, FIN_LANES), 0, st>>>(part, nullptr, static_cast<int>(chunks), d, out, nullptr, accumulate);
     KLAB_LAUNCH_CHECK();
     count_launch(2);
     return KLAB_OK;

@@ -100,22 +100,27 @@ __device__ __forceinline__ float inv_norm32(const float* v, float& norm) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// forward: grid (ceil(B*nW / 2), heads), 128 threads; thread t = row t = (slot t/64, token t%64)
+// forward: grid (nchunks, heads), 128 threads, two CTAs per SM; thread t = row t = (slot t/64, token t%64).  The CTA walks the
+// window pairs pair = blockIdx.x, blockIdx.x + nchunks, ... of ONE head: the head's position bias (identical for every window)
+// sits in shared memory with rows padded to N + 1 floats -- lanes read different query rows, which from global memory costs
+// one cache line per lane per key (it used to dominate the kernel) -- and the q / k / v rows of the next pair are prefetched
+// into registers while the tensor core and the softmax work on the current one.
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) swin_attn_fwd_tc_kernel(SwinTcArgs a) {
+__global__ void __launch_bounds__(128) swin_attn_fwd_tc_kernel(SwinTcArgs a, int npairs) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + TB;
     uint8_t* sV = sK + TB;
     uint8_t* sP = sV + TB;                               // 2 key blocks of 64
-    int* sreg = reinterpret_cast<int*>(sP + 2 * TB);     // [128]
+    const int N = a.N;
+    float* sB = reinterpret_cast<float*>(sP + 2 * TB);   // [N][N + 1] bias of this head
+    int* sreg = reinterpret_cast<int*>(sB + N * (N + 1));   // [128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sreg + TILE);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, h = blockIdx.y;
     const int g = tid >> 6, n = tid & 63;
-    const int bw = blockIdx.x * 2 + g;
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
@@ -126,106 +131,135 @@ __global__ void __launch_bounds__(128) swin_attn_fwd_tc_kernel(SwinTcArgs a) {
         tmem_alloc(tmem_ptr, 256);
         tmem_relinquish();
     }
-    int region;
-    const int tok = window_token(a, bw, n, region);
-    sreg[tid] = region;
     {
-        float q[HD], k[HD], v[HD];
-        if (tok >= 0) {
-            load_row32(a.q, a.ld, tok, h, q);
-            load_row32(a.k, a.ld, tok, h, k);
-            load_row32(a.v, a.ld, tok, h, v);
-            float nq, nk;
-            const float iq = inv_norm32(q, nq), ik = inv_norm32(k, nk);
-#pragma unroll
-            for (int c = 0; c < HD; ++c) { q[c] *= iq; k[c] *= ik; }
-        } else {
-#pragma unroll
-            for (int c = 0; c < HD; ++c) { q[c] = 0.0f; k[c] = 0.0f; v[c] = 0.0f; }
-        }
-        stage_row32_hilo(sQ, tid, q);
-        stage_row32_hilo(sK, tid, k);
-        stage_row32(sV, tid, v);
+        const float* bh = a.bias + static_cast<long long>(h) * N * N;
+        for (int idx = tid; idx < N * N; idx += 128) sB[(idx / N) * (N + 1) + idx % N] = __ldg(bh + idx);
     }
-    fence_proxy_async_smem();
+    // the other window slot's key block of P stays zero for the whole kernel (cross-window half of the 128 x 128 product)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) st_tile8_raw(sP + (1 - g) * TB, tid, c, make_uint4(0, 0, 0, 0));
+
+    // prefetch registers: the q / k / v head slices of this thread's row of the pair about to be staged
+    uint4 pq[4], pk[4], pv[4];
+    int ptok = -1, pregion = 0;
+    auto prefetch = [&](int pair) {
+        ptok = window_token(a, pair * 2 + g, n, pregion);
+        if (ptok >= 0) {
+            const long long o = static_cast<long long>(ptok) * a.ld + h * HD;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                pq[c] = __ldg(reinterpret_cast<const uint4*>(a.q + o) + c);
+                pk[c] = __ldg(reinterpret_cast<const uint4*>(a.k + o) + c);
+                pv[c] = __ldg(reinterpret_cast<const uint4*>(a.v + o) + c);
+            }
+        }
+    };
+    if (static_cast<int>(blockIdx.x) < npairs) prefetch(blockIdx.x);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
     constexpr int O_COL = 128;
-
-    if (tid == 0) {
-        issue_cosine_logits(tmem, smem_u32(sQ), smem_u32(sK), umma_idesc_bf16(TILE, TILE, false, false));
-        umma_commit(&bars[0]);
-    }
-    mbar_wait(&bars[0], 0);
-    tc_fence_after();
-
     const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
     const float scale = __expf(fminf(a.logit_scale[h], LOGIT_MAX));
-    const float* brow = a.bias + (static_cast<long long>(h) * a.N + (tok >= 0 ? n : 0)) * a.N;
-    const int N = a.N;
-    float sv[SLOT];
-    float mx = -INFINITY;
+    const uint32_t id_s = umma_idesc_bf16(TILE, TILE, false, false), id_o = umma_idesc_bf16(TILE, HD, false, true);
+    uint32_t phase = 0;
+
+    for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+        const int tok = ptok, region = pregion;
+        const int bw = pair * 2 + g;
+        sreg[tid] = region;
+        {
+            float q[HD], k[HD];
+            if (tok >= 0) {
 #pragma unroll
-    for (int c0 = 0; c0 < SLOT; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(trow + g * SLOT + c0, r);
-        tmem_ld_wait();
+                for (int c = 0; c < 4; ++c) { unpack8(pq[c], q + 8 * c); unpack8(pk[c], k + 8 * c); }
+                float nq, nk;
+                const float iq = inv_norm32(q, nq), ik = inv_norm32(k, nk);
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-            const int j = c0 + t;
-            float s = -INFINITY;
-            if (tok >= 0 && j < N) {
-                s = __uint_as_float(r[t]) * scale + brow[j];
-                if (sreg[g * SLOT + j] != region) s += -200.0f;
-                mx = fmaxf(mx, s);
+                for (int c = 0; c < HD; ++c) { q[c] *= iq; k[c] *= ik; }
+            } else {
+#pragma unroll
+                for (int c = 0; c < HD; ++c) { q[c] = 0.0f; k[c] = 0.0f; }
             }
-            sv[j] = s;
+            stage_row32_hilo(sQ, tid, q);
+            stage_row32_hilo(sK, tid, k);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) st_tile8_raw(sV, tid, c, tok >= 0 ? pv[c] : make_uint4(0, 0, 0, 0));
         }
-    }
-    float sum = 0.0f;
-#pragma unroll
-    for (int j = 0; j < SLOT; ++j) {
-        const float e = (tok >= 0 && j < N) ? __expf(sv[j] - mx) : 0.0f;
-        sv[j] = e;
-        sum += e;
-    }
-    // own slot's 64 keys -> key block g; the other slot's keys -> zeros
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        st_tile8(sP + g * TB, tid, c, sv + 8 * c);
-        st_tile8_raw(sP + (1 - g) * TB, tid, c, make_uint4(0, 0, 0, 0));
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (tid == 0) {
-        const uint32_t idesc = umma_idesc_bf16(TILE, HD, false, true);
-        const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
-#pragma unroll
-        for (int ks = 0; ks < TILE / 16; ++ks)
-            umma_bf16(tmem + O_COL, umma_smem_desc_sw128(pa + (ks >> 2) * TB + (ks & 3) * 32, 16, 1024),
-                      umma_smem_desc_sw128(va + ks * 2048, 8192, 1024), idesc, ks != 0);
-        umma_commit(&bars[1]);
-    }
-    mbar_wait(&bars[1], 0);
-    tc_fence_after();
-    {
-        uint32_t r[32];
-        tmem_ld_32x32(trow + O_COL, r);
-        tmem_ld_wait();
-        if (tok >= 0) {
-            const float inv = 1.0f / sum;
-            float o[HD];
-#pragma unroll
-            for (int c = 0; c < HD; ++c) o[c] = __uint_as_float(r[c]) * inv;
-            store_row32(a.out, a.ldc, tok, h, o);
-            a.lse[(static_cast<long long>(bw) * a.heads + h) * N + n] = mx + __logf(sum);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (tid == 0) {
+            issue_cosine_logits(tmem, smem_u32(sQ), smem_u32(sK), id_s);
+            umma_commit(&bars[0]);
         }
+        if (pair + static_cast<int>(gridDim.x) < npairs) prefetch(pair + gridDim.x);
+        mbar_wait(&bars[0], phase);
+        tc_fence_after();
+
+        const float* brow = sB + (tok >= 0 ? n : 0) * (N + 1);
+        float sv[SLOT];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c0 = 0; c0 < SLOT; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(trow + g * SLOT + c0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+                const int j = c0 + t;
+                float sc = -INFINITY;
+                if (tok >= 0 && j < N) {
+                    sc = __uint_as_float(r[t]) * scale + brow[j];
+                    if (sreg[g * SLOT + j] != region) sc += -200.0f;
+                    mx = fmaxf(mx, sc);
+                }
+                sv[j] = sc;
+            }
+        }
+        float sum = 0.0f;
+#pragma unroll
+        for (int j = 0; j < SLOT; ++j) {
+            const float e = (tok >= 0 && j < N) ? __expf(sv[j] - mx) : 0.0f;
+            sv[j] = e;
+            sum += e;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) st_tile8(sP + g * TB, tid, c, sv + 8 * c);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (tid == 0) {
+            const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
+#pragma unroll
+            for (int ks = 0; ks < TILE / 16; ++ks)
+                umma_bf16(tmem + O_COL, umma_smem_desc_sw128(pa + (ks >> 2) * TB + (ks & 3) * 32, 16, 1024),
+                          umma_smem_desc_sw128(va + ks * 2048, 8192, 1024), id_o, ks != 0);
+            umma_commit(&bars[1]);
+        }
+        mbar_wait(&bars[1], phase);
+        phase ^= 1;
+        tc_fence_after();
+        {
+            uint32_t r[32];
+            tmem_ld_32x32(trow + O_COL, r);
+            tmem_ld_wait();
+            if (tok >= 0) {
+                const float inv = 1.0f / sum;
+                float o[HD];
+#pragma unroll
+                for (int c = 0; c < HD; ++c) o[c] = __uint_as_float(r[c]) * inv;
+                store_row32(a.out, a.ldc, tok, h, o);
+                a.lse[(static_cast<long long>(bw) * a.heads + h) * N + n] = mx + __logf(sum);
+            }
+        }
+        // the next iteration's staging overwrites sQ / sK / sV / sreg: every thread is past the softmax (second barrier above) and
+        // both MMAs have completed (bars[1]); the accumulators are re-issued only after the next iteration's first barrier
+        tc_fence_before();
     }
-    tc_fence_before();
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
@@ -262,7 +296,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) swin_attn_bwd_tc_kernel(SwinTc
     float* sqn = reinterpret_cast<float*>(sreg + TILE);            // [128] |q|
     float* skn = sqn + TILE;                                       // [128] |k|
     float* sD = skn + TILE;                                        // [4][128] partial D_i
-    float* red = sD + 4 * TILE;                                    // [16]
+    float* sB = sD + 4 * TILE;                                     // [N][N + 1] position bias of this head (see the forward kernel)
+    float* red = sB + N * (N + 1);                                 // [16]
     uint64_t* bars = reinterpret_cast<uint64_t*>(red + 16);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
     constexpr int TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 288, TM_DQ = 352;      // dK / dQ: 64 columns ([hi | lo] of B)
@@ -283,6 +318,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) swin_attn_bwd_tc_kernel(SwinTc
         tmem_relinquish();
     }
     for (int idx = tid; idx < N * (N + 1); idx += BWD_THREADS) dbias_s[idx] = 0.0f;
+    {
+        const float* bh = a.bias + static_cast<long long>(h) * N * N;
+        for (int idx = tid; idx < N * N; idx += BWD_THREADS) sB[(idx / N) * (N + 1) + idx % N] = __ldg(bh + idx);
+    }
     // the bias gradient of element (n, j) is owned by the thread with TMEM row n (either window slot) and key quarter j / 16 for
     // EVERY window pair this CTA visits, so it accumulates in registers (a shared-memory row per thread would put the 32 lanes
     // of a warp on one bank: rows are 64 floats apart) and is combined once at the end
@@ -376,7 +415,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) swin_attn_bwd_tc_kernel(SwinTc
         const bool valid = region >= 0;
         const int bw = pair * 2 + g;
         const float lse = valid ? a.lse[(static_cast<long long>(bw) * a.heads + h) * N + n] : 0.0f;
-        const float* brow = a.bias + (static_cast<long long>(h) * N + (valid ? n : 0)) * N + cq * 16;
+        const float* brow = sB + (valid ? n : 0) * (N + 1) + cq * 16;
         int kreg[16];
 #pragma unroll
         for (int t = 0; t < 16; ++t) kreg[t] = sreg[g * SLOT + cq * 16 + t];
@@ -398,7 +437,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) swin_attn_bwd_tc_kernel(SwinTc
             const int j = cq * 16 + t;
             float p = 0.0f;
             if (valid && j < N) {
-                float sc = __uint_as_float(rs[t]) * scale + __ldg(brow + t);
+                float sc = __uint_as_float(rs[t]) * scale + brow[t];
                 if (kreg[t] != region) sc += -200.0f;
                 p = __expf(sc - lse);
                 Dp = fmaf(p, __uint_as_float(rp[t]), Dp);
@@ -553,14 +592,19 @@ int swin_attention_fwd_tc(cudaStream_t st, int B, int res, int heads, int window
                           long long ld, void* ctx, long long ldc, const float* logit_scale, const float* bias, float* lse) {
     SwinTcArgs a = make_args(B, res, heads, window, shift, q, k, v, ld, ldc, logit_scale, bias, lse);
     a.out = static_cast<__nv_bfloat16*>(ctx);
-    const size_t smem = 1024 + 5 * TB + sizeof(int) * TILE + 64;
-    static bool set = false;
-    if (!set) {
+    const int N = a.N;
+    const size_t smem = 1024 + 5 * TB + sizeof(float) * N * (N + 1) + sizeof(int) * TILE + 64;
+    static size_t set = 0;
+    if (smem > set) {
         KLAB_CHECK_CUDA(cudaFuncSetAttribute(swin_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        set = true;
+        set = smem;
     }
-    const dim3 grid((B * a.nW + 1) / 2, heads);
-    swin_attn_fwd_tc_kernel<<<grid, 128, smem, st>>>(a);
+    const int npairs = (B * a.nW + 1) / 2;
+    int nchunks = (2 * sm_count() + heads - 1) / heads;            // two resident CTAs per SM
+    if (nchunks > npairs) nchunks = npairs;
+    if (nchunks < 1) nchunks = 1;
+    const dim3 grid(nchunks, heads);
+    swin_attn_fwd_tc_kernel<<<grid, 128, smem, st>>>(a, npairs);
     KLAB_LAUNCH_CHECK();
     count_launch();
     return KLAB_OK;
@@ -574,7 +618,7 @@ int swin_attention_bwd_tc(cudaStream_t st, int B, int res, int heads, int window
     a.dq = static_cast<__nv_bfloat16*>(dq); a.dk = static_cast<__nv_bfloat16*>(dk); a.dv = static_cast<__nv_bfloat16*>(dv);
     a.dbias = dbias; a.dlogit_scale = dlogit_scale;
     const int N = a.N;
-    const size_t smem = 1024 + 10 * TB + sizeof(float) * N * (N + 1) + sizeof(int) * TILE + sizeof(float) * (6 * TILE + 16) + 64;
+    const size_t smem = 1024 + 10 * TB + 2 * sizeof(float) * N * (N + 1) + sizeof(int) * TILE + sizeof(float) * (6 * TILE + 16) + 64;
     static size_t set = 0;
     if (smem > set) {
         KLAB_CHECK_CUDA(cudaFuncSetAttribute(swin_attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -11,6 +11,8 @@ autograd graph only.  Citations: HF/ = site-packages/transformers 5.5.0.
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from . import _lib as L
@@ -21,12 +23,40 @@ from .graphs import POOL
 # ------------------------------------------------------------------------------------------------
 # operand cache: fp32 master weights -> (concatenated) operands in the compute dtype
 # ------------------------------------------------------------------------------------------------
+# parameter id -> [(weakref to the owning OperandCache, entry key, first row, rows)]: where the compute-dtype copies of a parameter live.  The fused optimizer
+# (optim.py) writes the bf16 copy in the same pass that updates the fp32 master and then marks the entry fresh, so a
+# training step contains no cast kernels at all.
+_PARAM_SLOTS: dict = {}
+
+
+def operand_slots(p):
+    """[(entry, view of the operand rows that hold `p`)] for every cached compute-dtype copy of parameter `p`."""
+    out, live = [], []
+    for ref, key, r0, r in _PARAM_SLOTS.get(id(p), ()):
+        cache = ref()
+        e = cache._store.get(key) if cache is not None else None
+        if e is None:
+            continue                                          # the cache (model) is gone or was cleared: drop the stale slot
+        live.append((ref, key, r0, r))
+        if e[4][e[5].index(id(p))] is p and e[1].device == p.device:
+            out.append((e, e[1][r0:r0 + r]))
+    if id(p) in _PARAM_SLOTS:
+        _PARAM_SLOTS[id(p)] = live
+    return out
+
+
+def mark_operands_fresh(entries):
+    """Called by the optimizer after it rewrote EVERY parameter of each entry (fp32 master and compute-dtype copy alike)."""
+    for e in entries:
+        e[0] = OperandCache._version(e[4])
+
+
 class OperandCache:
     """Keeps, per group of parameters, one contiguous [sum(N_i), K] operand in the compute dtype (bf16 copies for the
     tensor cores; q|k|v weights concatenated so one GEMM produces all three).  The buffer of a group never moves, so CUDA
-    graphs can bake its address.  `get` refreshes a stale entry eagerly (a parameter's version counter changed, i.e. after
-    optimizer.step()); `recast` converts unconditionally (used INSIDE a captured training region: the conversion is then part
-    of the graph); `peek` returns the buffer as is (backward reuses what forward converted)."""
+    graphs can bake its address.  `get` refreshes a stale entry eagerly (a parameter's version counter or address changed,
+    e.g. after a foreign optimizer's step or load_state_dict); `peek` returns the buffer as is (captured regions and backward
+    reuse what `get` validated before the region was launched).  entry = [version, buffer, rows, k, params, param ids]."""
 
     def __init__(self):
         self._store: dict = {}
@@ -44,7 +74,11 @@ class OperandCache:
             k = params[0][0].numel() if params[0].dim() > 1 else params[0].numel()
             rows = [p.numel() // k for p in params]
             buf = torch.empty(sum(rows), k, dtype=dtype, device=params[0].device)
-            e = self._store[key] = [None, buf, rows, k]
+            e = self._store[key] = [None, buf, rows, k, list(params), [id(p) for p in params]]
+            r0, ref = 0, weakref.ref(self)
+            for p, r in zip(params, rows):
+                _PARAM_SLOTS.setdefault(id(p), []).append((ref, key, r0, r))
+                r0 += r
         return e
 
     @staticmethod
@@ -52,7 +86,7 @@ class OperandCache:
         return tuple(p._version for p in params) + tuple(p.data_ptr() for p in params)
 
     def _convert(self, e, params, dtype):
-        _, buf, rows, k = e
+        buf, rows, k = e[1], e[2], e[3]
         r0 = 0
         for p, r in zip(params, rows):
             O.cast(p.detach().reshape(r, k), dtype, out=buf[r0:r0 + r])
@@ -65,13 +99,6 @@ class OperandCache:
         e = self._entry(params, dtype)
         if e[0] != self._version(params):
             self._convert(e, params, dtype)
-        return e[1]
-
-    def recast(self, params, dtype) -> torch.Tensor:
-        if self._direct(params, dtype):
-            return params[0].detach()
-        e = self._entry(params, dtype)
-        self._convert(e, params, dtype)
         return e[1]
 
     def peek(self, params, dtype) -> torch.Tensor:
@@ -239,7 +266,7 @@ def _t5_ff_bwd(c, dout, x, ln_w, wi, wo, n, rstd, f, seed):
 
 
 def _t5_operands(c, params, cd, mode):
-    """(wqkv, w_o, w_i, w_ff[, w_cq, w_ckv, w_co]) in the compute dtype; mode in {"get", "recast", "peek"}."""
+    """(wqkv, w_o, w_i, w_ff[, w_cq, w_ckv, w_co]) in the compute dtype; mode in {"get", "peek"}."""
     f = getattr(c.cache, mode)
     if c.is_decoder:
         ln0, q, k, v, o, ln1, cq, ck, cv, co, ln2, wi, wo = params
@@ -248,11 +275,11 @@ def _t5_operands(c, params, cd, mode):
     return f([q, k, v], cd), f([o], cd), f([wi], cd), f([wo], cd)
 
 
-def _t5_block_fwd_body(x, enc_out, c, save, recast, table, *params):
+def _t5_block_fwd_body(x, enc_out, c, save, table, *params):
     """-> (out,) or (out, n0, rstd0, qkv, ctx, lse, h1, [n1, rstd1, qc, kvbuf, ctx2, lse2, h2,] n2, rstd2, f)"""
     cd = x.dtype
     dec = c.is_decoder
-    ws = _t5_operands(c, params, cd, "recast" if recast else "peek")
+    ws = _t5_operands(c, params, cd, "peek")
     seed = c.seed
     if dec:
         ln0, ln1, ln2 = params[0], params[5], params[10]
@@ -314,11 +341,9 @@ class T5BlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, c, x, enc_out, table, *params):
         save = _needs_grad((x, enc_out, table) + tuple(params))
-        trainable = save and any(p.requires_grad for p in params)
-        if not trainable:                                   # frozen / eval: convert stale weights eagerly, outside any graph
-            _t5_operands(c, params, x.dtype, "get")
+        _t5_operands(c, params, x.dtype, "get")             # stale compute-dtype copies are refreshed eagerly, outside any graph
         x = x.contiguous()
-        outs, graphed = POOL.run(("t5f", id(c), save), _t5_block_fwd_body, (x, enc_out), (c, save, trainable, table) + tuple(params),
+        outs, graphed = POOL.run(("t5f", id(c), save), _t5_block_fwd_body, (x, enc_out), (c, save, table) + tuple(params),
                                  allow_graph=not c.busy)
         if save:
             ctx.c = c
@@ -556,12 +581,12 @@ def _swin_operands(c, params, cd, mode):
     return f([qw, kw, vw], cd), f([pw], cd), f([f1w], cd), f([f2w], cd)
 
 
-def _swin_block_fwd_body(x, c, save, recast, *params):
+def _swin_block_fwd_body(x, c, save, *params):
     """-> (out,) or (out, qkv, bias16, hidden, tab, ctx, lse, a, mean1, rstd1, h, m_pre, m_act, m2, mean2, rstd2)"""
     (ls, w1, b1, w2, qw, qb, kw, vw, vb, pw, pb, g1, be1, f1w, f1b, f2w, f2b, g2, be2) = params
     cd = x.dtype
     C_ = x.shape[1]
-    wqkv, w_p, w_f1, w_f2 = _swin_operands(c, params, cd, "recast" if recast else "peek")
+    wqkv, w_p, w_f1, w_f2 = _swin_operands(c, params, cd, "peek")
     bqkv = cat_vec([(qb, C_), (None, C_), (vb, C_)], x.device)            # key has no bias (:417)
     qkv = O.linear_fwd(x, wqkv, bias=bqkv)
     bias16, hidden, tab = O.swin_cpb_fwd(c.coords, c.index, w1.detach(), b1.detach(), w2.detach(), c.heads, c.N)
@@ -616,11 +641,9 @@ class SwinBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, c, x, *params):
         save = _needs_grad((x,) + tuple(params))
-        trainable = save and any(p.requires_grad for p in params)
-        if not trainable:
-            _swin_operands(c, params, x.dtype, "get")
+        _swin_operands(c, params, x.dtype, "get")
         x = x.contiguous()
-        outs, graphed = POOL.run(("swf", id(c), save), _swin_block_fwd_body, (x,), (c, save, trainable) + tuple(params),
+        outs, graphed = POOL.run(("swf", id(c), save), _swin_block_fwd_body, (x,), (c, save) + tuple(params),
                                  allow_graph=not c.busy)
         if save:
             ctx.c = c

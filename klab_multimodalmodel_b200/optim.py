@@ -26,16 +26,16 @@ class Adam(torch.optim.Optimizer):
         self._tables: dict = {}
 
     def _table(self, key, items):
-        """items: list of (p, g, m, v).  Device tables are rebuilt only when a pointer changed (with CUDA graphs the gradient
+        """items: list of (p, g, m, v, w16 pointer or 0).  Device tables are rebuilt only when a pointer changed (with CUDA graphs the gradient
         buffers are static, so this happens once).  Rebuilds go through two alternating pinned staging buffers and an event, so
         they never synchronise the device."""
-        sig = tuple((p.data_ptr(), g.data_ptr(), m.data_ptr()) for p, g, m, v in items)
+        sig = tuple((p.data_ptr(), g.data_ptr(), m.data_ptr(), w) for p, g, m, v, w in items)
         ent = self._tables.get(key)
         if ent is not None and ent["sig"] == sig:
             return ent["table"], ent["blockmap"], ent["nblocks"]
         chunk = int(L.lib().klab_adam_chunk_elems())
         dev = items[0][0].device
-        shape_sig = tuple(p.numel() for p, _, _, _ in items)
+        shape_sig = tuple(it[0].numel() for it in items)
         if ent is None or ent["shape_sig"] != shape_sig:
             bm = []
             for ti, n in enumerate(shape_sig):
@@ -51,7 +51,7 @@ class Adam(torch.optim.Optimizer):
         if ent["events"][i] is not None:
             ent["events"][i].synchronize()                     # the copy that last used this staging buffer (two rebuilds ago)
         host = ent["host"][i]
-        host.copy_(torch.tensor([[p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), 0, p.numel()] for p, g, m, v in items],
+        host.copy_(torch.tensor([[p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), w, p.numel()] for p, g, m, v, w in items],
                                 dtype=torch.int64))
         ent["table"].copy_(host, non_blocking=True)
         ev = torch.cuda.Event()
@@ -67,8 +67,10 @@ class Adam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        from .functional import mark_operands_fresh, operand_slots
         for gi, group in enumerate(self.param_groups):
             by_step: dict = {}
+            written: dict = {}                          # id(entry) -> [entry, parameter ids whose bf16 copy this step rewrites]
             for p in group["params"]:
                 if p.grad is None:
                     continue
@@ -85,7 +87,13 @@ class Adam(torch.optim.Optimizer):
                     raise RuntimeError("klab Adam: parameters and gradients must be contiguous")
                 t = int(st["step"]) + 1
                 st["step"] = t
-                by_step.setdefault(t, []).append((p, p.grad, st["exp_avg"], st["exp_avg_sq"]))
+                w16 = 0                                 # bf16 operand copy of p (what the tensor cores read): refreshed in the same pass
+                for e, view in operand_slots(p):
+                    if view.dtype == torch.bfloat16 and view.is_contiguous() and view.numel() == p.numel():
+                        w16 = view.data_ptr()
+                        written.setdefault(id(e), [e, set()])[1].add(id(p))
+                        break
+                by_step.setdefault(t, []).append((p, p.grad, st["exp_avg"], st["exp_avg_sq"], w16))
             b1, b2 = group["betas"]
             for t, items in by_step.items():
                 table, blockmap, nblocks = self._table((gi, len(by_step) > 1 and t), items)
@@ -93,4 +101,7 @@ class Adam(torch.optim.Optimizer):
                 L.check(L.lib().klab_adam_step(stream, table.data_ptr(), blockmap.data_ptr(), nblocks, float(group["lr"]), float(b1),
                                                float(b2), float(group["eps"]), float(group["weight_decay"]), t,
                                                float(group.get("grad_scale", 1.0))))
+                # the kernel wrote the masters through raw pointers: tell autograd (and every operand cache) that they changed
+                torch.autograd.graph.increment_version([it[0] for it in items])
+            mark_operands_fresh([e for e, ids in written.values() if ids == set(e[5])])
         return loss

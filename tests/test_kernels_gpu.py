@@ -221,7 +221,9 @@ def test_t5_bucket_lut_matches_oracle():
 
 # ------------------------------------------------------------------------------------------------ Swin attention
 @pytest.mark.parametrize("dtype", DTYPES)
-@pytest.mark.parametrize("B,res,heads,hd,w,shift", [(2, 8, 2, 32, 4, 2), (1, 8, 1, 32, 8, 0), (2, 14, 2, 32, 7, 3), (1, 16, 3, 16, 4, 0)])
+@pytest.mark.parametrize("B,res,heads,hd,w,shift", [(2, 8, 2, 32, 4, 2), (1, 8, 1, 32, 8, 0), (2, 14, 2, 32, 7, 3), (1, 16, 3, 16, 4, 0),
+                                                    (24, 32, 2, 32, 8, 4),      # 192 window pairs: the persistent CTAs loop (prefetch path)
+                                                    (3, 7, 1, 32, 7, 0)])       # odd window count: padded second slot
 def test_swin_attention(dtype, B, res, heads, hd, w, shift):
     o = ops()
     Cc = heads * hd
@@ -335,6 +337,65 @@ def test_embedding_patch_ce(dtype):
     close(LG[:, :Vv], 0.5 * lr.grad, dtype, "ce bwd")
     assert (LG[:, Vv:] == 0).all()
     o.check_err_flag(LG.device)
+
+
+@pytest.mark.parametrize("rows,d,ld", [(5000, 512, 512), (4099, 128, 384), (777, 96, 96), (9001, 1536, 1536), (3, 256, 256), (70000, 384, 1152)])
+def test_colsum_shapes(rows, d, ld):
+    """Bias-gradient column sums: the 16-byte bf16 path (d % 8 == 0, strided rows as in dqkv slices), its scalar fallback and
+    the 32-lane finalize, at row counts that exercise several row chunks."""
+    o = ops()
+    gen = torch.Generator().manual_seed(rows + d)
+    full = torch.randn(rows, ld, generator=gen)
+    for dtype in (torch.bfloat16, torch.float32):
+        X = full.to(dtype).cuda()
+        view = X[:, ld - d:]
+        ref = view.float().cpu().double().sum(0)
+        got = o.colsum(view).cpu().double()
+        tol = 2e-5 * math.sqrt(rows) * 4 + 1e-6
+        assert (got - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item()), (dtype, (got - ref).abs().max().item())
+
+
+def test_fused_adam_refreshes_bf16_operands():
+    """The optimizer pass also rewrites the bf16 operand copies the tensor cores read (no cast kernels in a training step):
+    after klab Adam the OperandCache entry is fresh and equals bf16(master); after a foreign optimizer (torch.optim.Adam
+    bumps the version counters) `get` notices and re-casts."""
+    from klab_multimodalmodel_b200 import ops as O
+    from klab_multimodalmodel_b200.functional import OperandCache
+    from klab_multimodalmodel_b200.optim import Adam
+    torch.manual_seed(1)
+    ps = [torch.randn(64, 256, device="cuda").requires_grad_() for _ in range(3)] + [torch.randn(40, 256, device="cuda").requires_grad_()]
+    cache = OperandCache()
+    qkv = cache.get(ps[:3], torch.bfloat16)
+    solo = cache.get(ps[3:], torch.bfloat16)
+    assert torch.equal(qkv, torch.cat([p.detach() for p in ps[:3]]).bfloat16())
+    opt = Adam(ps, lr=1e-2)
+    for _ in range(2):
+        for p in ps:
+            p.grad = torch.randn_like(p)
+        v0 = [p._version for p in ps]
+        opt.step()
+        assert all(p._version > v for p, v in zip(ps, v0))
+        n0 = O.launch_count()
+        assert cache.get(ps[:3], torch.bfloat16).data_ptr() == qkv.data_ptr() and cache.get(ps[3:], torch.bfloat16).data_ptr() == solo.data_ptr()
+        assert O.launch_count() == n0, "operand copies were re-cast although the optimizer refreshed them"
+        assert torch.equal(qkv, torch.cat([p.detach() for p in ps[:3]]).bfloat16())
+        assert torch.equal(solo, ps[3].detach().bfloat16())
+    # a group only partly owned by the optimizer must NOT be marked fresh
+    opt2 = Adam(ps[:2], lr=1e-2)
+    for p in ps[:2]:
+        p.grad = torch.randn_like(p)
+    with torch.no_grad():
+        ps[2].add_(1.0)
+    opt2.step()
+    n0 = O.launch_count()
+    assert torch.equal(cache.get(ps[:3], torch.bfloat16), torch.cat([p.detach() for p in ps[:3]]).bfloat16())
+    assert O.launch_count() > n0
+    # foreign optimizer
+    topt = torch.optim.Adam(ps, lr=1e-2)
+    for p in ps:
+        p.grad = torch.randn_like(p)
+    topt.step()
+    assert torch.equal(cache.get(ps[:3], torch.bfloat16), torch.cat([p.detach() for p in ps[:3]]).bfloat16())
 
 
 def test_fused_adam_matches_torch_adam():
