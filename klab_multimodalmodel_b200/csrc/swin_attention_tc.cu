@@ -100,9 +100,10 @@ __device__ __forceinline__ float inv_norm32(const float* v, float& norm) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// forward: grid (nchunks, heads), 128 threads, two CTAs per SM; thread t = row t = (slot t/64, token t%64).  The CTA walks the
-// window pairs pair = blockIdx.x, blockIdx.x + nchunks, ... of ONE head: the head's position bias (identical for every window)
-// sits in shared memory with rows padded to N + 1 floats -- lanes read different query rows, which from global memory costs
+// forward: 1-D grid of two CTAs per SM, 128 threads; thread t = row t = (slot t/64, token t%64).  Work item = (head, window
+// pair), numbered head-major; CTA c owns the contiguous range [c T / G, (c + 1) T / G) of the T = heads * npairs items, so every
+// CTA gets the same number of items (+-1) whatever the head count, and changes head at most a few times.  The current head's
+// position bias (identical for every window) sits in shared memory with rows padded to N + 1 floats -- lanes read different query rows, which from global memory costs
 // one cache line per lane per key (it used to dominate the kernel) -- and the q / k / v rows of the next pair are prefetched
 // into registers while the tensor core and the softmax work on the current one.
 // ------------------------------------------------------------------------------------------------------------------
@@ -119,8 +120,11 @@ __global__ void __launch_bounds__(128) swin_attn_fwd_tc_kernel(SwinTcArgs a, int
     uint64_t* bars = reinterpret_cast<uint64_t*>(sreg + TILE);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
 
-    const int tid = threadIdx.x, warp = tid >> 5, h = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const int g = tid >> 6, n = tid & 63;
+    const int T = npairs * a.heads;
+    const int t_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * T / gridDim.x);
+    const int t_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * T / gridDim.x);
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
@@ -131,10 +135,6 @@ __global__ void __launch_bounds__(128) swin_attn_fwd_tc_kernel(SwinTcArgs a, int
         tmem_alloc(tmem_ptr, 256);
         tmem_relinquish();
     }
-    {
-        const float* bh = a.bias + static_cast<long long>(h) * N * N;
-        for (int idx = tid; idx < N * N; idx += 128) sB[(idx / N) * (N + 1) + idx % N] = __ldg(bh + idx);
-    }
     // the other window slot's key block of P stays zero for the whole kernel (cross-window half of the 128 x 128 product)
 #pragma unroll
     for (int c = 0; c < 8; ++c) st_tile8_raw(sP + (1 - g) * TB, tid, c, make_uint4(0, 0, 0, 0));
@@ -142,10 +142,11 @@ __global__ void __launch_bounds__(128) swin_attn_fwd_tc_kernel(SwinTcArgs a, int
     // prefetch registers: the q / k / v head slices of this thread's row of the pair about to be staged
     uint4 pq[4], pk[4], pv[4];
     int ptok = -1, pregion = 0;
-    auto prefetch = [&](int pair) {
+    auto prefetch = [&](int t) {
+        const int ph = t / npairs, pair = t - ph * npairs;
         ptok = window_token(a, pair * 2 + g, n, pregion);
         if (ptok >= 0) {
-            const long long o = static_cast<long long>(ptok) * a.ld + h * HD;
+            const long long o = static_cast<long long>(ptok) * a.ld + ph * HD;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 pq[c] = __ldg(reinterpret_cast<const uint4*>(a.q + o) + c);
@@ -154,18 +155,28 @@ __global__ void __launch_bounds__(128) swin_attn_fwd_tc_kernel(SwinTcArgs a, int
             }
         }
     };
-    if (static_cast<int>(blockIdx.x) < npairs) prefetch(blockIdx.x);
+    if (t_begin < t_end) prefetch(t_begin);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
     constexpr int O_COL = 128;
     const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-    const float scale = __expf(fminf(a.logit_scale[h], LOGIT_MAX));
     const uint32_t id_s = umma_idesc_bf16(TILE, TILE, false, false), id_o = umma_idesc_bf16(TILE, HD, false, true);
     uint32_t phase = 0;
+    int h = -1;
+    float scale = 0.0f;
 
-    for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    for (int t = t_begin; t < t_end; ++t) {
+        const int th = t / npairs, pair = t - th * npairs;
+        if (th != h) {
+            // every thread is past the previous item's softmax (its second barrier), so the old bias is dead; the staging barrier
+            // below publishes the new one
+            h = th;
+            scale = __expf(fminf(a.logit_scale[h], LOGIT_MAX));
+            const float* bh = a.bias + static_cast<long long>(h) * N * N;
+            for (int idx = tid; idx < N * N; idx += 128) sB[(idx / N) * (N + 1) + idx % N] = __ldg(bh + idx);
+        }
         const int tok = ptok, region = pregion;
         const int bw = pair * 2 + g;
         sreg[tid] = region;
@@ -195,7 +206,7 @@ __global__ void __launch_bounds__(128) swin_attn_fwd_tc_kernel(SwinTcArgs a, int
             issue_cosine_logits(tmem, smem_u32(sQ), smem_u32(sK), id_s);
             umma_commit(&bars[0]);
         }
-        if (pair + static_cast<int>(gridDim.x) < npairs) prefetch(pair + gridDim.x);
+        if (t + 1 < t_end) prefetch(t + 1);
         mbar_wait(&bars[0], phase);
         tc_fence_after();
 
@@ -268,7 +279,9 @@ __global__ void __launch_bounds__(128) swin_attn_fwd_tc_kernel(SwinTcArgs a, int
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// backward: grid (nchunks, heads), 512 threads; the CTA walks window pairs pair = blockIdx.x, blockIdx.x + nchunks, ...
+// backward: 1-D grid of one CTA per SM, 512 threads; work items (head, window pair) are numbered head-major and CTA c owns the
+// contiguous range [c T / G, (c + 1) T / G) (see the forward kernel); the bias / logit-scale gradients of a head are flushed
+// when the CTA moves on to the next head.
 // TMEM: S 0..127 | dP 128..255 | dV 256..287 | dK 288..351 | dQ 352..415
 //
 // One window pair is a serial chain (stage operands -> S, dP MMAs -> softmax backward -> dV, dK, dQ MMAs -> write out) and
@@ -302,7 +315,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) swin_attn_bwd_tc_kernel(SwinTc
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
     constexpr int TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 288, TM_DQ = 352;      // dK / dQ: 64 columns ([hi | lo] of B)
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, h = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int T = npairs * a.heads;
+    const int t_begin = static_cast<int>(static_cast<long long>(blockIdx.x) * T / gridDim.x);
+    const int t_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * T / gridDim.x);
     // staging view: 4 consecutive threads share token row srow, each moves the 16-byte chunk `part` (8 channels) of q, k, v, dO
     const int srow = tid >> 2, part = tid & 3, sg = srow >> 6, sn = srow & 63;
     // TMEM view: TMEM lane = row; the four warps with the same (warp & 3) split the row's 64 keys into quarters
@@ -317,17 +333,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) swin_attn_bwd_tc_kernel(SwinTc
         tmem_alloc(tmem_ptr, 512);
         tmem_relinquish();
     }
-    for (int idx = tid; idx < N * (N + 1); idx += BWD_THREADS) dbias_s[idx] = 0.0f;
-    {
-        const float* bh = a.bias + static_cast<long long>(h) * N * N;
-        for (int idx = tid; idx < N * N; idx += BWD_THREADS) sB[(idx / N) * (N + 1) + idx % N] = __ldg(bh + idx);
-    }
     // the bias gradient of element (n, j) is owned by the thread with TMEM row n (either window slot) and key quarter j / 16 for
     // EVERY window pair this CTA visits, so it accumulates in registers (a shared-memory row per thread would put the 32 lanes
     // of a warp on one bank: rows are 64 floats apart) and is combined once at the end
     float dbacc[16];
-#pragma unroll
-    for (int t = 0; t < 16; ++t) dbacc[t] = 0.0f;
     // P / dS / dSl hold, per row, the keys of the row's OWN window in key block g; the other block stays zero for the whole
     // kernel (it is the cross-window half of the 128 x 128 product), so it is cleared once, not once per pair
     for (int idx = tid; idx < 6 * TB / 16; idx += BWD_THREADS) reinterpret_cast<uint4*>(sP)[idx] = make_uint4(0, 0, 0, 0);
@@ -336,8 +345,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) swin_attn_bwd_tc_kernel(SwinTc
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
     const uint32_t trow = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    const float raw_ls = a.logit_scale[h];
-    const float scale = __expf(fminf(raw_ls, LOGIT_MAX));
+    int h = -1;
+    float raw_ls = 0.0f, scale = 0.0f;
     const uint32_t id_s = umma_idesc_bf16(TILE, TILE, false, false);   // S / dP
     const uint32_t id_t = umma_idesc_bf16(TILE, HD, true, true);       // dV / dK : A = P^T (MN-major), B MN-major
     const uint32_t id_q = umma_idesc_bf16(TILE, HD, false, true);      // dQ      : A = dS (K-major), B = Kh MN-major
@@ -349,11 +358,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) swin_attn_bwd_tc_kernel(SwinTc
     // prefetch registers (rows of the pair about to be staged)
     uint4 pq = make_uint4(0, 0, 0, 0), pk = pq, pv = pq, pdo = pq;
     int ptok = -1, pregion = 0;
-    auto prefetch = [&](int pair) {
+    auto prefetch = [&](int t) {
+        const int ph = t / npairs, pair = t - ph * npairs;
         ptok = window_token(a, pair * 2 + sg, sn, pregion);
         if (ptok >= 0) {
-            const long long o = static_cast<long long>(ptok) * a.ld + h * HD;
-            const long long oc = static_cast<long long>(ptok) * a.ldc + h * HD;
+            const long long o = static_cast<long long>(ptok) * a.ld + ph * HD;
+            const long long oc = static_cast<long long>(ptok) * a.ldc + ph * HD;
             pq = __ldg(reinterpret_cast<const uint4*>(a.q + o) + part);
             pk = __ldg(reinterpret_cast<const uint4*>(a.k + o) + part);
             pv = __ldg(reinterpret_cast<const uint4*>(a.v + o) + part);
@@ -362,9 +372,49 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) swin_attn_bwd_tc_kernel(SwinTc
             pq = pk = pv = pdo = make_uint4(0, 0, 0, 0);
         }
     };
-    if (static_cast<int>(blockIdx.x) < npairs) prefetch(blockIdx.x);
+    if (t_begin < t_end) prefetch(t_begin);
 
-    for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    // flush of one head: bias gradient of every window this CTA visited for it (the two window slots are combined in shared
+    // memory first) and d(logit_scale)
+    auto flush_head = [&]() {
+        if (n < N) {
+#pragma unroll
+            for (int t = 0; t < 16; ++t)
+                if (cq * 16 + t < N && dbacc[t] != 0.0f) atomicAdd(&dbias_s[n * (N + 1) + cq * 16 + t], dbacc[t]);
+        }
+        __syncthreads();
+        float* dbias = a.dbias + static_cast<long long>(h) * N * N;
+        for (int idx = tid; idx < N * N; idx += BWD_THREADS) {
+            const float v = dbias_s[(idx / N) * (N + 1) + idx % N];
+            if (v != 0.0f) atomicAdd(&dbias[idx], v);
+        }
+        dscale_acc = warp_sum(dscale_acc);
+        if (lane == 0) red[warp] = dscale_acc;
+        __syncthreads();
+        if (tid == 0) {
+            float t = 0.0f;
+#pragma unroll
+            for (int w = 0; w < BWD_THREADS / 32; ++w) t += red[w];
+            atomicAdd(&a.dlogit_scale[h], raw_ls <= LOGIT_MAX ? t * scale : 0.0f);
+        }
+        __syncthreads();          // dbias_s and red are re-initialised for the next head right after this
+    };
+
+    for (int t = t_begin; t < t_end; ++t) {
+        const int th = t / npairs, pair = t - th * npairs;
+        if (th != h) {
+            if (h >= 0) flush_head();
+            h = th;
+            raw_ls = a.logit_scale[h];
+            scale = __expf(fminf(raw_ls, LOGIT_MAX));
+            dscale_acc = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dbacc[i] = 0.0f;
+            for (int idx = tid; idx < N * (N + 1); idx += BWD_THREADS) dbias_s[idx] = 0.0f;
+            const float* bh = a.bias + static_cast<long long>(h) * N * N;
+            for (int idx = tid; idx < N * N; idx += BWD_THREADS) sB[(idx / N) * (N + 1) + idx % N] = __ldg(bh + idx);
+            // published by the staging barrier below (dbias_s is next touched by a flush, sB by the softmax backward)
+        }
         // ---- stage the pair: L2-normalise q, k (fp32), split into bf16 hi | lo, copy v and dO ----
         {
             float q[8], k[8];
@@ -409,7 +459,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) swin_attn_bwd_tc_kernel(SwinTc
             umma_commit(&bars[0]);
         }
         // rows of the next pair travel while the tensor core and the softmax phase work on this one
-        if (pair + static_cast<int>(gridDim.x) < npairs) prefetch(pair + gridDim.x);
+        if (t + 1 < t_end) prefetch(t + 1);
 
         const int region = sreg[r];
         const bool valid = region >= 0;
@@ -539,28 +589,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) swin_attn_bwd_tc_kernel(SwinTc
         tc_fence_after();
     }
 
-    // flush: bias gradient of every window this CTA visited (the two window slots are combined in shared memory first), and
-    // d(logit_scale)
-    if (n < N) {
-#pragma unroll
-        for (int t = 0; t < 16; ++t)
-            if (cq * 16 + t < N && dbacc[t] != 0.0f) atomicAdd(&dbias_s[n * (N + 1) + cq * 16 + t], dbacc[t]);
-    }
-    __syncthreads();
-    float* dbias = a.dbias + static_cast<long long>(h) * N * N;
-    for (int idx = tid; idx < N * N; idx += BWD_THREADS) {
-        const float v = dbias_s[(idx / N) * (N + 1) + idx % N];
-        if (v != 0.0f) atomicAdd(&dbias[idx], v);
-    }
-    dscale_acc = warp_sum(dscale_acc);
-    if (lane == 0) red[warp] = dscale_acc;
-    __syncthreads();
-    if (tid == 0) {
-        float t = 0.0f;
-#pragma unroll
-        for (int w = 0; w < BWD_THREADS / 32; ++w) t += red[w];
-        atomicAdd(&a.dlogit_scale[h], raw_ls <= LOGIT_MAX ? t * scale : 0.0f);
-    }
+    if (h >= 0) flush_head();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -600,10 +629,8 @@ int swin_attention_fwd_tc(cudaStream_t st, int B, int res, int heads, int window
         set = smem;
     }
     const int npairs = (B * a.nW + 1) / 2;
-    int nchunks = (2 * sm_count() + heads - 1) / heads;            // two resident CTAs per SM
-    if (nchunks > npairs) nchunks = npairs;
-    if (nchunks < 1) nchunks = 1;
-    const dim3 grid(nchunks, heads);
+    int grid = 2 * sm_count();                                      // two resident CTAs per SM, equal shares of the work items
+    if (grid > npairs * heads) grid = npairs * heads;
     swin_attn_fwd_tc_kernel<<<grid, 128, smem, st>>>(a, npairs);
     KLAB_LAUNCH_CHECK();
     count_launch();
@@ -627,10 +654,8 @@ int swin_attention_bwd_tc(cudaStream_t st, int B, int res, int heads, int window
     KLAB_CHECK_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * heads * N * N, st));
     KLAB_CHECK_CUDA(cudaMemsetAsync(dlogit_scale, 0, sizeof(float) * heads, st));
     const int npairs = (B * a.nW + 1) / 2;
-    int nchunks = (sm_count() + heads - 1) / heads;
-    if (nchunks > npairs) nchunks = npairs;
-    if (nchunks < 1) nchunks = 1;
-    const dim3 grid(nchunks, heads);
+    int grid = sm_count();                                           // one resident CTA per SM, equal shares of the work items
+    if (grid > npairs * heads) grid = npairs * heads;
     swin_attn_bwd_tc_kernel<<<grid, BWD_THREADS, smem, st>>>(a, npairs);
     KLAB_LAUNCH_CHECK();
     count_launch();
