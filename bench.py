@@ -327,6 +327,8 @@ def run_ours(args, w):
     dev = torch.device("cuda", local)
     if world > 1:
         import datetime
+        # the collective shares the GPU with the persistent tcgen05 kernels: cap its CTAs; the model leaves that many SMs free
+        os.environ.setdefault("NCCL_MAX_CTAS", "8")
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=int(os.environ.get("KLAB_NCCL_TIMEOUT_S", "600"))))
     L.check(L.lib().klab_check_device())
     model, tcfg = build_model(w, dev, args.dtype)
@@ -417,6 +419,13 @@ def run_ours(args, w):
     clocks = sampler.summary(lo, hi) if sampler else None
     if sampler:
         sampler.stop()
+    dp_sync = None
+    if world > 1:                                       # data-parallel sanity: after K averaged steps every rank holds the same weights
+        probe = torch.stack([p.detach().double().sum() for p in list(model.transformer.parameters())[:8] + list(model.transformer.parameters())[-8:]])
+        lo_, hi_ = probe.clone(), probe.clone()
+        dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+        dp_sync = bool(torch.equal(lo_, hi_))
     B = w["batch"]
     ms_step = ms_res / args.steps
     value = world * B / (ms_step * 1e-3)
@@ -425,6 +434,8 @@ def run_ours(args, w):
     if world > 1:                                       # collectives are over: what follows is rank-0-local reporting
         dist.barrier()
         dist.destroy_process_group()
+        if getattr(model, "_klab_reducer", None) is not None:
+            model._klab_reducer.enabled = False
     def local_step():                                   # rank-local (no DDP collectives): only rank 0 runs the roofline probe
         loss = model({"pixel_values": px_d}, {"input_ids": src_d}, {"input_ids": tgt_d})
         loss.backward()
@@ -458,6 +469,11 @@ def run_ours(args, w):
             "step_model_tflops": step_tflops, "step_frac_of_peak": step_tflops / pk["tflops"], "loss": loss_v,
             "cuda_graphs": POOL.stats(),
         }
+        if world > 1:
+            red = getattr(model, "_klab_reducer", None)
+            line["data_parallel"] = {"weights_identical_across_ranks": dp_sync, "reducer": "klab GradReducer (grouped in-place NCCL all-reduce per bucket)" if red else "torch DDP",
+                                     "buckets_per_step": getattr(red, "buckets_last_backward", None), "sm_reserve": O.sm_reserve_info(),
+                                     "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS")}
         emit(line)
 
 

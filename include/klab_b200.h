@@ -39,6 +39,12 @@ const char* klab_last_error(void);
 int klab_check_device(void);
 /* number of kernels this library has launched since load (bench.py's `gpu_launches`). */
 long long klab_launch_count(void);
+/* Data parallelism (replaces nothing in HF; serves /root/reference/train.py:26): the persistent kernels of this library size
+ * their grids to the SM count minus `n_sms`, leaving those SMs to the CTAs of a concurrently running NCCL collective (a
+ * 230 KB-shared-memory CTA cannot share an SM with them; without the reserve every persistent kernel that overlaps a
+ * collective runs a second, nearly empty wave).  0 = use every SM (default).  klab_sm_budget returns the SMs in use. */
+int klab_set_sm_reserve(int n_sms);
+int klab_sm_budget(void);
 
 /* ---- K5: GEMM with fused epilogue -----------------------------------------------------------
  * Replaces every nn.Linear on the path: HF/models/swinv2/modeling_swinv2.py:535,578-579,591,385 and

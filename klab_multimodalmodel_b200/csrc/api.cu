@@ -20,6 +20,10 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+static std::atomic<int> g_sm_reserve{0};
+
+// SMs the persistent kernels may fill: the device's SM count minus the reserve set by klab_set_sm_reserve (SMs left to a
+// concurrently running collective, whose CTAs cannot be co-resident with a full-shared-memory CTA of ours).
 int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -27,7 +31,8 @@ int sm_count() {
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
             n = 148;
     }
-    return n;
+    const int r = g_sm_reserve.load(std::memory_order_relaxed);
+    return n - r > 16 ? n - r : (n < 16 ? n : 16);
 }
 
 // cuTensorMapEncodeTiled is fetched through the runtime so that the library carries no link-time
@@ -97,6 +102,11 @@ int klab_abi_version(void) { return KLAB_ABI_VERSION; }
 const char* klab_last_error(void) { return g_err; }
 int klab_check_device(void) { return check_device_impl(); }
 long long klab_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+int klab_set_sm_reserve(int n_sms) {
+    g_sm_reserve.store(n_sms < 0 ? 0 : n_sms, std::memory_order_relaxed);
+    return KLAB_OK;
+}
+int klab_sm_budget(void) { return sm_count(); }
 
 static klab_gemm_epilogue default_epilogue(const klab_gemm_epilogue* epi, int in_dtype) {
     klab_gemm_epilogue e;

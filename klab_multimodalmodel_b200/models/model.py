@@ -11,10 +11,16 @@ checkpoint keys and error behaviour -- the arithmetic behind `forward` is libkla
 
 One optional extra: `args.compute_dtype` ("bf16" default | "fp32"); the reference's argparse namespace does not have it, so
 the default applies and train.py needs no change.
+
+Data parallelism: `DistributedDataParallel(model)` (train.py:26) works unchanged.  When DDP's constructor asks the module which
+parameters to ignore, the module hands it all trainable parameters but one and averages those gradients itself (reducer.py:
+grouped in-place NCCL all-reduces issued block by block during backward, no bucket copies).  KLAB_GRAD_REDUCER=0 leaves
+everything to DDP's own reducer.
 """
 import os
 
 import torch
+import torch.distributed as dist
 from torch import nn
 
 from .. import functional as Fn
@@ -33,6 +39,27 @@ class MyModel(nn.Module):
 
         self.transformer = T5ForConditionalGeneration.from_pretrained(args.transformer_model_name)
         self.compute_dtype = _compute_dtype(getattr(args, "compute_dtype", None))
+        self._klab_reducer = None
+
+    # the one trainable tensor left to DDP's own reducer (DDP refuses a module that has nothing to reduce)
+    _DDP_KEEPS = "transformer.decoder.final_layer_norm.weight"
+
+    @property
+    def _ddp_params_and_buffers_to_ignore(self):
+        """Read by DistributedDataParallel.__init__ (torch/nn/parallel/distributed.py: `hasattr(module, ...)`).  Outside an
+        initialised multi-rank process group -- or with KLAB_GRAD_REDUCER=0 -- nothing is ignored and DDP does all the work."""
+        if os.environ.get("KLAB_GRAD_REDUCER", "1") == "0" or not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2:
+            return []
+        named = [(n, p) for n, p in self.named_parameters() if p.requires_grad and n != self._DDP_KEEPS]
+        if self._klab_reducer is None and named:
+            from .. import _lib as L
+            from ..reducer import GradReducer, broadcast_from_rank0
+            broadcast_from_rank0([p for _, p in named])                # DDP broadcasts only the parameters it keeps
+            self._klab_reducer = GradReducer([p for _, p in named])
+            if named[0][1].is_cuda:
+                # persistent kernels leave room for the collective's CTAs (which cannot share an SM with a 230 KB GEMM CTA)
+                L.lib().klab_set_sm_reserve(int(os.environ.get("KLAB_SM_RESERVE", os.environ.get("NCCL_MAX_CTAS", "8"))))
+        return [n for n, _ in named]
 
     def _concat_embeddings(self, images, source_encoding):
         cd = self.compute_dtype

@@ -31,6 +31,10 @@ def launch_count() -> int:
     return int(L.lib().klab_launch_count())
 
 
+def sm_reserve_info() -> dict:
+    return {"sm_budget": int(L.lib().klab_sm_budget())}
+
+
 # ------------------------------------------------------------------------------------------------
 # GEMM
 # ------------------------------------------------------------------------------------------------

@@ -45,7 +45,12 @@ def _worker(rank, world, port, q):
             r.copy_(p.detach())
             dist.broadcast(r, src=0)
             assert torch.equal(r, p.detach()), "parameters were not broadcast from rank 0"
+        # the module took the gradient exchange over: DDP's own reducer keeps exactly one trainable tensor
+        assert model._klab_reducer is not None
+        assert sum(p.requires_grad for p in ddp._module_parameters) == 1
+        assert "transformer.decoder.final_layer_norm.weight" not in ddp.parameters_to_ignore
         trainable = [p for p in ddp.parameters() if p.requires_grad]
+        assert len(model._klab_reducer.params) == len(trainable) - 1
         assert all(not p.requires_grad for p in model.language_model.parameters())
         assert len({id(p) for p in model.transformer.parameters()}) == len(list(model.transformer.parameters()))   # tied weight once
         # gradients: a rank-dependent surrogate loss through DDP's hooks -> every rank ends with the mean over ranks
@@ -56,6 +61,28 @@ def _worker(rank, world, port, q):
         out.backward()
         for p in trainable:
             assert p.grad is not None and torch.allclose(p.grad, torch.full_like(p.grad, (1.0 + world) / 2.0)), "gradients not averaged"
+        assert model._klab_reducer.buckets_last_backward >= 1 and not model._klab_reducer._works
+        # second micro-step without zero_grad (the reference accumulates and all-reduces every time, train.py:61-67): the
+        # accumulated value is averaged again, which leaves the already-averaged part unchanged
+        out = sum((p * (10.0 * (rank + 1.0))).sum() for p in trainable)
+        ddp.reducer.prepare_for_backward([])
+        out.backward()
+        for p in trainable:
+            assert torch.allclose(p.grad, torch.full_like(p.grad, 11.0 * (1.0 + world) / 2.0)), "accumulated gradients not averaged"
+        # no_sync: local accumulation only
+        for p in trainable:
+            p.grad = None
+        with model._klab_reducer.no_sync(), ddp.no_sync():
+            sum((p * (rank + 1.0)).sum() for p in trainable).backward()
+        assert all(torch.allclose(p.grad, torch.full_like(p.grad, rank + 1.0)) for p in trainable)
+        # small buckets: several grouped all-reduces per backward, same result
+        model._klab_reducer.bucket_bytes = 64 << 10
+        for p in trainable:
+            p.grad = None
+        ddp.reducer.prepare_for_backward([])
+        sum((p * (rank + 1.0)).sum() for p in trainable).backward()
+        assert model._klab_reducer.buckets_last_backward > 1
+        assert all(torch.allclose(p.grad, torch.full_like(p.grad, (1.0 + world) / 2.0)) for p in trainable)
         # bench helpers: per-rank shards differ; timing is the max over ranks
         w = dict(bench.WORKLOADS["tiny"])
         px, src, tgt = bench.synth_batch(w, 512, 1234 + rank, pin=False)
