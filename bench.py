@@ -327,8 +327,9 @@ def run_ours(args, w):
     dev = torch.device("cuda", local)
     if world > 1:
         import datetime
-        # the collective shares the GPU with the persistent tcgen05 kernels: cap its CTAs; the model leaves that many SMs free
-        os.environ.setdefault("NCCL_MAX_CTAS", "8")
+        # the collective shares the GPU with the persistent tcgen05 kernels (which hand out work dynamically and simply run
+        # on the SMs that are left): cap its CTAs so that it never takes more than ~10 % of the machine
+        os.environ.setdefault("NCCL_MAX_CTAS", "16")
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=int(os.environ.get("KLAB_NCCL_TIMEOUT_S", "600"))))
     L.check(L.lib().klab_check_device())
     model, tcfg = build_model(w, dev, args.dtype)

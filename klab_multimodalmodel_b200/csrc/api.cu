@@ -1,6 +1,7 @@
 // C-ABI entry points (include/klab_b200.h) and host-side plumbing shared by all kernels.
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -24,15 +25,45 @@ static std::atomic<int> g_sm_reserve{0};
 
 // SMs the persistent kernels may fill: the device's SM count minus the reserve set by klab_set_sm_reserve (SMs left to a
 // concurrently running collective, whose CTAs cannot be co-resident with a full-shared-memory CTA of ours).
-int sm_count() {
+int sm_count_physical() {
     static int n = 0;
     if (n == 0) {
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
             n = 148;
     }
+    return n;
+}
+
+int sm_count() {
+    const int n = sm_count_physical();
     const int r = g_sm_reserve.load(std::memory_order_relaxed);
     return n - r > 16 ? n - r : (n < 16 ? n : 16);
+}
+
+// Work-item counters of the dynamically scheduled persistent kernels (GEMM, attention): {next item, finished CTAs} per slot,
+// zero between launches (the last CTA of a launch re-arms its slot, so CUDA graphs can replay it).  Launches take slots
+// round-robin; two launches share a slot only when SCHED_SLOTS launches apart, long after the first has finished in any
+// stream order this library produces.  Returns nullptr (= static striding) when the pool does not exist yet and cannot be
+// created because the stream is capturing, or with KLAB_STATIC_SCHED=1.
+constexpr int SCHED_SLOTS = 8192;
+static int* g_sched_base[16] = {};
+static std::atomic<unsigned> g_sched_seq{0};
+
+int* sched_slot(cudaStream_t stream) {
+    static const bool off = []() { const char* e = getenv("KLAB_STATIC_SCHED"); return e && e[0] == '1'; }();
+    if (off) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    if (!g_sched_base[dev]) {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;
+        int* p = nullptr;
+        if (cudaMalloc(&p, SCHED_SLOTS * 2 * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        if (cudaMemset(p, 0, SCHED_SLOTS * 2 * sizeof(int)) != cudaSuccess) { cudaGetLastError(); cudaFree(p); return nullptr; }
+        g_sched_base[dev] = p;
+    }
+    return g_sched_base[dev] + 2 * (g_sched_seq.fetch_add(1, std::memory_order_relaxed) % SCHED_SLOTS);
 }
 
 // cuTensorMapEncodeTiled is fetched through the runtime so that the library carries no link-time

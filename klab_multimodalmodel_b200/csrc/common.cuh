@@ -39,7 +39,39 @@ void set_error(const char* fmt, ...);
 
 inline size_t dtype_size(int dt) { return dt == KLAB_BF16 ? 2 : 4; }
 
-int sm_count();
+int sm_count();             // SMs the persistent kernels may fill (physical count minus klab_set_sm_reserve)
+int sm_count_physical();
+int* sched_slot(cudaStream_t stream);      // {next item, finished CTAs} counters of one dynamically scheduled launch, or nullptr
+
+// Dynamic work distribution of a persistent kernel (device side).  A CTA's FIRST item is static (its block index: no atomic
+// round trip in front of the first load of every launch -- that alone cost ~2 us x 1 200 GEMMs per step); later items come
+// from the counter, starting at gridDim.x.  `claim` is called by ONE thread per CTA; without a counter it is the static
+// stride blockIdx.x + i * gridDim.x.  If a concurrent collective holds some SMs, the CTAs that start late process only their
+// one static item; everything else has been taken by the CTAs that were resident.
+struct WorkClaim {
+    int* ctr;
+    int next_static;
+    __device__ __forceinline__ void init(int* c) { ctr = c; next_static = blockIdx.x + gridDim.x; ticket = -1; }
+    __device__ __forceinline__ int first() const { return blockIdx.x; }
+    __device__ __forceinline__ int claim() {
+        if (ctr) return static_cast<int>(gridDim.x) + atomicAdd(&ctr[0], 1);
+        const int v = next_static;
+        next_static += gridDim.x;
+        return v;
+    }
+    // After the CTA's last claim (the claiming thread has SEEN a result past the end, so all its claims have been performed):
+    // count this CTA as finished; the last one re-arms the counters.  Split in two so that the atomic's round trip can overlap
+    // the CTA's remaining work: finish_begin() right after the last claim, finish_end() at the very end.  No fence is needed:
+    // the next user of the slot is a later launch.
+    int ticket;
+    __device__ __forceinline__ void finish_begin() { ticket = ctr ? atomicAdd(&ctr[1], 1) : -1; }
+    __device__ __forceinline__ void finish_end() {
+        if (ctr && ticket == static_cast<int>(gridDim.x) - 1) {
+            ctr[0] = 0;
+            ctr[1] = 0;
+        }
+    }
+};
 
 // ------------------------------------------------------------------------------------------------
 // Scalar conversion helpers

@@ -16,6 +16,14 @@
 //                                    paced every GEMM with K <= 1024.
 // Two TMEM accumulator stages (columns 0.. and 256..) let the epilogue of tile i overlap the MMAs of tile i+1.
 //
+// Work items after a CTA's first (= its block index) are handed out DYNAMICALLY: the producer thread claims the next item
+// with an atomicAdd on a per-launch counter and publishes it to the MMA and epilogue warps through a 4-deep shared-memory queue (mbarrier pair per slot).  A static
+// stride (item = blockIdx.x + i * gridDim.x) assumes every CTA of the grid is resident at once; under data parallelism the
+// NCCL all-reduce of the gradient buckets holds some SMs for hundreds of microseconds, the CTAs that do not fit wait for a
+// whole wave and every GEMM that overlaps a collective takes twice as long (measured: +10 ms per step at 2 GPUs).  With the
+// counter the resident CTAs simply take more items and late CTAs find none.  The last CTA to finish resets the counter, so a
+// CUDA graph can replay the launch.
+//
 // The N tile BN is a RUN-TIME parameter (multiple of 16, or of 64 when B is MN-major): with 148 SMs and tile counts
 // like 48 x 4, a fixed 256-wide tile leaves the second wave 70 % empty; BN = 176 gives 288 tiles = 1.95 waves.
 // The choice is made by a small cost model that knows the two things that actually bound this kernel on B200:
@@ -45,6 +53,7 @@ constexpr int SMEM_BYTES = 227 * 1024;                   // everything an SM has
 constexpr int RING_BYTES = SMEM_BYTES - 1024 /*align slack*/ - CTRL_BYTES;
 constexpr int ACC_STRIDE = 256;                          // TMEM columns between the two accumulator stages
 constexpr int CH = 16;                                   // epilogue chunk (columns per tcgen05.ld)
+constexpr int SQ = 4;                                    // depth of the in-CTA work-item queue
 
 struct SplitK {
     float* ws;            // [splits][m_pad][n_pad] fp32 partial results
@@ -74,7 +83,7 @@ template <bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     void* __restrict__ D, long long ldd, int M, int N, int K, int BN, int stages, SplitK sk,
-                    klab_gemm_epilogue epi, CeArgs ce) {
+                    klab_gemm_epilogue epi, CeArgs ce, int* __restrict__ sched) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* ctrl = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* ring = ctrl + CTRL_BYTES;
@@ -82,7 +91,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint64_t* empty_bar = full_bar + MAX_STAGES;
     uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* sq_full = tmem_empty_bar + 2;
+    uint64_t* sq_empty = sq_full + SQ;
+    int* sq_item = reinterpret_cast<int*>(sq_empty + SQ);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sq_item + SQ);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -105,6 +117,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             mbar_init(&tmem_full_bar[s], 1);
             mbar_init(&tmem_empty_bar[s], NUM_EPI_WARPS);
         }
+        for (int s = 0; s < SQ; ++s) {
+            mbar_init(&sq_full[s], 1);
+            mbar_init(&sq_empty[s], 1 + NUM_EPI_WARPS);        // MMA issuer + every epilogue warp
+        }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -126,7 +142,28 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            int sq = 0;
+            uint32_t sq_phase = 0;
+            int item = blockIdx.x;                              // first item: static, no atomic in front of the first load
+            while (true) {
+                if (sched) {                                    // publish the claimed item (or the end marker) to the consumers
+                    mbar_wait(&sq_empty[sq], sq_phase ^ 1);
+                    sq_item[sq] = item < num_items ? item : -1;
+                    mbar_arrive(&sq_full[sq]);
+                    if (++sq == SQ) { sq = 0; sq_phase ^= 1; }
+                }
+                if (item >= num_items) {
+                    // this CTA's claims are over (the result of the last one has been seen): count it as finished now, while
+                    // the MMA and epilogue warps still work; the last CTA to get here re-arms the counters for the next launch /
+                    // graph replay that uses this slot (nobody touches them again during this launch)
+                    if (sched && atomicAdd(&sched[1], 1) == static_cast<int>(gridDim.x) - 1) {
+                        sched[0] = 0;
+                        sched[1] = 0;
+                    }
+                    break;
+                }
+                // claim the next item now: the atomic's round trip hides behind this item's loads
+                const int next_item = (sched ? atomicAdd(&sched[0], 1) : item) + static_cast<int>(gridDim.x);
                 const int tile = item / splits, split = item - tile * splits;
                 // consecutive items share the m tile (and therefore A) while sweeping n: CTAs running side by side hit the same
                 // A rows in L2
@@ -154,6 +191,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     }
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
+                item = next_item;
             }
         }
     } else if (warp == 1) {
@@ -164,7 +202,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+            int sq = 0;
+            uint32_t sq_phase = 0;
+            int item = blockIdx.x;
+            while (true) {
+                if (sched) {
+                    mbar_wait(&sq_full[sq], sq_phase);
+                    item = sq_item[sq];
+                    mbar_arrive(&sq_empty[sq]);
+                    if (++sq == SQ) { sq = 0; sq_phase ^= 1; }
+                    if (item < 0) break;
+                } else if (item >= num_items) {
+                    break;
+                }
                 const int split = item % splits;
                 const int kb0 = split * kps, kb1 = min(num_k, kb0 + kps);
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
@@ -188,6 +238,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
                 umma_commit(&tmem_full_bar[acc]);             // accumulator complete -> epilogue
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (!sched) item += gridDim.x;
             }
         }
     } else {
@@ -199,7 +250,20 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         const int nchunks = BN / CH;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int sq = 0;
+        uint32_t sq_phase = 0;
+        int item = blockIdx.x;
+        while (true) {
+            if (sched) {
+                mbar_wait(&sq_full[sq], sq_phase);
+                item = sq_item[sq];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sq_empty[sq]);
+                if (++sq == SQ) { sq = 0; sq_phase ^= 1; }
+                if (item < 0) break;
+            } else if (item >= num_items) {
+                break;
+            }
             const int tile = item / splits, split = item - tile * splits;
             const int m0 = (tile / num_n) * BM;
             const int n0 = (tile % num_n) * BN;
@@ -304,6 +368,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (!sched) item += gridDim.x;
         }
     }
 
@@ -401,7 +466,7 @@ double epilogue_instr(const klab_gemm_epilogue& e) {
 //   split-K adds the partial round trip through L2 (write + read by the last CTA).
 void pick_config(int M, int N, int K, bool b_mn, bool can_split, size_t ws_bytes, const klab_gemm_epilogue& epi, int* bn_out,
                  int* splits_out) {
-    const int sms = sm_count();
+    const int sms = sm_count_physical();
     const int num_m = (M + BM - 1) / BM, num_k = (K + BK - 1) / BK;
     const double instr = epilogue_instr(epi);
     double best = 1e30;
@@ -462,7 +527,10 @@ int launch_cfg(cudaStream_t stream, int M, int N, int K, int bn, int splits, Wor
         sk.ws = w->ws; sk.n_pad = n_pad; sk.split_stride = m_pad * n_pad;
     }
     const int items = tiles * splits;
-    const int grid = items < sm_count() ? items : sm_count();
+    int* sched = sched_slot(stream);
+    // dynamic scheduling needs no SM reserve (CTAs that find the SMs taken by a collective simply find no work later)
+    const int sms = sched ? sm_count_physical() : sm_count();
+    const int grid = items < sms ? items : sms;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(NUM_THREADS);
@@ -474,7 +542,7 @@ int launch_cfg(cudaStream_t stream, int M, int N, int K, int bn, int splits, Wor
     static const bool pdl = []() { const char* e = getenv("KLAB_PDL"); return !(e && e[0] == '0'); }();
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    KLAB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, D, ldd, M, N, K, bn, stages_for(bn), sk, epi, ce));
+    KLAB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, D, ldd, M, N, K, bn, stages_for(bn), sk, epi, ce, sched));
     KLAB_LAUNCH_CHECK();
     count_launch();
     if (splits > 1) {

@@ -35,6 +35,7 @@ struct TcArgs {
     float dropout_p;
     unsigned long long seed;
     const unsigned long long* seed_ptr;
+    int* sched;                // dynamic work distribution of the persistent kernels ({next problem, finished CTAs}) or null
 };
 
 // byte offset of element (row, col) inside a [rows x 64] bf16 tile stored with the 128-byte swizzle (TMA SWIZZLE_128B /
@@ -541,17 +542,40 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_fwd_tc1_kernel(const __
         tma_load_2d(base + T, &tmk, &bars[buf], h * DK, b * Lk);
         tma_load_2d(base + 2 * T, &tmv, &bars[buf], h * DK, b * Lk);
     };
-    if (tid == 0 && static_cast<int>(blockIdx.x) < nprob) issue_loads(blockIdx.x, 0);
+    // problems are claimed dynamically (common.cuh: WorkClaim), one ahead of the one being computed so that its operands
+    // can be prefetched; s_bh[buf] = problem whose operands sit in buffer set buf
+    __shared__ int s_bh[2];
+    WorkClaim wc;
+    wc.init(a.sched);
+    int n1 = nprob, n2 = nprob;                            // thread 0: the next problem and the one after (claimed ahead: the
+    if (tid == 0) {                                        // atomic's round trip must not sit in front of an MMA issue)
+        const int first = wc.first();
+        s_bh[0] = first;
+        if (first < nprob) {
+            issue_loads(first, 0);
+            n1 = wc.claim();
+        }
+    }
+    __syncthreads();
 
     uint32_t mma_phase = 0;
     int it = 0;
-    for (int bh = blockIdx.x; bh < nprob; bh += gridDim.x, ++it) {
+    for (int bh = s_bh[0]; bh < nprob; ++it) {
         const int buf = it & 1;
         const int h = bh % a.H, b = bh / a.H;
         uint8_t* sQ = sIn + buf * 3 * T;
         uint8_t* sK = sQ + T;
         uint8_t* sV = sK + T;
-        if (tid == 0 && bh + static_cast<int>(gridDim.x) < nprob) issue_loads(bh + gridDim.x, buf ^ 1);
+        if (tid == 0) {
+            s_bh[buf ^ 1] = n1;
+            if (n1 < nprob) {
+                issue_loads(n1, buf ^ 1);
+                n2 = wc.claim();                           // consumed at the end of this iteration
+            } else {
+                wc.finish_begin();                         // this is the CTA's last iteration (bh becomes n1 >= nprob): its claims
+                n2 = nprob;                                //   are over; the atomic's round trip overlaps the last problem
+            }
+        }
         const bool has_bias = a.bias_table != nullptr;
         if (has_bias && tid < Lq + Lk - 1) {
             const int rel = tid - (Lq - 1) - a.q_offset;
@@ -654,7 +678,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_fwd_tc1_kernel(const __
         tc_fence_before();
         __syncthreads();                                   // TMEM, sP, brel, sred are reused by the next problem
         tc_fence_after();
+        bh = s_bh[buf ^ 1];
+        n1 = n2;
     }
+    if (tid == 0) wc.finish_end();                         // (the grid never exceeds the problem count: every CTA ran >= 1 iteration)
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -721,18 +748,39 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_bwd_tc1_kernel(const __
         tma_load_2d(base + 2 * T, &tmk, &bars[buf], h * DK, b * Lk);
         tma_load_2d(base + 3 * T, &tmv, &bars[buf], h * DK, b * Lk);
     };
-    if (tid == 0 && static_cast<int>(blockIdx.x) < nprob) issue_loads(blockIdx.x, 0);
+    __shared__ int s_bh[2];                                // see the forward kernel
+    WorkClaim wc;
+    wc.init(a.sched);
+    int n1 = nprob, n2 = nprob;                            // thread 0: the next problem and the one after (claimed ahead: the
+    if (tid == 0) {                                        // atomic's round trip must not sit in front of an MMA issue)
+        const int first = wc.first();
+        s_bh[0] = first;
+        if (first < nprob) {
+            issue_loads(first, 0);
+            n1 = wc.claim();
+        }
+    }
+    __syncthreads();
 
     uint32_t mma_phase = 0;
     int it = 0;
-    for (int bh = blockIdx.x; bh < nprob; bh += gridDim.x, ++it) {
+    for (int bh = s_bh[0]; bh < nprob; ++it) {
         const int buf = it & 1;
         const int h = bh % a.H, b = bh / a.H;
         uint8_t* sQ = sIn + buf * 4 * T;
         uint8_t* sdO = sQ + T;
         uint8_t* sK = sdO + T;
         uint8_t* sV = sK + T;
-        if (tid == 0 && bh + static_cast<int>(gridDim.x) < nprob) issue_loads(bh + gridDim.x, buf ^ 1);
+        if (tid == 0) {
+            s_bh[buf ^ 1] = n1;
+            if (n1 < nprob) {
+                issue_loads(n1, buf ^ 1);
+                n2 = wc.claim();                           // consumed at the end of this iteration
+            } else {
+                wc.finish_begin();                         // this is the CTA's last iteration (bh becomes n1 >= nprob): its claims
+                n2 = nprob;                                //   are over; the atomic's round trip overlaps the last problem
+            }
+        }
         if (has_bias && tid < Lq + Lk - 1) {
             const int rel = tid - (Lq - 1) - a.q_offset;
             brel[tid] = a.bias_table[a.rel_bucket[rel + a.rel_zero] * a.H + h];
@@ -897,7 +945,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_bwd_tc1_kernel(const __
         __syncthreads();                                   // TMEM, sP / sdS, brel / bins are reused by the next problem
         tc_fence_after();
         if (has_bias && tid < a.num_buckets) a.dbias_partial[static_cast<long long>(bh) * a.num_buckets + tid] = bins[tid];
+        bh = s_bh[buf ^ 1];
+        n1 = n2;
     }
+    if (tid == 0) wc.finish_end();                         // (the grid never exceeds the problem count: every CTA ran >= 1 iteration)
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -950,7 +1001,9 @@ int t5_attention_fwd_tc(cudaStream_t st, int B, int H, int Lq, int Lk, const voi
             set1 = true;
         }
         const int nprob = B * H;
-        t5_attn_fwd_tc1_kernel<<<nprob < sm_count() ? nprob : sm_count(), ST_THREADS, smem1, st>>>(tq, tk, tv, a, lkp);
+        a.sched = sched_slot(st);
+        const int sms = a.sched ? sm_count_physical() : sm_count();
+        t5_attn_fwd_tc1_kernel<<<nprob < sms ? nprob : sms, ST_THREADS, smem1, st>>>(tq, tk, tv, a, lkp);
         KLAB_LAUNCH_CHECK();
         count_launch();
         return KLAB_OK;
@@ -1006,7 +1059,9 @@ int t5_attention_bwd_tc(cudaStream_t st, int B, int H, int Lq, int Lk, const voi
             set1 = true;
         }
         const int nprob = B * H;
-        t5_attn_bwd_tc1_kernel<<<nprob < sm_count() ? nprob : sm_count(), ST_THREADS, smem1, st>>>(tq, tk, tv, tdo, a, (Lq + 15) / 16 * 16,
+        a.sched = sched_slot(st);
+        const int sms = a.sched ? sm_count_physical() : sm_count();
+        t5_attn_bwd_tc1_kernel<<<nprob < sms ? nprob : sms, ST_THREADS, smem1, st>>>(tq, tk, tv, tdo, a, (Lq + 15) / 16 * 16,
                                                                                                    (Lk + 15) / 16 * 16);
         KLAB_LAUNCH_CHECK();
         count_launch();

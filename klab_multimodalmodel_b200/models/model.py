@@ -57,8 +57,10 @@ class MyModel(nn.Module):
             broadcast_from_rank0([p for _, p in named])                # DDP broadcasts only the parameters it keeps
             self._klab_reducer = GradReducer([p for _, p in named])
             if named[0][1].is_cuda:
-                # persistent kernels leave room for the collective's CTAs (which cannot share an SM with a 230 KB GEMM CTA)
-                L.lib().klab_set_sm_reserve(int(os.environ.get("KLAB_SM_RESERVE", os.environ.get("NCCL_MAX_CTAS", "8"))))
+                # GEMM and T5-attention kernels hand out their work dynamically and need no SMs set aside; the Swin attention
+                # kernels keep static contiguous shares (head affinity) and leave the collective's SMs free instead -- a 200 KB
+                # CTA cannot share an SM with an NCCL CTA, and a CTA that starts a wave late doubles the kernel's time.
+                L.lib().klab_set_sm_reserve(int(os.environ.get("KLAB_SM_RESERVE", os.environ.get("NCCL_MAX_CTAS", "16"))))
         return [n for n, _ in named]
 
     def _concat_embeddings(self, images, source_encoding):
