@@ -11,6 +11,7 @@ autograd graph only.  Citations: HF/ = site-packages/transformers 5.5.0.
 """
 from __future__ import annotations
 
+import os
 import weakref
 
 import torch
@@ -197,6 +198,54 @@ def _detach_aliased_grads(params):
 
 
 # ------------------------------------------------------------------------------------------------
+# weight-gradient side stream
+# ------------------------------------------------------------------------------------------------
+class _Side:
+    """Weight (and bias) gradients hang off the backward critical path: nothing inside a block consumes them.  They are issued
+    on a second stream -- inside a captured region that becomes a parallel branch of the CUDA graph -- so they fill the SMs
+    that the latency-bound chain of small dgrad GEMMs / attention / norm kernels leaves idle (the persistent GEMM hands out its
+    tiles dynamically, so two GEMMs share the machine gracefully).  All split-K GEMMs of a step are weight gradients and
+    therefore serialise on this one stream, which is what their shared fp32 workspace requires (gemm_tc.cu).
+    Inputs of a side-stream kernel are kept alive until the join (the caching allocator knows only the allocating stream).
+    KLAB_WGRAD_STREAM=0 issues everything on one stream."""
+    enabled = os.environ.get("KLAB_WGRAD_STREAM", "1") != "0"
+    streams: dict = {}
+    keep: list = []
+    dirty = False
+
+    @classmethod
+    def run(cls, fn, *tensors, **kw):
+        if not cls.enabled or not tensors[0].is_cuda:
+            return fn(*tensors, **kw)
+        main = torch.cuda.current_stream()
+        side = cls.streams.get(main.device)
+        if side is None:
+            side = cls.streams[main.device] = torch.cuda.Stream(main.device)
+        side.wait_stream(main)                     # everything issued so far (the operands) happens-before the side kernel
+        with torch.cuda.stream(side):
+            out = fn(*tensors, **kw)
+        cls.keep.extend(tensors)
+        cls.dirty = True
+        return out
+
+    @classmethod
+    def join(cls):
+        if cls.dirty:
+            main = torch.cuda.current_stream()
+            main.wait_stream(cls.streams[main.device])
+            cls.keep.clear()
+            cls.dirty = False
+
+
+def _wgrad(dy, x, **kw):
+    return _Side.run(O.linear_wgrad, dy, x, **kw)
+
+
+def _colsum(dy):
+    return _Side.run(O.colsum, dy)
+
+
+# ------------------------------------------------------------------------------------------------
 # T5 block  (HF/models/t5/modeling_t5.py: T5LayerSelfAttention :356-377, T5LayerCrossAttention :387-408,
 #            T5LayerFF :135-150, T5Attention :253-344)
 # dropout sites of block `c` use seeds c.seed + {0..5} plus the device-side step counter c.seed_ptr
@@ -227,7 +276,7 @@ def _t5_attn_bwd(c, dh, n, kv_src, wq_or_qkv, wkv, wo, qkv, kvbuf, ctxt, lse, ta
     if c.p > 0.0:                                        # dropout on the o-projection output (:375 / :406)
         dh = O.dropout_apply(dh, c.p, seed + 1, c.seed_ptr)
     dctx = O.linear_dgrad(dh, wo)
-    dwo = O.linear_wgrad(dh, ctxt)
+    dwo = _wgrad(dh, ctxt)
     dqkv = torch.empty_like(qkv)
     if kv_src is None:
         q, k, v = qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:]
@@ -240,11 +289,11 @@ def _t5_attn_bwd(c, dh, n, kv_src, wq_or_qkv, wkv, wo, qkv, kvbuf, ctxt, lse, ta
     O.t5_attention_bwd(q, k, v, ctxt, dctx, lse, dq, dk_, dv, c.B, H, Lq, Lk, dk, bias_table=table, lut=lut, rel_zero=rz,
                        num_buckets=c.num_buckets, causal=causal, dbias_table=dtable, dropout_p=c.p, seed=seed, seed_ptr=c.seed_ptr)
     dn = O.linear_dgrad(dqkv, wq_or_qkv)
-    dwq = O.linear_wgrad(dqkv, n)
+    dwq = _wgrad(dqkv, n)
     if kv_src is None:
         return dn, None, dwq, None, dwo
     dkv_src = O.linear_dgrad(dkvbuf, wkv)
-    dwkv = O.linear_wgrad(dkvbuf, kv_src)
+    dwkv = _wgrad(dkvbuf, kv_src)
     return dn, dkv_src, dwq, dwkv, dwo
 
 
@@ -258,9 +307,9 @@ def _t5_ff_fwd(c, x, ln_w, wi, wo, seed):
 def _t5_ff_bwd(c, dout, x, ln_w, wi, wo, n, rstd, f, seed):
     dy = O.dropout_apply(dout, c.p, seed + 1, c.seed_ptr) if c.p > 0.0 else dout
     df = O.linear_dgrad(dy, wo, act=L.ACT_RELU_BWD, aux_in=f, dropout_p=c.p, seed=seed, seed_ptr=c.seed_ptr)
-    dwo = O.linear_wgrad(dy, f)
+    dwo = _wgrad(dy, f)
     dn = O.linear_dgrad(df, wi)
-    dwi = O.linear_wgrad(df, n)
+    dwi = _wgrad(df, n)
     dx, dln = O.rmsnorm_bwd(dn, x, ln_w, rstd, dres=dout)
     return dx, dln, dwi, dwo
 
@@ -325,6 +374,7 @@ def _t5_block_bwd_body(dout, x, enc_out, *rest):
     dn0, _, dwqkv, _, dwo = _t5_attn_bwd(c, dh1, n0, None, wqkv, None, w_o, qkv, None, ctxt, lse, table, c.lut, c.rz, dec,
                                          c.L, c.L, seed, dtable)
     dx, dln0 = O.rmsnorm_bwd(dn0, x, ln0, rstd0, dres=dh1)
+    _Side.join()
     gq, gk, gv = dwqkv[:inner], dwqkv[inner:2 * inner], dwqkv[2 * inner:]
     if dec:
         grads = (dln0, gq, gk, gv, dwo, dln1, dwcq, dwckv[:inner], dwckv[inner:], dwco, dln2, dwi, dwo_ff)
@@ -611,15 +661,15 @@ def _swin_block_bwd_body(dout, x, qkv, bias16, hidden, tab, ctxt, lse, a, mean1,
     wqkv, w_p, w_f1, w_f2 = _swin_operands(c, params, cd, "peek")
     dm2, dg2, dbe2 = O.layernorm_bwd(dout, m2, g2, mean2, rstd2)
     dm_pre = O.linear_dgrad(dm2, w_f2, act=L.ACT_GELU_BWD, aux_in=m_pre)
-    df2w = O.linear_wgrad(dm2, m_act)
-    df2b = O.colsum(dm2)
+    df2w = _wgrad(dm2, m_act)
+    df2b = _colsum(dm2)
     dh = O.linear_dgrad(dm_pre, w_f1, residual=dout)                     # + residual path of the second norm
-    df1w = O.linear_wgrad(dm_pre, h)
-    df1b = O.colsum(dm_pre)
+    df1w = _wgrad(dm_pre, h)
+    df1b = _colsum(dm_pre)
     da, dg1, dbe1 = O.layernorm_bwd(dh, a, g1, mean1, rstd1)
     dctx = O.linear_dgrad(da, w_p)
-    dpw = O.linear_wgrad(da, ctxt)
-    dpb = O.colsum(da)
+    dpw = _wgrad(da, ctxt)
+    dpb = _colsum(da)
     dqkv = torch.empty_like(qkv)
     q, k, v = qkv[:, :C_], qkv[:, C_:2 * C_], qkv[:, 2 * C_:]
     lsv = ls.detach().reshape(-1)
@@ -627,8 +677,9 @@ def _swin_block_bwd_body(dout, x, qkv, bias16, hidden, tab, ctxt, lse, a, mean1,
                                       c.heads, c.hd, c.w, c.shift, lsv, bias16, lse)
     dw1, db1, dw2 = O.swin_cpb_bwd(c.coords, c.index, w2.detach(), hidden, tab, dbias, c.heads, c.N)
     dx = O.linear_dgrad(dqkv, wqkv, residual=dh)                          # + residual path of the first norm
-    dwqkv = O.linear_wgrad(dqkv, x)
-    dbqkv = O.colsum(dqkv)
+    dwqkv = _wgrad(dqkv, x)
+    dbqkv = _colsum(dqkv)
+    _Side.join()
     return (dx, dls.view(ls.shape), dw1, db1, dw2, dwqkv[:C_], dbqkv[:C_], dwqkv[C_:2 * C_], dwqkv[2 * C_:], dbqkv[2 * C_:],
             dpw, dpb, dg1, dbe1, df1w, df1b, df2w, df2b, dg2, dbe2)
 
