@@ -40,6 +40,7 @@ class MyModel(nn.Module):
         self.transformer = T5ForConditionalGeneration.from_pretrained(args.transformer_model_name)
         self.compute_dtype = _compute_dtype(getattr(args, "compute_dtype", None))
         self._klab_reducer = None
+        self._tower_streams = {}
 
     # the one trainable tensor left to DDP's own reducer (DDP refuses a module that has nothing to reduce)
     _DDP_KEEPS = "transformer.decoder.final_layer_norm.weight"
@@ -68,9 +69,23 @@ class MyModel(nn.Module):
         src = source_encoding["input_ids"]
         pixel_values = images["pixel_values"]
         B = pixel_values.shape[0]
-        with torch.no_grad():
-            lang = self.language_model.hidden_before_norm(src, cd)
-        img, n_img = self.image_model.features(pixel_values, cd)
+        # model.py:20-22: the frozen text encoder and the Swin encoder are independent until the concat.  The text tower is a
+        # chain of small (B * L_src rows) latency-bound kernels; on a second stream it fills the SMs the Swin kernels leave idle.
+        if src.is_cuda and os.environ.get("KLAB_TOWER_STREAM", "1") != "0":
+            main = torch.cuda.current_stream()
+            side = self._tower_streams.get(main.device)
+            if side is None:
+                side = self._tower_streams[main.device] = torch.cuda.Stream(main.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side), torch.no_grad():
+                lang = self.language_model.hidden_before_norm(src, cd)
+            img, n_img = self.image_model.features(pixel_values, cd)
+            main.wait_stream(side)
+            lang.record_stream(main)
+        else:
+            with torch.no_grad():
+                lang = self.language_model.hidden_before_norm(src, cd)
+            img, n_img = self.image_model.features(pixel_values, cd)
         d_img, d_lang, d_tr = img.shape[1], lang.shape[1], self.transformer.config.d_model
         if d_img != d_lang:        # torch.cat in the reference (model.py:23) raises the same way
             raise RuntimeError(f"Sizes of tensors must match except in dimension 1. Expected size {d_img} but got size {d_lang} "
