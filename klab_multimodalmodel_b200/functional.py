@@ -250,8 +250,9 @@ def _colsum(dy):
 #            T5LayerFF :135-150, T5Attention :253-344)
 # dropout sites of block `c` use seeds c.seed + {0..5} plus the device-side step counter c.seed_ptr
 # ------------------------------------------------------------------------------------------------
-def _t5_attn_fwd(c, n, kv_src, wq_or_qkv, wkv, wo, resid, table, lut, rz, causal, Lq, Lk, seed):
-    """n: normed input [B*Lq, d]; returns (h_out, qkv, kvbuf, ctx, lse) with h_out = resid + dropout(attn(n) Wo^T)."""
+def _t5_attn_fwd(c, n, kv_src, wq_or_qkv, wkv, wo, resid, table, lut, rz, causal, Lq, Lk, seed, kvbuf=None):
+    """n: normed input [B*Lq, d]; returns (h_out, qkv, kvbuf, ctx, lse) with h_out = resid + dropout(attn(n) Wo^T).
+    Cross-attention: `kvbuf` = k|v projection of the encoder output, possibly still in flight on the side stream."""
     H, dk = c.H, c.dk
     inner = H * dk
     qkv = O.linear_fwd(n, wq_or_qkv)
@@ -260,7 +261,10 @@ def _t5_attn_fwd(c, n, kv_src, wq_or_qkv, wkv, wo, resid, table, lut, rz, causal
         kvbuf = None
     else:                                                # cross-attention: q from n, k|v from the encoder output
         q = qkv
-        kvbuf = O.linear_fwd(kv_src, wkv)
+        if kvbuf is None:
+            kvbuf = O.linear_fwd(kv_src, wkv)
+        else:
+            _Side.join()
         k, v = kvbuf[:, :inner], kvbuf[:, inner:]
     ctxt, lse = O.t5_attention_fwd(q, k, v, c.B, H, Lq, Lk, dk, bias_table=table, lut=lut, rel_zero=rz,
                                    num_buckets=c.num_buckets, causal=causal, dropout_p=c.p, seed=seed, seed_ptr=c.seed_ptr)
@@ -292,7 +296,7 @@ def _t5_attn_bwd(c, dh, n, kv_src, wq_or_qkv, wkv, wo, qkv, kvbuf, ctxt, lse, ta
     dwq = _wgrad(dqkv, n)
     if kv_src is None:
         return dn, None, dwq, None, dwo
-    dkv_src = O.linear_dgrad(dkvbuf, wkv)
+    dkv_src = _Side.run(O.linear_dgrad, dkvbuf, wkv)    # gradient w.r.t. the encoder output: consumed after the block
     dwkv = _wgrad(dkvbuf, kv_src)
     return dn, dkv_src, dwq, dwkv, dwo
 
@@ -336,11 +340,14 @@ def _t5_block_fwd_body(x, enc_out, c, save, table, *params):
     else:
         ln0, ln1 = params[0], params[5]
         wqkv, w_o, w_i, w_ff = ws
+    # the k|v projection of the encoder output does not depend on this block's input: side stream, joined before cross-attention
+    kv_pre = _Side.run(O.linear_fwd, enc_out, w_ckv) if dec else None
     n0, rstd0 = O.rmsnorm_fwd(x, ln0, c.eps)
     h1, qkv, _, ctxt, lse = _t5_attn_fwd(c, n0, None, wqkv, None, w_o, x, table, c.lut, c.rz, dec, c.L, c.L, seed)
     if dec:
         n1, rstd1 = O.rmsnorm_fwd(h1, ln1, c.eps)
-        h2, qc, kvbuf, ctx2, lse2 = _t5_attn_fwd(c, n1, enc_out, w_cq, w_ckv, w_co, h1, None, None, 0, False, c.L, c.Le, seed + 2)
+        h2, qc, kvbuf, ctx2, lse2 = _t5_attn_fwd(c, n1, enc_out, w_cq, w_ckv, w_co, h1, None, None, 0, False, c.L, c.Le, seed + 2,
+                                                 kvbuf=kv_pre)
         out, n2, rstd2, f = _t5_ff_fwd(c, h2, ln2, w_i, w_ff, seed + 4)
         return (out, n0, rstd0, qkv, ctxt, lse, h1, n1, rstd1, qc, kvbuf, ctx2, lse2, h2, n2, rstd2, f) if save else (out,)
     out, n2, rstd2, f = _t5_ff_fwd(c, h1, ln1, w_i, w_ff, seed + 4)
