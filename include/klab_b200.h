@@ -45,6 +45,11 @@ long long klab_launch_count(void);
  * collective runs a second, nearly empty wave).  0 = use every SM (default).  klab_sm_budget returns the SMs in use. */
 int klab_set_sm_reserve(int n_sms);
 int klab_sm_budget(void);
+/* 1: the persistent GEMM / T5-attention kernels launched from now on take their work items from a per-launch counter (first
+ * item static), so CTAs that find their SM held by a collective do not stretch the kernel by a whole wave; 0 (default, also
+ * KLAB_DYNAMIC_SCHED=0/1): static stride, ~1 us per launch cheaper when nothing else shares the GPU.  Set before the first
+ * forward: CUDA graphs bake the choice. */
+int klab_set_dynamic_sched(int on);
 
 /* ---- K5: GEMM with fused epilogue -----------------------------------------------------------
  * Replaces every nn.Linear on the path: HF/models/swinv2/modeling_swinv2.py:535,578-579,591,385 and

@@ -56,6 +56,7 @@ SIGNATURES = {
     "klab_launch_count": [],
     "klab_set_sm_reserve": [_i],
     "klab_sm_budget": [],
+    "klab_set_dynamic_sched": [_i],
     "klab_gemm": [_vp, _i, _i, _i, _i, _vp, _ll, _i, _vp, _ll, _i, _vp, _ll, C.POINTER(GemmEpilogue)],
     "klab_gemm_simt": [_vp, _i, _i, _i, _i, _vp, _ll, _i, _vp, _ll, _i, _vp, _ll, C.POINTER(GemmEpilogue)],
     "klab_rmsnorm_fwd": [_vp, _i, _ll, _i, _vp, _ll, _vp, _f, _vp, _ll, _i, _ll, _vp],

@@ -45,14 +45,21 @@ int sm_count() {
 // zero between launches (the last CTA of a launch re-arms its slot, so CUDA graphs can replay it).  Launches take slots
 // round-robin; two launches share a slot only when SCHED_SLOTS launches apart, long after the first has finished in any
 // stream order this library produces.  Returns nullptr (= static striding) when the pool does not exist yet and cannot be
-// created because the stream is capturing, or with KLAB_STATIC_SCHED=1.
+// created because the stream is capturing, or when dynamic distribution is off -- the default on a single GPU, where the static
+// stride is ~1 us per launch cheaper; the data-parallel reducer switches it on (klab_set_dynamic_sched).
 constexpr int SCHED_SLOTS = 8192;
 static int* g_sched_base[16] = {};
 static std::atomic<unsigned> g_sched_seq{0};
 
+static std::atomic<int> g_dynamic_sched{-1};          // -1: KLAB_DYNAMIC_SCHED (default 0); 0 / 1: klab_set_dynamic_sched
+
 int* sched_slot(cudaStream_t stream) {
-    static const bool off = []() { const char* e = getenv("KLAB_STATIC_SCHED"); return e && e[0] == '1'; }();
-    if (off) return nullptr;
+    int on = g_dynamic_sched.load(std::memory_order_relaxed);
+    if (on < 0) {
+        const char* e = getenv("KLAB_DYNAMIC_SCHED");
+        on = e && e[0] == '1';
+    }
+    if (!on) return nullptr;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
     if (!g_sched_base[dev]) {
@@ -138,6 +145,10 @@ int klab_set_sm_reserve(int n_sms) {
     return KLAB_OK;
 }
 int klab_sm_budget(void) { return sm_count(); }
+int klab_set_dynamic_sched(int on) {
+    g_dynamic_sched.store(on ? 1 : 0, std::memory_order_relaxed);
+    return KLAB_OK;
+}
 
 static klab_gemm_epilogue default_epilogue(const klab_gemm_epilogue* epi, int in_dtype) {
     klab_gemm_epilogue e;

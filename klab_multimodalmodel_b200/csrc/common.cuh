@@ -107,10 +107,20 @@ __device__ __forceinline__ float warp_max(float v) {
 // It is branch free and costs one MUFU.RCP + one MUFU.EX2, which matters because the GEMM epilogue that applies it is
 // instruction-issue bound (libdevice erff is ~40 instructions with two divergent branches).  GELU' reuses the same
 // exponential: phi(x) = exp(-x^2 / 2) / sqrt(2 pi) and exp(-z^2) with z = |x| / sqrt(2) are the same number.
+__device__ __forceinline__ float rcp_approx(float x) {     // one MUFU.RCP (__frcp_rn is the ~11-instruction IEEE sequence)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {     // one MUFU.EX2
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ void gelu_terms(float x, float& half_erfc, float& u) {
     const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-    u = __expf(-z * z);
+    const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));             // argument in [1, inf): relative error ~1e-7
+    u = ex2_approx(z * z * -1.4426950408889634f);                      // exp(-z^2)
     float poly = fmaf(1.061405429f, t, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);
@@ -247,6 +257,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 26)) {
+            printf("klab: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+
+// Same, for waits with slack (a producer waiting for a free ring slot, the MMA issuer waiting for a drained accumulator): back
+// off between polls so that the polling does not take issue slots from the warps doing the work (the fused GEMM epilogues are
+// issue bound; ncu attributed ~9 % of all issued instructions of a GELU GEMM to the spin loops of two waiting threads).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(40);
+        if (++spins > (1u << 24)) {
             printf("klab: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
             __trap();
         }

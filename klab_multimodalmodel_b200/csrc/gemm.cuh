@@ -114,10 +114,13 @@ __device__ __forceinline__ void store_chunk(void* base, int dt, long long idx0, 
 }
 
 // Apply the epilogue to CH consecutive columns [col0, col0+nvalid) of output row `row` and store.
+// `aux_raw` (optional): the CH bf16 values of e.aux_in for this chunk, already fetched by the caller (software prefetch: the
+// tcgen05 kernel loads the next chunk's aux values while it works on the current one -- the dependent global load used to be
+// the largest single stall of the activation-backward epilogues).
 template <int CH>
 __device__ __forceinline__ void epilogue_apply_store(const klab_gemm_epilogue& e, const DropKey& dr, float (&v)[CH],
                                                      long long row, long long col0, int nvalid, int N,
-                                                     void* D, long long ldd) {
+                                                     void* D, long long ldd, const uint32_t* aux_raw = nullptr) {
 #pragma unroll
     for (int i = 0; i < CH; ++i) v[i] *= e.alpha;
     if (e.bias) {
@@ -143,7 +146,15 @@ __device__ __forceinline__ void epilogue_apply_store(const klab_gemm_epilogue& e
         for (int i = 0; i < CH; ++i) v[i] = gelu_erf(v[i]);
     } else if (e.act == KLAB_ACT_RELU_BWD || e.act == KLAB_ACT_GELU_BWD) {
         float a[CH];
-        load_chunk<CH>(e.aux_in, e.aux_in_dtype, row * e.ld_aux_in + col0, nvalid, a);
+        if (aux_raw) {
+#pragma unroll
+            for (int j = 0; j < CH / 2; ++j) {
+                a[2 * j] = __uint_as_float(aux_raw[j] << 16);
+                a[2 * j + 1] = __uint_as_float(aux_raw[j] & 0xffff0000u);
+            }
+        } else {
+            load_chunk<CH>(e.aux_in, e.aux_in_dtype, row * e.ld_aux_in + col0, nvalid, a);
+        }
         if (e.act == KLAB_ACT_RELU_BWD) {
 #pragma unroll
             for (int i = 0; i < CH; ++i) v[i] = a[i] > 0.0f ? v[i] : 0.0f;

@@ -171,7 +171,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 const int n0 = (tile % num_n) * BN;
                 const int kb0 = split * kps, kb1 = min(num_k, kb0 + kps);
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = ring + stage * stage_bytes;
                     uint8_t* sb = sa + A_TILE_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
@@ -217,7 +217,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
                 const int split = item % splits;
                 const int kb0 = split * kps, kb1 = min(num_k, kb0 + kps);
-                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                mbar_wait_relaxed(&tmem_empty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * ACC_STRIDE;
                 for (int kb = kb0; kb < kb1; ++kb) {
@@ -267,10 +267,22 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             const int tile = item / splits, split = item - tile * splits;
             const int m0 = (tile / num_n) * BM;
             const int n0 = (tile % num_n) * BN;
-            mbar_wait(&tmem_full_bar[acc], acc_phase);
-            tc_fence_after();
             const int r_in = sub * 32 + lane;
             const long long row = static_cast<long long>(m0) + r_in;
+            // Activation-backward epilogues read one bf16 value per output element (the saved pre-activation).  The dependent
+            // global load was the largest single stall of those GEMMs: the first chunk is fetched before the accumulator
+            // barrier, later ones one iteration ahead.
+            bool pf = false;
+            const __nv_bfloat16* aux_row = nullptr;
+            uint32_t a_nxt[CH / 2];
+            if constexpr (EPI == EPI_STORE) {
+                pf = splits == 1 && epi.aux_in != nullptr && epi.aux_in_dtype == KLAB_BF16 && row < M && (epi.ld_aux_in & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(epi.aux_in) & 31) == 0 && (n0 & 15) == 0 && n0 + BN <= N;
+                aux_row = reinterpret_cast<const __nv_bfloat16*>(epi.aux_in) + row * epi.ld_aux_in + n0;
+                if (pf && quarter < nchunks) ld_global_v8(aux_row + quarter * CH, a_nxt);
+            }
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(sub * 32) << 16) + acc * ACC_STRIDE;
             if constexpr (EPI == EPI_CE_FWD) {
                 const long long lab = row < M ? ce.labels[row] - ce.col_offset : -1;
@@ -336,6 +348,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 for (int c = quarter; c < nchunks; c += 4) {
                     uint32_t r[CH];
                     tmem_ld_32x16(t_row + c * CH, r);
+                    uint32_t a_cur[CH / 2];
+#pragma unroll
+                    for (int i = 0; i < CH / 2; ++i) a_cur[i] = a_nxt[i];
+                    if (pf && c + 4 < nchunks) ld_global_v8(aux_row + (c + 4) * CH, a_nxt);
                     tmem_ld_wait();
                     const int col0 = n0 + c * CH;
                     const int nvalid = min(CH, N - col0);
@@ -343,7 +359,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                         float v[CH];
 #pragma unroll
                         for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
-                        epilogue_apply_store<CH>(epi, dr, v, row, col0, nvalid, N, D, ldd);
+                        epilogue_apply_store<CH>(epi, dr, v, row, col0, nvalid, N, D, ldd, pf ? a_cur : nullptr);
                     }
                 }
                 tc_fence_before();

@@ -62,6 +62,7 @@ class MyModel(nn.Module):
                 # kernels keep static contiguous shares (head affinity) and leave the collective's SMs free instead -- a 200 KB
                 # CTA cannot share an SM with an NCCL CTA, and a CTA that starts a wave late doubles the kernel's time.
                 L.lib().klab_set_sm_reserve(int(os.environ.get("KLAB_SM_RESERVE", os.environ.get("NCCL_MAX_CTAS", "16"))))
+                L.lib().klab_set_dynamic_sched(int(os.environ.get("KLAB_DYNAMIC_SCHED", "1")))
         return [n for n, _ in named]
 
     def _concat_embeddings(self, images, source_encoding):
