@@ -490,3 +490,65 @@ def test_fused_lmhead_cross_entropy(rows, V, d):
     o.lmhead_ce_fwd(h, E, alpha, bad)
     with pytest.raises(IndexError):
         o.check_err_flag(h.device)
+
+
+# ------------------------------------------------------------------------------------------------ dynamic work distribution
+def test_dynamic_work_distribution_matches_static():
+    """klab_set_dynamic_sched(1) (what the data-parallel reducer arms): the persistent GEMM and T5-attention kernels claim
+    work items from a per-launch counter.  Results must be bit-identical to the static stride, also when a launch has many
+    more items than CTAs, uses split-K, is replayed from a CUDA graph (the last CTA re-arms the counter) and when far more
+    launches than counter slots have been issued."""
+    o, lib = ops(), L()
+    dev = "cuda"
+
+    def run_all():
+        outs = []
+        for (M, N, K, a_mn, b_mn, od) in [(4096, 2048, 256, False, False, torch.bfloat16), (1000, 520, 136, False, True, torch.bfloat16),
+                                          (512, 384, 4096, True, True, torch.float32), (20000, 128, 64, False, False, torch.bfloat16)]:
+            A, _ = rnd(K if a_mn else M, M if a_mn else K, dtype=torch.bfloat16, seed=M)
+            B, _ = rnd(K if b_mn else N, N if b_mn else K, dtype=torch.bfloat16, seed=N)
+            outs.append(o.gemm(A, B, M, N, K, a_mn=a_mn, b_mn=b_mn, out_dtype=od))
+        Bt, H, Lq, dk = 40, 8, 32, 64                      # 320 problems > 148 CTAs
+        QKV, _ = rnd(Bt * Lq, 3 * H * dk, dtype=torch.bfloat16, seed=7, scale=0.5)
+        q, k, v = QKV[:, :H * dk], QKV[:, H * dk:2 * H * dk], QKV[:, 2 * H * dk:]
+        table = (0.5 * torch.randn(32, H, generator=torch.Generator().manual_seed(3))).cuda()
+        lut, rz = o.t5_rel_bucket_lut(Lq, Lq, bidirectional=False, num_buckets=32, max_distance=128)
+        kw = dict(bias_table=table, lut=lut.cuda(), rel_zero=rz, causal=True)
+        ctx, lse = o.t5_attention_fwd(q, k, v, Bt, H, Lq, Lq, dk, **kw)
+        DO, _ = rnd(Bt * Lq, H * dk, dtype=torch.bfloat16, seed=8)
+        dQKV = torch.zeros_like(QKV)
+        dtab = torch.zeros_like(table)
+        o.t5_attention_bwd(q, k, v, ctx, DO, lse, dQKV[:, :H * dk], dQKV[:, H * dk:2 * H * dk], dQKV[:, 2 * H * dk:], Bt, H, Lq, Lq, dk,
+                           dbias_table=dtab, **kw)
+        return outs + [ctx, lse, dQKV, dtab]
+
+    static = run_all()
+    lib.lib().klab_set_dynamic_sched(1)
+    try:
+        dyn = run_all()
+        for s_, d_ in zip(static, dyn):
+            assert torch.equal(s_, d_)
+        # graph replay: the counters must be back at zero after every launch
+        A, _ = rnd(2048, 512, dtype=torch.bfloat16, seed=11)
+        B, _ = rnd(1024, 512, dtype=torch.bfloat16, seed=12)
+        D = torch.empty(2048, 1024, dtype=torch.bfloat16, device=dev)
+        o.gemm(A, B, 2048, 1024, 512, out=D)
+        ref = D.clone()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(3):
+                o.gemm(A, B, 2048, 1024, 512, out=D)
+        for _ in range(4):
+            D.zero_()
+            g.replay()
+            assert torch.equal(D, ref)
+        # slot reuse: more launches than the 8192 counter slots
+        small_a, _ = rnd(256, 64, dtype=torch.bfloat16, seed=13)
+        small_b, _ = rnd(128, 64, dtype=torch.bfloat16, seed=14)
+        first = o.gemm(small_a, small_b, 256, 128, 64)
+        for _ in range(9000):
+            last = o.gemm(small_a, small_b, 256, 128, 64)
+        assert torch.equal(first, last)
+    finally:
+        lib.lib().klab_set_dynamic_sched(0)
