@@ -2,8 +2,12 @@
 the reference relies on (HF/generation/utils.py:765-804,2658-2800): greedy, 20 new tokens, start id 0, EOS 1, pad 0, finished
 rows keep emitting pad, stop as soon as every row has finished.
 
-This first version re-runs the decoder on the whole prefix every step (same arithmetic as HF's KV cache, O(T^2) work for
-T <= 20); the cached single-token path reuses the same kernels with q_offset and is the next step.
+`greedy_generate` is the cached single-token path (HF/models/t5/modeling_t5.py:281-305, HF/cache_utils.py): per
+decoder block the self-attention keys / values of the tokens emitted so far live in a preallocated [B, T_max, 3*inner] buffer
+-- the q|k|v GEMM of step t writes row (b, t) of it directly through its output row stride, so "growing the cache" costs no
+copy at all (HF re-allocates it with torch.cat every step) -- and the cross-attention keys / values of the encoder output are
+projected once before the loop.  Every step is one token per sample: O(T) work instead of the O(T^2) of re-running the prefix.
+`greedy_generate_recompute` is that older prefix-recompute schedule, kept as a cross-check (identical ids; tests).
 """
 from __future__ import annotations
 
@@ -16,6 +20,60 @@ from . import ops as O
 
 @torch.no_grad()
 def greedy_generate(tr, embeds, B, Le, max_new_tokens: int = 20):
+    cfg = tr.config
+    cd = embeds.dtype
+    dev = embeds.device
+    dec = tr.decoder
+    H, dk, d, eps = cfg.num_heads, cfg.d_kv, cfg.d_model, cfg.layer_norm_epsilon
+    inner = H * dk
+    nb = cfg.relative_attention_num_buckets
+    T = max_new_tokens                                                   # decoder positions 0 .. T-1 are ever attended to
+    enc = tr.encoder.run_blocks(embeds, B, Le, tr.cache)
+    enc, _ = O.rmsnorm_fwd(enc, tr.encoder.final_layer_norm.weight, eps, save_stats=False)
+    tab = tr.cache.get([tr.shared.weight], cd)
+    V = tr.shared.weight.shape[0]
+    table = dec.block[0].layer[0].SelfAttention.relative_attention_bias.weight.detach()
+    lut, rz = dec.lut(T, dev)                                            # covers relative positions -(T-1) .. T-1
+    layers = []
+    for blk in dec.block:
+        ln0, q, k, v, o, ln1, cq, ck, cv, co, ln2, wi, wo = blk.flat_params()
+        g = tr.cache.get
+        cross_kv = O.linear_fwd(enc, g([ck, cv], cd))                    # [B*Le, 2*inner], once (modeling_t5.py:291-299)
+        self_qkv = torch.zeros(B * T, 3 * inner, dtype=cd, device=dev)   # row (b, t): q | k | v of token t of sample b
+        layers.append((ln0.detach(), g([q, k, v], cd), g([o], cd), ln1.detach(), g([cq], cd), g([co], cd), ln2.detach(), g([wi], cd),
+                       g([wo], cd), cross_kv, self_qkv))
+    ids = torch.full((B, T + 1), cfg.pad_token_id, dtype=torch.int64, device=dev)
+    ids[:, 0] = cfg.decoder_start_token_id
+    unfinished = torch.ones(B, dtype=torch.int32, device=dev)
+    n_out = 1
+    for t in range(T):
+        x = O.embedding_fwd(ids[:, t:t + 1].contiguous(), tab)          # [B, d]
+        for (ln0, wqkv, w_o, ln1, w_cq, w_co, ln2, w_i, w_ff, cross_kv, self_qkv) in layers:
+            n0, _ = O.rmsnorm_fwd(x, ln0, eps, save_stats=False)
+            row_t = self_qkv.view(B, T, 3 * inner)[:, t]                 # [B, 3*inner] view, row stride T*3*inner
+            O.linear_fwd(n0, wqkv, out=row_t)                            # q | k | v of the new token, written into the cache
+            ctx, _ = O.t5_attention_fwd(row_t[:, :inner], self_qkv[:, inner:2 * inner], self_qkv[:, 2 * inner:], B, H, 1, T, dk,
+                                        bias_table=table, lut=lut, rel_zero=rz, num_buckets=nb, causal=True, q_offset=t)
+            h1 = O.linear_fwd(ctx, w_o, residual=x)
+            n1, _ = O.rmsnorm_fwd(h1, ln1, eps, save_stats=False)
+            qc = O.linear_fwd(n1, w_cq)
+            ctx2, _ = O.t5_attention_fwd(qc, cross_kv[:, :inner], cross_kv[:, inner:], B, H, 1, Le, dk)
+            h2 = O.linear_fwd(ctx2, w_co, residual=h1)
+            n2, _ = O.rmsnorm_fwd(h2, ln2, eps, save_stats=False)
+            f = O.linear_fwd(n2, w_i, act=L.ACT_RELU)
+            x = O.linear_fwd(f, w_ff, residual=h2)
+        n, _ = O.rmsnorm_fwd(x, dec.final_layer_norm.weight, eps, save_stats=False)
+        logits = O.linear_fwd(n, tab, alpha=d ** -0.5, out_dtype=torch.float32)
+        L.check(L.lib().klab_greedy_step(torch.cuda.current_stream().cuda_stream, B, V, logits.data_ptr(), logits.stride(0),
+                                         ids.data_ptr(), ids.stride(0), t + 1, unfinished.data_ptr(), cfg.pad_token_id, cfg.eos_token_id))
+        n_out = t + 2
+        if not bool(unfinished.cpu().any()):                           # HF checks the stopping criteria every step too
+            break
+    return ids[:, :n_out]
+
+
+@torch.no_grad()
+def greedy_generate_recompute(tr, embeds, B, Le, max_new_tokens: int = 20):
     cfg = tr.config
     cd = embeds.dtype
     dev = embeds.device
