@@ -36,6 +36,7 @@ struct TcArgs {
     unsigned long long seed;
     const unsigned long long* seed_ptr;
     int* sched;                // dynamic work distribution of the persistent kernels ({next problem, finished CTAs}) or null
+    int pack;                  // single-tile kernels: G = 128 / L problems (consecutive batch entries of one head) share one tile; 1 = off
 };
 
 // byte offset of element (row, col) inside a [rows x 64] bf16 tile stored with the 128-byte swizzle (TMA SWIZZLE_128B /
@@ -485,7 +486,12 @@ __global__ void __launch_bounds__(128) t5_attn_bwd_tc_kernel(const __grid_consta
 //   * the operands of problem i+1 are fetched by TMA into a second buffer set while problem i computes;
 //   * every SIMT phase is spread over 16 warps: 4 threads per query row (TMEM lane), 32 keys each; row statistics are
 //     combined through shared memory;
-//   * backward takes D_i = sum_j P~_ij dP_ij from the same P~ and dP that form dS (no dO . O re-read, exact cancellation).
+//   * backward takes D_i = sum_j P~_ij dP_ij from the same P~ and dP that form dS (no dO . O re-read, exact cancellation);
+//   * short self-attention problems are PACKED: with Lq = Lk = L in {32, 64} (decoder self-attention, the frozen text encoder)
+//     a 128-row tile holds the G = 128 / L problems of consecutive batch entries of one head -- the TMA box already spans
+//     them, the rows are contiguous in the projection output -- and S = Q K^T is used block-diagonally: row r belongs to
+//     problem r / L, keys of other problems get P = dS = 0 exactly, so P V, dV, dK, dQ and the diagonal sums of the bias
+//     gradient come out right without further masking.  A 32 x 32 problem used to pay for a whole 128 x 128 tile.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int ST_THREADS = 512;
 
@@ -509,7 +515,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_fwd_tc1_kernel(const __
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int r = (warp & 3) * 32 + lane, cq = warp >> 2;       // TMEM lane = query row; key quarter
-    const int Lq = a.Lq, Lk = a.Lk, nprob = a.B * a.H;
+    const int Lq = a.Lq, Lk = a.Lk;
+    const int G = a.pack;                                   // problems per tile (1: one problem, rows = queries)
+    const int nprob = ((a.B + G - 1) / G) * a.H;            // work items: (batch group, head)
     constexpr int O_COL = 128;
 
     if (tid == 0) {
@@ -535,7 +543,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_fwd_tc1_kernel(const __
     const int nks = lk_pad / 16;
 
     auto issue_loads = [&](int bh, int buf) {
-        const int b = bh / a.H, h = bh - b * a.H;
+        const int bg = bh / a.H, h = bh - bg * a.H, b = bg * G;
         uint8_t* base = sIn + buf * 3 * T;
         mbar_arrive_expect_tx(&bars[buf], 3 * T);
         tma_load_2d(base, &tmq, &bars[buf], h * DK, b * Lq);
@@ -562,7 +570,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_fwd_tc1_kernel(const __
     int it = 0;
     for (int bh = s_bh[0]; bh < nprob; ++it) {
         const int buf = it & 1;
-        const int h = bh % a.H, b = bh / a.H;
+        const int h = bh % a.H, b = (bh / a.H) * G;           // b: first batch entry of the tile
         uint8_t* sQ = sIn + buf * 3 * T;
         uint8_t* sK = sQ + T;
         uint8_t* sV = sK + T;
@@ -595,11 +603,17 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_fwd_tc1_kernel(const __
         mma_phase ^= 1;
         tc_fence_after();
 
-        const int i = r;
+        // row r of the tile = query i of sub-problem `sub` (packed) or query r of the only problem
+        const int sub = G > 1 ? r / Lq : 0;
+        const int i = r - sub * Lq;
+        const bool row_ok = G > 1 ? b + sub < a.B : i < Lq;
+        const long long bh_row = static_cast<long long>(b + sub) * a.H + h;
         const int jmax = a.causal ? min(Lk, i + a.q_offset + 1) : Lk;
-        const int j0 = cq * 32;
-        const float* br = brel + (Lq - 1 - i) + j0;
-        const bool bias_on = has_bias && i < Lq;
+        const int j0 = cq * 32;                            // first of this thread's 32 keys (tile column)
+        const bool own = G == 1 || j0 / Lk == sub;         // the 32 keys lie inside one problem (Lk is 32 or 64 when packed)
+        const int jb = j0 - sub * Lk;                      // ... at key index jb of it
+        const float* br = brel + (Lq - 1 - i) + jb;
+        const bool bias_on = has_bias && row_ok && own;
         const bool active = j0 < lk_pad;                   // warp-uniform
         float sv[32];
         float mx = -INFINITY;
@@ -611,9 +625,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_fwd_tc1_kernel(const __
                 tmem_ld_wait();
 #pragma unroll
                 for (int t = 0; t < 16; ++t) {
-                    const int j = j0 + hf * 16 + t;
+                    const int j = jb + hf * 16 + t;
                     float sc = -INFINITY;
-                    if (j < jmax) {
+                    if (own && j < jmax) {
                         sc = __uint_as_float(rr[t]) + (bias_on ? br[hf * 16 + t] : 0.0f);
                         mx = fmaxf(mx, sc);
                     }
@@ -627,14 +641,14 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_fwd_tc1_kernel(const __
         __syncthreads();                                   // sred is reused for the sums
         float sum = 0.0f;
         if (active) {
-            const uint64_t base = (static_cast<uint64_t>(bh) * Lq + i) * Lk + j0;
+            const uint64_t base = (static_cast<uint64_t>(bh_row) * Lq + i) * Lk + jb;
 #pragma unroll
             for (int t = 0; t < 32; ++t) {
                 const float e = sv[t] > -INFINITY ? __expf(sv[t] - mx) : 0.0f;
                 sum += e;
                 sv[t] = e;
             }
-            if (dkey.on && i < Lq) dropout_apply_run<32>(dkey, base, sv);     // elements past jmax are zero already
+            if (dkey.on && row_ok && own) dropout_apply_run<32>(dkey, base, sv);     // elements past jmax are zero already
             uint8_t* blk = sP + (j0 >> 6) * T;
             st_tile16(blk, r, (j0 & 63) >> 4, sv);
             st_tile16(blk, r, ((j0 & 63) >> 4) + 1, sv + 16);
@@ -659,9 +673,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_fwd_tc1_kernel(const __
             uint32_t ro[32];
             tmem_ld_32x32(trow + O_COL + cq * 32, ro);
             tmem_ld_wait();
-            if (i < Lq) {
+            if (row_ok) {
                 const float inv = 1.0f / sum;
-                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + (static_cast<long long>(b) * Lq + i) * a.ldo + h * DK + cq * 32;
+                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + (static_cast<long long>(b) * Lq + r) * a.ldo + h * DK + cq * 32;
 #pragma unroll
                 for (int gq = 0; gq < 4; ++gq) {
                     uint4 q;
@@ -672,8 +686,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_fwd_tc1_kernel(const __
                     reinterpret_cast<uint4*>(op)[gq] = q;
                 }
             }
-        } else if (cq == 2 && i < Lq) {
-            a.lse[static_cast<long long>(bh) * Lq + i] = mx + __logf(sum);
+        } else if (cq == 2 && row_ok) {
+            a.lse[bh_row * Lq + i] = mx + __logf(sum);
         }
         tc_fence_before();
         __syncthreads();                                   // TMEM, sP, brel, sred are reused by the next problem
@@ -711,7 +725,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_bwd_tc1_kernel(const __
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int r = (warp & 3) * 32 + lane, cq = warp >> 2;
-    const int Lq = a.Lq, Lk = a.Lk, nprob = a.B * a.H;
+    const int Lq = a.Lq, Lk = a.Lk;
+    const int G = a.pack;                                   // problems per tile (see the forward kernel)
+    const int nprob = ((a.B + G - 1) / G) * a.H;
 
     if (tid == 0) {
         mbar_init(&bars[0], 1);
@@ -740,7 +756,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_bwd_tc1_kernel(const __
     const bool has_bias = a.bias_table != nullptr;
 
     auto issue_loads = [&](int bh, int buf) {
-        const int b = bh / a.H, h = bh - b * a.H;
+        const int bg = bh / a.H, h = bh - bg * a.H, b = bg * G;
         uint8_t* base = sIn + buf * 4 * T;
         mbar_arrive_expect_tx(&bars[buf], 4 * T);
         tma_load_2d(base, &tmq, &bars[buf], h * DK, b * Lq);
@@ -766,7 +782,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_bwd_tc1_kernel(const __
     int it = 0;
     for (int bh = s_bh[0]; bh < nprob; ++it) {
         const int buf = it & 1;
-        const int h = bh % a.H, b = bh / a.H;
+        const int h = bh % a.H, b = (bh / a.H) * G;           // b: first batch entry of the tile
         uint8_t* sQ = sIn + buf * 4 * T;
         uint8_t* sdO = sQ + T;
         uint8_t* sK = sdO + T;
@@ -787,9 +803,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_bwd_tc1_kernel(const __
             drel[tid] = 0.0f;
         }
         if (tid < 64) bins[tid] = 0.0f;
-        const int i = r;
-        const bool row_ok = i < Lq;
-        const float lse = row_ok ? a.lse[static_cast<long long>(bh) * Lq + i] : 0.0f;
+        const int sub = G > 1 ? r / Lq : 0;                   // row r = query i of sub-problem `sub`
+        const int i = r - sub * Lq;
+        const bool row_ok = G > 1 ? b + sub < a.B : i < Lq;
+        const long long bh_row = static_cast<long long>(b + sub) * a.H + h;
+        const float lse = row_ok ? a.lse[bh_row * Lq + i] : 0.0f;
         if (tid == 0) {
             mbar_wait(&bars[buf], (it >> 1) & 1);
             tc_fence_after();
@@ -807,9 +825,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_bwd_tc1_kernel(const __
         mma_phase ^= 1;
         tc_fence_after();
 
-        const int jmax = a.causal ? min(Lk, i + a.q_offset + 1) : Lk;
-        const int j0 = cq * 32;
-        const float* br = brel + (Lq - 1 - i) + j0;
+        const int j0 = cq * 32;                            // first of this thread's 32 keys (tile column)
+        const bool own = G == 1 || j0 / Lk == sub;         // they lie inside one problem (Lk is 32 or 64 when packed) ...
+        const int jb = j0 - sub * Lk;                      // ... at key index jb of it
+        const int jmax = own ? (a.causal ? min(Lk, i + a.q_offset + 1) : Lk) : -(1 << 30);      // foreign keys: P = dS = 0
+        const float* br = brel + (Lq - 1 - i) + jb;
         const bool active = j0 < lk_pad;                   // warp-uniform
         // pass 1: P~ = P * dropout multiplier (what the forward multiplied into V) and the partial D_i = sum_j P~_ij dP_ij
         uint32_t keep = 0xFFFFFFFFu;                       // dropout keep bits of the 32 keys
@@ -819,7 +839,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_bwd_tc1_kernel(const __
         float Dp = 0.0f;
         if (active) {
             if (dkey.on) {
-                const uint64_t base = (static_cast<uint64_t>(bh) * Lq + i) * Lk + j0;
+                const uint64_t base = (static_cast<uint64_t>(bh_row) * Lq + i) * Lk + (own ? jb : 0);
                 keep = 0;
                 if ((base & 1) == 0) {
 #pragma unroll
@@ -842,7 +862,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_bwd_tc1_kernel(const __
                 float pm[16];                              // P~
 #pragma unroll
                 for (int t = 0; t < 16; ++t) {
-                    const int j = j0 + hf * 16 + t;
+                    const int j = jb + hf * 16 + t;
                     float p = 0.0f;
                     if (row_ok && j < jmax) {
                         p = __expf(__uint_as_float(rs[t]) + (has_bias ? br[hf * 16 + t] : 0.0f) - lse);
@@ -869,7 +889,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_bwd_tc1_kernel(const __
                 tmem_ld_wait();
 #pragma unroll
                 for (int t = 0; t < 16; ++t) {
-                    const int j = j0 + hf * 16 + t;
+                    const int j = jb + hf * 16 + t;
                     float ds = 0.0f;
                     if (row_ok && j < jmax) {
                         const bool kept = (keep >> (hf * 16 + t)) & 1u;
@@ -903,7 +923,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_bwd_tc1_kernel(const __
         // At a fixed row the lanes of a warp read consecutive bf16 of that row (no bank conflicts).
         if (has_bias && tid < 2 * TILE - 1) {
             const int dd = tid;                               // j - i + 127
-            const int lo = max(0, TILE - 1 - dd), hi = min(min(TILE - 1, 2 * TILE - 2 - dd), Lq - 1);
+            const int lo = max(0, TILE - 1 - dd), hi = min(min(TILE - 1, 2 * TILE - 2 - dd), (G > 1 ? TILE : Lq) - 1);
             float acc = 0.0f;
             for (int il = lo; il <= hi; ++il) {
                 const int jl = il + dd - (TILE - 1);
@@ -919,6 +939,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_bwd_tc1_kernel(const __
         // write-out: warps 0-3 dq, 4-7 dk, 8-11 dv (row = TMEM lane)
         if (cq < 3) {
             const int rows = cq == 0 ? Lq : Lk;
+            const int rows_ok = G > 1 ? min(TILE, (a.B - b) * rows) : rows;      // valid rows of the tile
             const uint32_t col = cq == 0 ? TM_DQ : (cq == 1 ? TM_DK : TM_DV);
             __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(cq == 0 ? a.dq : (cq == 1 ? a.dk : a.dv));
             const long long ld = cq == 0 ? a.ldq : (cq == 1 ? a.ldk : a.ldv);
@@ -927,7 +948,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_bwd_tc1_kernel(const __
                 uint32_t ro[32];
                 tmem_ld_32x32(trow + col + c0, ro);
                 tmem_ld_wait();
-                if (r < rows) {
+                if (r < rows_ok) {
                     uint4* dst = reinterpret_cast<uint4*>(base + (static_cast<long long>(b) * rows + r) * ld + h * DK + c0);
 #pragma unroll
                     for (int gq = 0; gq < 4; ++gq) {
@@ -944,7 +965,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_bwd_tc1_kernel(const __
         tc_fence_before();
         __syncthreads();                                   // TMEM, sP / sdS, brel / bins are reused by the next problem
         tc_fence_after();
-        if (has_bias && tid < a.num_buckets) a.dbias_partial[static_cast<long long>(bh) * a.num_buckets + tid] = bins[tid];
+        // partial bias gradient of the tile: into the slot of its first (batch, head); the other packed problems' slots get zeros
+        if (has_bias && tid < a.num_buckets) {
+            for (int g = 0; g < G && b + g < a.B; ++g)
+                a.dbias_partial[(static_cast<long long>(b + g) * a.H + h) * a.num_buckets + tid] = g == 0 ? bins[tid] : 0.0f;
+        }
         bh = s_bh[buf ^ 1];
         n1 = n2;
     }
@@ -967,6 +992,14 @@ __global__ void t5_dbias_reduce_tc_kernel(const float* __restrict__ part, int B,
     dtable[idx] += s;
 }
 
+// Problems per 128-row tile of the single-tile kernels: self-attention shapes whose length divides the tile (the 32 keys a
+// thread owns must not straddle two problems, hence 32 or 64).  KLAB_T5_ATTN_PACK=0 switches packing off.
+int pack_factor(int Lq, int Lk, int q_offset) {
+    static const bool off = []() { const char* e = getenv("KLAB_T5_ATTN_PACK"); return e && e[0] == '0'; }();
+    if (off || Lq != Lk || q_offset != 0 || (Lq != 32 && Lq != 64)) return 1;
+    return TILE / Lq;
+}
+
 int make_head_map(CUtensorMap* m, const void* base, long long rows, int H, long long ld, int box_rows) {
     return make_tmap_2d_bf16(m, base, static_cast<uint64_t>(rows), static_cast<uint64_t>(H) * DK, static_cast<uint64_t>(ld), box_rows, DK);
 }
@@ -985,7 +1018,8 @@ int t5_attention_fwd_tc(cudaStream_t st, int B, int H, int Lq, int Lk, const voi
                         int rel_zero, int num_buckets, int causal, int q_offset, float* lse, float dropout_p, unsigned long long seed,
                         const unsigned long long* seed_ptr) {
     if (Lq <= TILE && Lk <= TILE && !getenv("KLAB_T5_ATTN_MULTI")) {          // persistent single-tile kernel
-        const int lkp = (Lk + 15) / 16 * 16;
+        const int pack = pack_factor(Lq, Lk, q_offset);
+        const int lkp = pack > 1 ? TILE : (Lk + 15) / 16 * 16;
         CUtensorMap tq, tk, tv;
         if (int rc = make_head_map(&tq, q, 1ll * B * Lq, H, ldq, TILE)) return rc;
         if (int rc = make_head_map(&tk, k, 1ll * B * Lk, H, ldk, TILE)) return rc;
@@ -1000,7 +1034,8 @@ int t5_attention_fwd_tc(cudaStream_t st, int B, int H, int Lq, int Lk, const voi
             KLAB_CHECK_CUDA(cudaFuncSetAttribute(t5_attn_fwd_tc1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
             set1 = true;
         }
-        const int nprob = B * H;
+        a.pack = pack;
+        const int nprob = ((B + pack - 1) / pack) * H;
         a.sched = sched_slot(st);
         const int sms = a.sched ? sm_count_physical() : sm_count();
         t5_attn_fwd_tc1_kernel<<<nprob < sms ? nprob : sms, ST_THREADS, smem1, st>>>(tq, tk, tv, a, lkp);
@@ -1058,11 +1093,12 @@ int t5_attention_bwd_tc(cudaStream_t st, int B, int H, int Lq, int Lk, const voi
             KLAB_CHECK_CUDA(cudaFuncSetAttribute(t5_attn_bwd_tc1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
             set1 = true;
         }
-        const int nprob = B * H;
+        a.pack = pack_factor(Lq, Lk, q_offset);
+        const int nprob = ((B + a.pack - 1) / a.pack) * H;
         a.sched = sched_slot(st);
         const int sms = a.sched ? sm_count_physical() : sm_count();
-        t5_attn_bwd_tc1_kernel<<<nprob < sms ? nprob : sms, ST_THREADS, smem1, st>>>(tq, tk, tv, tdo, a, (Lq + 15) / 16 * 16,
-                                                                                                   (Lk + 15) / 16 * 16);
+        t5_attn_bwd_tc1_kernel<<<nprob < sms ? nprob : sms, ST_THREADS, smem1, st>>>(tq, tk, tv, tdo, a, a.pack > 1 ? TILE : (Lq + 15) / 16 * 16,
+                                                                                                   a.pack > 1 ? TILE : (Lk + 15) / 16 * 16);
         KLAB_LAUNCH_CHECK();
         count_launch();
         if (bias_table && dbias_table) {

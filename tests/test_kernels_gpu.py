@@ -171,7 +171,9 @@ def test_norm_grouped_output():
 @pytest.mark.parametrize("mode,B,H,Lq,Lk,dk", [("enc", 2, 3, 13, 13, 64), ("dec", 2, 2, 9, 9, 64), ("cross", 2, 2, 7, 13, 64),
                                                ("enc", 1, 2, 81, 81, 16), ("dec", 1, 1, 40, 40, 32),
                                                ("enc", 2, 2, 96, 96, 64), ("enc", 1, 2, 176, 176, 64), ("dec", 2, 2, 130, 130, 64),
-                                               ("cross", 1, 2, 32, 200, 64), ("cross", 2, 1, 150, 96, 64), ("dec", 3, 2, 32, 32, 64)])
+                                               ("cross", 1, 2, 32, 200, 64), ("cross", 2, 1, 150, 96, 64), ("dec", 3, 2, 32, 32, 64),
+                                               # packed single-tile path: 128 / L problems per tile, partial last tile, both mask kinds
+                                               ("enc", 9, 2, 32, 32, 64), ("dec", 8, 3, 32, 32, 64), ("dec", 5, 3, 64, 64, 64), ("enc", 2, 2, 64, 64, 64)])
 def test_t5_attention(dtype, mode, B, H, Lq, Lk, dk):
     o = ops()
     dims = ot5.T5Dims(num_heads=H, d_kv=dk)
@@ -508,7 +510,7 @@ def test_dynamic_work_distribution_matches_static():
             A, _ = rnd(K if a_mn else M, M if a_mn else K, dtype=torch.bfloat16, seed=M)
             B, _ = rnd(K if b_mn else N, N if b_mn else K, dtype=torch.bfloat16, seed=N)
             outs.append(o.gemm(A, B, M, N, K, a_mn=a_mn, b_mn=b_mn, out_dtype=od))
-        Bt, H, Lq, dk = 40, 8, 32, 64                      # 320 problems > 148 CTAs
+        Bt, H, Lq, dk = 40, 8, 48, 64                      # 320 problems > 148 CTAs (48: not packed into shared tiles)
         QKV, _ = rnd(Bt * Lq, 3 * H * dk, dtype=torch.bfloat16, seed=7, scale=0.5)
         q, k, v = QKV[:, :H * dk], QKV[:, H * dk:2 * H * dk], QKV[:, 2 * H * dk:]
         table = (0.5 * torch.randn(32, H, generator=torch.Generator().manual_seed(3))).cuda()
