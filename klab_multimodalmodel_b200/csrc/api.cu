@@ -53,13 +53,17 @@ static std::atomic<unsigned> g_sched_seq{0};
 
 static std::atomic<int> g_dynamic_sched{-1};          // -1: KLAB_DYNAMIC_SCHED (default 0); 0 / 1: klab_set_dynamic_sched
 
-int* sched_slot(cudaStream_t stream) {
+int sched_slot_enabled() {
     int on = g_dynamic_sched.load(std::memory_order_relaxed);
     if (on < 0) {
         const char* e = getenv("KLAB_DYNAMIC_SCHED");
         on = e && e[0] == '1';
     }
-    if (!on) return nullptr;
+    return on;
+}
+
+int* sched_slot(cudaStream_t stream) {
+    if (!sched_slot_enabled()) return nullptr;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
     if (!g_sched_base[dev]) {

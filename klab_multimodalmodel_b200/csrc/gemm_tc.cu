@@ -79,7 +79,12 @@ struct CeArgs {
     int num_parts;             // fwd: partials per row = 4 * number of N tiles
 };
 
-template <bool A_MN, bool B_MN, int EPI>
+// CTA2 = true: the kernel runs as clusters of two CTAs (one TPC).  A work item is a 256 x BN output tile: CTA `rank` of the pair
+// stages its own 128 rows of A and rows [rank * BN/2, +BN/2) of the B tile, the leader issues tcgen05.mma.cta_group::2 (M = 256)
+// into the TMEM of both SMs, and each CTA runs the epilogue of its own 128 x BN half.  Per SM and k-block that is 16 KiB of A
+// plus BN * 64 B of B instead of BN * 128 B: the L2 -> SM feed, which bounds the one-CTA kernel at ~1.1 PFLOP/s, is relieved.
+// Work distribution is the static stride over pairs (the dynamic counter is a one-CTA feature).
+template <bool A_MN, bool B_MN, int EPI, bool CTA2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     void* __restrict__ D, long long ldd, int M, int N, int K, int BN, int stages, SplitK sk,
@@ -98,8 +103,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int stage_bytes = A_TILE_BYTES + BN * BK * 2;
-    const int num_m = (M + BM - 1) / BM;
+    const int BNL = CTA2 ? BN / 2 : BN;                     // B rows staged by this CTA
+    const int stage_bytes = A_TILE_BYTES + BNL * BK * 2;
+    const int rank = CTA2 ? static_cast<int>(cluster_ctarank()) : 0;
+    const int work_id = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);      // CTA (or pair) index
+    const int work_stride = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    constexpr int TM = CTA2 ? 2 * BM : BM;                  // rows of an output tile
+    const int num_m = (M + TM - 1) / TM;
     const int num_n = (N + BN - 1) / BN;
     const int num_k = (K + BK - 1) / BK;
     const int splits = sk.splits;
@@ -110,12 +120,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_b);
         for (int s = 0; s < stages; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], CTA2 ? 2 : 1);             // pair: the producer of either CTA arrives on the leader's barrier
             mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full_bar[s], 1);
-            mbar_init(&tmem_empty_bar[s], NUM_EPI_WARPS);
+            mbar_init(&tmem_empty_bar[s], (CTA2 ? 2 : 1) * NUM_EPI_WARPS);      // pair: the epilogue warps of both CTAs
         }
         for (int s = 0; s < SQ; ++s) {
             mbar_init(&sq_full[s], 1);
@@ -124,11 +134,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_ptr_smem, 512);
-        tmem_relinquish();
+        if constexpr (CTA2) {
+            tmem_alloc_2cta(tmem_ptr_smem, 512);
+            tmem_relinquish_2cta();
+        } else {
+            tmem_alloc(tmem_ptr_smem, 512);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CTA2) cluster_sync_all();                // the peer's barriers must be initialised before anyone signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
     // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail
@@ -144,7 +160,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             uint32_t phase = 0;
             int sq = 0;
             uint32_t sq_phase = 0;
-            int item = blockIdx.x;                              // first item: static, no atomic in front of the first load
+            int item = work_id;                                 // first item: static, no atomic in front of the first load
             while (true) {
                 if (sched) {                                    // publish the claimed item (or the end marker) to the consumers
                     mbar_wait(&sq_empty[sq], sq_phase ^ 1);
@@ -163,31 +179,41 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     break;
                 }
                 // claim the next item now: the atomic's round trip hides behind this item's loads
-                const int next_item = (sched ? atomicAdd(&sched[0], 1) : item) + static_cast<int>(gridDim.x);
+                const int next_item = (sched ? atomicAdd(&sched[0], 1) : item) + work_stride;
                 const int tile = item / splits, split = item - tile * splits;
                 // consecutive items share the m tile (and therefore A) while sweeping n: CTAs running side by side hit the same
                 // A rows in L2
-                const int m0 = (tile / num_n) * BM;
-                const int n0 = (tile % num_n) * BN;
+                const int m0 = (tile / num_n) * TM + rank * BM;                       // this CTA's 128 rows
+                const int n0 = (tile % num_n) * BN + rank * BNL;                      // this CTA's share of the B tile
                 const int kb0 = split * kps, kb1 = min(num_k, kb0 + kps);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait_relaxed(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = ring + stage * stage_bytes;
                     uint8_t* sb = sa + A_TILE_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+                    if constexpr (CTA2) {
+                        // both CTAs' bytes are credited to the leader's barrier (tma_load_2d_2cta); the peer only adds its arrival
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_bytes);
+                        else mbar_arrive_leader(&full_bar[stage]);
+                    } else {
+                        mbar_arrive_expect_tx(&full_bar[stage], stage_bytes);
+                    }
                     const int k0 = kb * BK;
+                    auto load = [&](void* dst, const CUtensorMap* map, int c0, int c1) {
+                        if constexpr (CTA2) tma_load_2d_2cta(dst, map, &full_bar[stage], c0, c1);
+                        else tma_load_2d(dst, map, &full_bar[stage], c0, c1);
+                    };
                     if constexpr (!A_MN) {
-                        tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);            // box {64 k, 128 m}
+                        load(sa, &tmap_a, k0, m0);                                        // box {64 k, 128 m}
                     } else {
 #pragma unroll
                         for (int i = 0; i < BM / 64; ++i)                                 // box {64 m, 64 k}
-                            tma_load_2d(sa + i * 8192, &tmap_a, &full_bar[stage], m0 + i * 64, k0);
+                            load(sa + i * 8192, &tmap_a, m0 + i * 64, k0);
                     }
                     if constexpr (!B_MN) {
-                        tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);            // box {64 k, BN n}
+                        load(sb, &tmap_b, k0, n0);                                        // box {64 k, BNL n}
                     } else {
-                        for (int i = 0; i < BN / 64; ++i)                                 // box {64 n, 64 k}
-                            tma_load_2d(sb + i * 8192, &tmap_b, &full_bar[stage], n0 + i * 64, k0);
+                        for (int i = 0; i < BNL / 64; ++i)                                // box {64 n, 64 k}
+                            load(sb + i * 8192, &tmap_b, n0 + i * 64, k0);
                     }
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
@@ -195,16 +221,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+        // ===================== MMA issuer (pair: the leader CTA only) =====================
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = umma_idesc_bf16(TM, BN, A_MN, B_MN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             int sq = 0;
             uint32_t sq_phase = 0;
-            int item = blockIdx.x;
+            int item = work_id;
             while (true) {
                 if (sched) {
                     mbar_wait(&sq_full[sq], sq_phase);
@@ -231,14 +257,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                                  : umma_smem_desc_sw128(sa + k * 32, 16, 1024);
                         const uint64_t db = B_MN ? umma_smem_desc_sw128(sb + k * 2048, 8192, 1024)
                                                  : umma_smem_desc_sw128(sb + k * 32, 16, 1024);
-                        umma_bf16(d_tmem, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                        if constexpr (CTA2) umma_bf16_2cta(d_tmem, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+                        else umma_bf16(d_tmem, da, db, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);           // frees the smem slot once these MMAs retire
+                    // frees the smem slot (in both CTAs of a pair) once these MMAs retire
+                    if constexpr (CTA2) umma_commit_2cta(&empty_bar[stage]);
+                    else umma_commit(&empty_bar[stage]);
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full_bar[acc]);             // accumulator complete -> epilogue
+                // accumulator complete -> epilogue (of both CTAs)
+                if constexpr (CTA2) umma_commit_2cta(&tmem_full_bar[acc]);
+                else umma_commit(&tmem_full_bar[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-                if (!sched) item += gridDim.x;
+                if (!sched) item += work_stride;
             }
         }
     } else {
@@ -248,11 +279,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         if (epi.dropout_p > 0.0f && epi.dropout_seed_ptr) epi.dropout_seed += *epi.dropout_seed_ptr;
         const DropKey dr = make_drop_key(epi.dropout_seed, epi.dropout_p);
         const int nchunks = BN / CH;
+        auto arrive_tmem_empty = [&](uint64_t* bar) {          // pair: the MMA issuer lives in the leader CTA
+            if constexpr (CTA2) mbar_arrive_leader(bar);
+            else mbar_arrive(bar);
+        };
         int acc = 0;
         uint32_t acc_phase = 0;
         int sq = 0;
         uint32_t sq_phase = 0;
-        int item = blockIdx.x;
+        int item = work_id;
         while (true) {
             if (sched) {
                 mbar_wait(&sq_full[sq], sq_phase);
@@ -265,7 +300,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 break;
             }
             const int tile = item / splits, split = item - tile * splits;
-            const int m0 = (tile / num_n) * BM;
+            const int m0 = (tile / num_n) * TM + rank * BM;
             const int n0 = (tile % num_n) * BN;
             const int r_in = sub * 32 + lane;
             const long long row = static_cast<long long>(m0) + r_in;
@@ -319,7 +354,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (row < M) ce.partials[row * ce.num_parts + (tile % num_n) * 4 + quarter] = make_float2(m_run, s_run);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                if (lane == 0) arrive_tmem_empty(&tmem_empty_bar[acc]);
             } else if constexpr (EPI == EPI_CE_BWD) {
                 const long long lab_raw = row < M ? ce.labels[row] : -100;
                 const long long lab = lab_raw - ce.col_offset;
@@ -342,7 +377,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                if (lane == 0) arrive_tmem_empty(&tmem_empty_bar[acc]);
             } else if (splits == 1) {
 #pragma unroll 1
                 for (int c = quarter; c < nchunks; c += 4) {
@@ -364,7 +399,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                if (lane == 0) arrive_tmem_empty(&tmem_empty_bar[acc]);
             } else {
                 // split-K: park the partial tile; splitk_reduce_kernel finishes the job
                 float* part = sk.ws + split * sk.split_stride + row * sk.n_pad + n0;
@@ -381,18 +416,20 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                if (lane == 0) arrive_tmem_empty(&tmem_empty_bar[acc]);
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-            if (!sched) item += gridDim.x;
+            if (!sched) item += work_stride;
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (CTA2) cluster_sync_all();                // the leader's MMAs read the peer's shared memory until the very end
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if constexpr (CTA2) tmem_dealloc_2cta(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -454,9 +491,14 @@ Workspace* get_workspace(cudaStream_t stream) {
     return &w;
 }
 
-int stages_for(int bn) {
-    const int s = RING_BYTES / (A_TILE_BYTES + bn * BK * 2);
+int stages_for(int bn_local) {                                // bn_local: B rows staged per CTA (BN, or BN / 2 in a CTA pair)
+    const int s = RING_BYTES / (A_TILE_BYTES + bn_local * BK * 2);
     return s > MAX_STAGES ? MAX_STAGES : s;
+}
+
+bool cta_pairs_enabled() {
+    static const bool on = []() { const char* e = getenv("KLAB_GEMM_CTA2"); return !(e && e[0] == '0'); }();
+    return on;
 }
 
 // Epilogue cost in instructions per output element (issue-bound estimate), see pick_config.
@@ -480,36 +522,46 @@ double epilogue_instr(const klab_gemm_epilogue& e) {
 //   epilogue: 128 * BN * instr / (96 thread-instructions per clock per SM); it overlaps the next tile's MMAs, so a CTA pays
 //   max(mainloop, epilogue) per tile plus ~2.5 us of fill / drain once;
 //   split-K adds the partial round trip through L2 (write + read by the last CTA).
-void pick_config(int M, int N, int K, bool b_mn, bool can_split, size_t ws_bytes, const klab_gemm_epilogue& epi, int* bn_out,
-                 int* splits_out) {
+// `pair_ok`: the CTA-pair kernel may be used (static work distribution, M large enough); it halves the B bytes each SM pulls
+// per k-block but works on 256-row tiles handed to 74 pairs, so it loses where the tile count quantises badly.
+void pick_config(int M, int N, int K, bool b_mn, bool can_split, bool pair_ok, size_t ws_bytes, const klab_gemm_epilogue& epi, int* bn_out,
+                 int* splits_out, int* cta2_out) {
     const int sms = sm_count_physical();
-    const int num_m = (M + BM - 1) / BM, num_k = (K + BK - 1) / BK;
+    const int num_k = (K + BK - 1) / BK;
     const double instr = epilogue_instr(epi);
     double best = 1e30;
     *bn_out = b_mn ? 64 : 16;
     *splits_out = 1;
+    *cta2_out = 0;
     const int step = b_mn ? 64 : 16;
-    for (int bn = 256; bn >= step; bn -= step) {
-        const int num_n = (N + bn - 1) / bn;
-        if (num_n > 1 && bn < 64) break;                       // tiles narrower than 64 only when one tile covers N
-        const long long tiles = 1ll * num_m * num_n;
-        const double t_epi = 128.0 * bn * instr / 96.0 / 1965.0;                 // us per tile
-        for (int s = 1; s <= (can_split ? 128 : 1); s *= 2) {
-            if (s > 1 && (num_k / s < 2 || static_cast<size_t>(tiles) * s * BM * bn * 4 > ws_bytes)) break;
-            const int kps = (num_k + s - 1) / s;
-            const long long items = tiles * s;
-            const long long waves = (items + sms - 1) / sms;
-            const double active = items < sms ? double(items) : double(sms);
-            double rate = 12.4e6 / active;                                       // bytes per us per SM
-            if (rate > 100e3) rate = 100e3;                                      // one SM pulls at most ~100 GB/s through TMA
-            const double t_k = fmax(bn / 256.0 * 0.26, (A_TILE_BYTES + bn * 128.0) / rate);
-            const double t_main = kps * t_k;
-            double t = waves * fmax(t_main, s > 1 ? 0.5 : t_epi) + 4.0 + (s > 1 ? 0.0 : fmin(t_epi, 1.5));
-            if (s > 1) {
-                const double bytes = double(tiles) * s * BM * bn * 4.0;
-                t += 3.0 + 2.0 * bytes / 5.0e6;                                  // reduce kernel: launch + partials out and back
+    for (int pair = 0; pair <= (pair_ok ? 1 : 0); ++pair) {
+        const int tm = pair ? 2 * BM : BM;
+        const int units = pair ? sms / 2 : sms;                                  // CTAs or CTA pairs working in parallel
+        const int num_m = (M + tm - 1) / tm;
+        for (int bn = 256; bn >= step; bn -= step) {
+            if (pair && bn % (2 * step) != 0) continue;                          // each CTA of a pair stages BN / 2 rows of B
+            const int num_n = (N + bn - 1) / bn;
+            if (num_n > 1 && bn < 64) break;                   // tiles narrower than 64 only when one tile covers N
+            const long long tiles = 1ll * num_m * num_n;
+            const double t_epi = 128.0 * bn * instr / 96.0 / 1965.0;             // us per tile (each CTA finishes its own 128 rows)
+            for (int s = 1; s <= (can_split ? 128 : 1); s *= 2) {
+                if (s > 1 && (num_k / s < 2 || static_cast<size_t>(tiles) * s * tm * bn * 4 > ws_bytes)) break;
+                const int kps = (num_k + s - 1) / s;
+                const long long items = tiles * s;
+                const long long waves = (items + units - 1) / units;
+                const double active = (items < units ? double(items) : double(units)) * (pair ? 2.0 : 1.0);    // SMs pulling operands
+                double rate = 12.4e6 / active;                                   // bytes per us per SM
+                if (rate > 100e3) rate = 100e3;                                  // one SM pulls at most ~100 GB/s through TMA
+                const double b_bytes = pair ? bn * 64.0 : bn * 128.0;
+                const double t_k = fmax(bn / 256.0 * 0.26, (A_TILE_BYTES + b_bytes) / rate);
+                const double t_main = kps * t_k;
+                double t = waves * fmax(t_main, s > 1 ? 0.5 : t_epi) + (pair ? 4.5 : 4.0) + (s > 1 ? 0.0 : fmin(t_epi, 1.5));
+                if (s > 1) {
+                    const double bytes = double(tiles) * s * tm * bn * 4.0;
+                    t += 3.0 + 2.0 * bytes / 5.0e6;                              // reduce kernel: launch + partials out and back
+                }
+                if (t < best * 0.97) { best = t; *bn_out = bn; *splits_out = s; *cta2_out = pair; }   // prefer wider tiles on near ties
             }
-            if (t < best * 0.97) { best = t; *bn_out = bn; *splits_out = s; }   // prefer wider tiles on near ties (less L2 traffic)
         }
     }
     if (*splits_out > 1) {                                                       // no empty K ranges
@@ -518,9 +570,11 @@ void pick_config(int M, int N, int K, bool b_mn, bool can_split, size_t ws_bytes
     }
 }
 
-template <bool A_MN, bool B_MN, int EPI = EPI_STORE>
+template <bool A_MN, bool B_MN, int EPI = EPI_STORE, bool CTA2 = false>
 int launch_cfg(cudaStream_t stream, int M, int N, int K, int bn, int splits, Workspace* w, const void* A, long long lda, const void* B,
                long long ldb, void* D, long long ldd, const klab_gemm_epilogue& epi, const CeArgs& ce = CeArgs{}) {
+    constexpr int TM = CTA2 ? 2 * BM : BM;
+    const int bnl = CTA2 ? bn / 2 : bn;
     CUtensorMap ta, tb;
     int rc;
     // A: K-major -> tensor [M rows, K cols], box [128, 64];  MN-major -> tensor [K rows, M cols], box [64, 64]
@@ -528,37 +582,49 @@ int launch_cfg(cudaStream_t stream, int M, int N, int K, int bn, int splits, Wor
               : make_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, 64);
     if (rc) return rc;
     rc = B_MN ? make_tmap_2d_bf16(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, 64)
-              : make_tmap_2d_bf16(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, bn, 64);
+              : make_tmap_2d_bf16(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, bnl, 64);
     if (rc) return rc;
-    auto kern = gemm_bf16_tc_kernel<A_MN, B_MN, EPI>;
+    auto kern = gemm_bf16_tc_kernel<A_MN, B_MN, EPI, CTA2>;
     static bool attr_set = false;   // per instantiation
     if (!attr_set) {
         KLAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
-    const int tiles = ((M + BM - 1) / BM) * ((N + bn - 1) / bn);
+    const int tiles = ((M + TM - 1) / TM) * ((N + bn - 1) / bn);
     SplitK sk{nullptr, 0, 0, splits};
     if (splits > 1) {
-        const long long m_pad = 1ll * ((M + BM - 1) / BM) * BM, n_pad = 1ll * ((N + bn - 1) / bn) * bn;
+        const long long m_pad = 1ll * ((M + TM - 1) / TM) * TM, n_pad = 1ll * ((N + bn - 1) / bn) * bn;
         sk.ws = w->ws; sk.n_pad = n_pad; sk.split_stride = m_pad * n_pad;
     }
     const int items = tiles * splits;
-    int* sched = sched_slot(stream);
+    int* sched = CTA2 ? nullptr : sched_slot(stream);
     // dynamic scheduling needs no SM reserve (CTAs that find the SMs taken by a collective simply find no work later)
     const int sms = sched ? sm_count_physical() : sm_count();
-    const int grid = items < sms ? items : sms;
+    int grid = items < sms ? items : sms;
+    if (CTA2) grid = 2 * (items < sms / 2 ? items : sms / 2);                   // CTA pairs
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
     static const bool pdl = []() { const char* e = getenv("KLAB_PDL"); return !(e && e[0] == '0'); }();
+    if (pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (CTA2) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    KLAB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, D, ldd, M, N, K, bn, stages_for(bn), sk, epi, ce, sched));
+    cfg.numAttrs = na;
+    KLAB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, D, ldd, M, N, K, bn, stages_for(bnl), sk, epi, ce, sched));
     KLAB_LAUNCH_CHECK();
     count_launch();
     if (splits > 1) {
@@ -568,6 +634,7 @@ int launch_cfg(cudaStream_t stream, int M, int N, int K, int bn, int splits, Wor
         cfg.gridDim = dim3(static_cast<unsigned>(blocks));
         cfg.blockDim = dim3(256);
         cfg.dynamicSmemBytes = 0;
+        cfg.numAttrs = pdl ? 1 : 0;                                              // (no cluster for the reduce kernel)
         KLAB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, splitk_reduce_kernel, sk, D, ldd, M, N, epi));
         KLAB_LAUNCH_CHECK();
         count_launch();
@@ -588,19 +655,33 @@ int gemm_tc_launch(cudaStream_t stream, int M, int N, int K, const void* A, long
     const bool splittable = epi.act == KLAB_ACT_NONE && !epi.bias && !epi.residual && !epi.aux_out && epi.dropout_p == 0.0f &&
                             epi.out_dtype == KLAB_F32;
     if (splittable) w = get_workspace(stream);
-    int bn, splits;
-    pick_config(M, N, K, b_mn != 0, w != nullptr, WS_BYTES, epi, &bn, &splits);
+    int bn, splits, cta2;
+    // the pair kernel distributes work statically: not while the data-parallel reducer has switched dynamic distribution on
+    const bool pair_ok = cta_pairs_enabled() && M > BM && sched_slot_enabled() == 0 && sm_count() == sm_count_physical();
+    pick_config(M, N, K, b_mn != 0, w != nullptr, pair_ok, WS_BYTES, epi, &bn, &splits, &cta2);
+    if (const char* f = getenv("KLAB_GEMM_FORCE_CTA2")) {       // development aid
+        const int v = atoi(f);
+        if (v == 0) cta2 = 0;
+        else if (pair_ok) { cta2 = 1; if (bn % (b_mn ? 128 : 32) != 0) bn = (bn + (b_mn ? 127 : 31)) / (b_mn ? 128 : 32) * (b_mn ? 128 : 32); if (bn > 256) bn = 256; }
+    }
     if (const char* f = getenv("KLAB_GEMM_FORCE_BN")) {          // development aid: pin the N tile (and disable split-K)
         const int v = atoi(f);
-        if (v >= 16 && v <= 256 && v % (b_mn ? 64 : 16) == 0) { bn = v; splits = 1; }
+        if (v >= 16 && v <= 256 && v % (b_mn ? 64 : 16) == 0 && (!cta2 || v % (b_mn ? 128 : 32) == 0)) { bn = v; splits = 1; }
     }
     if (const char* f = getenv("KLAB_GEMM_FORCE_SPLITS")) {
         const int v = atoi(f), num_k = (K + BK - 1) / BK;
-        const size_t tiles = static_cast<size_t>((M + BM - 1) / BM) * ((N + bn - 1) / bn);
-        if (w && v >= 1 && v <= num_k && tiles * v * BM * bn * 4 <= WS_BYTES) {
+        const int tm = cta2 ? 2 * BM : BM;
+        const size_t tiles = static_cast<size_t>((M + tm - 1) / tm) * ((N + bn - 1) / bn);
+        if (w && v >= 1 && v <= num_k && tiles * v * tm * bn * 4 <= WS_BYTES) {
             const int kps = (num_k + v - 1) / v;
             splits = (num_k + kps - 1) / kps;
         }
+    }
+    if (cta2) {
+        if (!a_mn && !b_mn) return launch_cfg<false, false, EPI_STORE, true>(stream, M, N, K, bn, splits, w, A, lda, B, ldb, D, ldd, epi);
+        if (!a_mn && b_mn) return launch_cfg<false, true, EPI_STORE, true>(stream, M, N, K, bn, splits, w, A, lda, B, ldb, D, ldd, epi);
+        if (a_mn && !b_mn) return launch_cfg<true, false, EPI_STORE, true>(stream, M, N, K, bn, splits, w, A, lda, B, ldb, D, ldd, epi);
+        return launch_cfg<true, true, EPI_STORE, true>(stream, M, N, K, bn, splits, w, A, lda, B, ldb, D, ldd, epi);
     }
     if (!a_mn && !b_mn) return launch_cfg<false, false>(stream, M, N, K, bn, splits, w, A, lda, B, ldb, D, ldd, epi);
     if (!a_mn && b_mn) return launch_cfg<false, true>(stream, M, N, K, bn, splits, w, A, lda, B, ldb, D, ldd, epi);
