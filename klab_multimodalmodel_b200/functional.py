@@ -645,10 +645,13 @@ def _swin_block_fwd_body(x, c, save, *params):
     C_ = x.shape[1]
     wqkv, w_p, w_f1, w_f2 = _swin_operands(c, params, cd, "peek")
     bqkv = cat_vec([(qb, C_), (None, C_), (vb, C_)], x.device)            # key has no bias (:417)
+    # the continuous position bias depends on weights only: side stream, joined before the attention kernel
+    w1d, b1d, w2d = w1.detach(), b1.detach(), w2.detach()
+    bias16, hidden, tab = _Side.run(lambda *_: O.swin_cpb_fwd(c.coords, c.index, w1d, b1d, w2d, c.heads, c.N), w1d, b1d, w2d)
     qkv = O.linear_fwd(x, wqkv, bias=bqkv)
-    bias16, hidden, tab = O.swin_cpb_fwd(c.coords, c.index, w1.detach(), b1.detach(), w2.detach(), c.heads, c.N)
     lsv = ls.detach().reshape(-1)
     q, k, v = qkv[:, :C_], qkv[:, C_:2 * C_], qkv[:, 2 * C_:]
+    _Side.join()
     ctxt, lse = O.swin_attention_fwd(q, k, v, c.B, c.res, c.heads, c.hd, c.w, c.shift, lsv, bias16)
     a = O.linear_fwd(ctxt, w_p, bias=pb)
     h, mean1, rstd1 = O.layernorm_fwd(a, g1, be1, c.eps, residual=x, save_stats=save)       # res-post-norm (:707-708)
@@ -682,7 +685,8 @@ def _swin_block_bwd_body(dout, x, qkv, bias16, hidden, tab, ctxt, lse, a, mean1,
     lsv = ls.detach().reshape(-1)
     dbias, dls = O.swin_attention_bwd(q, k, v, ctxt, dctx, dqkv[:, :C_], dqkv[:, C_:2 * C_], dqkv[:, 2 * C_:], c.B, c.res,
                                       c.heads, c.hd, c.w, c.shift, lsv, bias16, lse)
-    dw1, db1, dw2 = O.swin_cpb_bwd(c.coords, c.index, w2.detach(), hidden, tab, dbias, c.heads, c.N)
+    w2d = w2.detach()                                                    # position-bias MLP gradients: off the critical path
+    dw1, db1, dw2 = _Side.run(lambda *_: O.swin_cpb_bwd(c.coords, c.index, w2d, hidden, tab, dbias, c.heads, c.N), dbias, hidden, tab, w2d)
     dx = O.linear_dgrad(dqkv, wqkv, residual=dh)                          # + residual path of the first norm
     dwqkv = _wgrad(dqkv, x)
     dbqkv = _colsum(dqkv)
