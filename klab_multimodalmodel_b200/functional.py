@@ -178,6 +178,30 @@ def _needs_grad(tensors) -> bool:
     return _OUTER_GRAD[0] and any(t is not None and t.requires_grad for t in tensors)
 
 
+# Data parallelism: gradient all-reduces run on NCCL's stream DURING BACKWARD only (reducer.py waits for them at the end of
+# backward), so only backward kernels share the GPU with a collective.  While a backward function runs, the library is told to
+# distribute GEMM / T5-attention work dynamically and to keep `reserve` SMs out of the statically partitioned Swin kernels;
+# forward kernels keep the full machine, the static stride and the CTA-pair GEMM.  (CUDA graphs bake the choice at capture.)
+DP_BACKWARD = {"on": False, "reserve": 0}
+
+
+def _backward_phase(fn):
+    def wrapped(ctx, *grads):
+        if not DP_BACKWARD["on"]:
+            return fn(ctx, *grads)
+        lib = L.lib()
+        lib.klab_set_dynamic_sched(1)
+        lib.klab_set_sm_reserve(DP_BACKWARD["reserve"])
+        try:
+            return fn(ctx, *grads)
+        finally:
+            lib.klab_set_dynamic_sched(0)
+            lib.klab_set_sm_reserve(0)
+    wrapped.__name__ = fn.__name__
+    wrapped.__doc__ = fn.__doc__
+    return wrapped
+
+
 def _grad_outputs(outs, graphed):
     """Gradients handed back to autograd.  A captured region returns the SAME static tensors on every replay, and its tuple
     keeps a reference to them, so AccumulateGrad (which only adopts a gradient nobody else holds) would clone every parameter
@@ -413,6 +437,7 @@ class T5BlockFn(torch.autograd.Function):
         return outs[0]
 
     @staticmethod
+    @_backward_phase
     def backward(ctx, dout):
         c = ctx.c
         x, enc_out, table, *params = ctx.saved_tensors
@@ -439,6 +464,7 @@ class RMSNormFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_backward_phase
     def backward(ctx, dy):
         x, w, rstd = ctx.saved_tensors
         dx, dw = O.rmsnorm_bwd(dy.contiguous(), x, w, rstd)
@@ -454,6 +480,7 @@ class DropoutFn(torch.autograd.Function):
         return O.dropout_apply(x, p, seed, seed_ptr)
 
     @staticmethod
+    @_backward_phase
     def backward(ctx, dy):
         return O.dropout_apply(dy, ctx.p, ctx.seed, ctx.seed_ptr), None, None, None
 
@@ -479,6 +506,7 @@ class ConcatEmbeddingsFn(torch.autograd.Function):
         return buf.view(B * le, d)
 
     @staticmethod
+    @_backward_phase
     def backward(ctx, dbuf):
         img, ln_w, mean, rstd = ctx.saved_tensors
         n_img, le, d = ctx.geom
@@ -503,6 +531,7 @@ class DecoderEmbedFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_backward_phase
     def backward(ctx, dy):
         (labels,) = ctx.saved_tensors
         shape, start_id, pad_id = ctx.meta
@@ -548,6 +577,7 @@ class LMHeadLossFn(torch.autograd.Function):
         return stats[0].clone()
 
     @staticmethod
+    @_backward_phase
     def backward(ctx, gloss):
         ctx.step_token.release()
         x, ln_w, table, lab, rstd, n, logits, lse, stats = ctx.saved_tensors
@@ -596,6 +626,7 @@ class PatchEmbedFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_backward_phase
     def backward(ctx, dy):
         pm, e, ln_w, mean, rstd = ctx.saved_tensors
         de, dg, db = O.layernorm_bwd(dy.contiguous(), e, ln_w, mean, rstd)
@@ -621,6 +652,7 @@ class PatchMergeFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_backward_phase
     def backward(ctx, dy):
         g, r, red_w, ln_w, mean, rstd = ctx.saved_tensors
         cache, B, res, C_ = ctx.meta
@@ -718,6 +750,7 @@ class SwinBlockFn(torch.autograd.Function):
         return outs[0]
 
     @staticmethod
+    @_backward_phase
     def backward(ctx, dout):
         c = ctx.c
         x, *params = ctx.saved_tensors

@@ -58,11 +58,12 @@ class MyModel(nn.Module):
             broadcast_from_rank0([p for _, p in named])                # DDP broadcasts only the parameters it keeps
             self._klab_reducer = GradReducer([p for _, p in named])
             if named[0][1].is_cuda:
-                # GEMM and T5-attention kernels hand out their work dynamically and need no SMs set aside; the Swin attention
-                # kernels keep static contiguous shares (head affinity) and leave the collective's SMs free instead -- a 200 KB
-                # CTA cannot share an SM with an NCCL CTA, and a CTA that starts a wave late doubles the kernel's time.
-                L.lib().klab_set_sm_reserve(int(os.environ.get("KLAB_SM_RESERVE", os.environ.get("NCCL_MAX_CTAS", "16"))))
-                L.lib().klab_set_dynamic_sched(int(os.environ.get("KLAB_DYNAMIC_SCHED", "1")))
+                # The collectives run during backward only: backward kernels hand out GEMM / T5-attention work dynamically and
+                # the Swin attention kernels (static contiguous shares, for head affinity) leave the collective's SMs free -- a
+                # 200 KB CTA cannot share an SM with an NCCL CTA, and a CTA that starts a wave late doubles the kernel's time.
+                # Forward kernels keep the whole machine (functional.py: _backward_phase).
+                Fn.DP_BACKWARD["on"] = os.environ.get("KLAB_DYNAMIC_SCHED", "1") != "0"
+                Fn.DP_BACKWARD["reserve"] = int(os.environ.get("KLAB_SM_RESERVE", os.environ.get("NCCL_MAX_CTAS", "16")))
         return [n for n, _ in named]
 
     def _concat_embeddings(self, images, source_encoding):
