@@ -258,3 +258,63 @@ def test_kv_cached_decode_matches_prefix_recompute(dtype):
         same_prefix = (a[:, :n] == b[:, :n]).long().cumprod(1).sum(1)         # tokens before the first divergence, per sample
         assert same_prefix.float().mean().item() >= 0.9 * n, (a, b)
     assert a[:, 0].eq(0).all()
+
+
+@pytest.mark.parametrize("graphs", [True, False])
+def test_dropout_masks_of_forward_and_backward_agree(graphs):
+    """Training mode (T5 dropout p = 0.1 active, train.py:52): the masks are never stored -- every kernel regenerates them from
+    (site constant + device step counter, element index).  If a backward kernel drew a different mask than its forward twin
+    the gradient would silently be wrong, so check it against central differences of the loss along random directions with
+    the step counter pinned (fp32 path; the loss is piecewise smooth for fixed masks)."""
+    from klab_multimodalmodel_b200.graphs import POOL
+    from klab_multimodalmodel_b200.modeling import step_seed
+    case = EXTRA_CASES["mid"]
+    model, sds, swin, t5 = build(case, "fp32", style="hf")
+    model.transformer.train()
+    was = POOL.enabled
+    POOL.enabled = graphs and was
+    try:
+        px, src, tgt = [t.cuda() for t in seeded_inputs(case["batch"], swin, t5.vocab_size, case["l_src"], case["l_tgt"], ignore_tail=True)]
+        ctr = step_seed(px.device)
+        pinned = 123456789
+
+        def loss_at():
+            ctr.fill_(pinned)                              # forward advances the counter by one first: same masks every time
+            return model({"pixel_values": px}, {"input_ids": src}, {"input_ids": tgt})
+
+        eval_loss = None
+        for _ in range(3 if POOL.enabled else 1):          # warm-up call, capture, replay
+            for p in model.parameters():
+                p.grad = None
+            loss = loss_at()
+            loss.backward()
+        model.transformer.eval()
+        with torch.no_grad():
+            eval_loss = model({"pixel_values": px}, {"input_ids": src}, {"input_ids": tgt}).item()
+        model.transformer.train()
+        assert abs(loss.item() - eval_loss) > 1e-4 * abs(eval_loss), "dropout does not seem to be active"
+        params = [p for p in list(model.transformer.parameters()) + list(model.image_model.parameters()) if p.grad is not None]
+        grads = [p.grad.detach().clone() for p in params]
+        gen = torch.Generator(device="cuda").manual_seed(5)
+        checked = 0
+        for trial in range(3):
+            dirs = [torch.randn(p.shape, device=p.device, generator=gen) * p.detach().abs().mean().clamp_min(1e-3) for p in params]
+            norm = sum((d.double() ** 2).sum() for d in dirs).sqrt().item()
+            dirs = [d / norm for d in dirs]
+            analytic = sum((g.double() * d.double()).sum() for g, d in zip(grads, dirs)).item()
+            eps = 2e-2
+            with torch.no_grad():
+                for p, d in zip(params, dirs):
+                    p.add_(eps * d)
+                lp = loss_at().item()
+                for p, d in zip(params, dirs):
+                    p.sub_(2 * eps * d)
+                lm = loss_at().item()
+                for p, d in zip(params, dirs):
+                    p.add_(eps * d)
+            numeric = (lp - lm) / (2 * eps)
+            assert abs(numeric - analytic) <= 2e-2 * max(abs(analytic), abs(numeric)) + 2e-3, (trial, numeric, analytic)
+            checked += 1
+        assert checked == 3
+    finally:
+        POOL.enabled = was
