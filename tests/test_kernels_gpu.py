@@ -225,7 +225,8 @@ def test_t5_bucket_lut_matches_oracle():
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("B,res,heads,hd,w,shift", [(2, 8, 2, 32, 4, 2), (1, 8, 1, 32, 8, 0), (2, 14, 2, 32, 7, 3), (1, 16, 3, 16, 4, 0),
                                                     (24, 32, 3, 32, 8, 4),      # 576 (head, pair) items: persistent CTAs loop, prefetch, and change head mid-range
-                                                    (3, 7, 1, 32, 7, 0)])       # odd window count: padded second slot
+                                                    (3, 7, 1, 32, 7, 0),        # odd window count: padded second slot
+                                                    (2, 24, 2, 32, 12, 6)])     # 12 x 12 windows (384^2 inputs): CUDA-core kernel, N = 144
 def test_swin_attention(dtype, B, res, heads, hd, w, shift):
     o = ops()
     Cc = heads * hd
