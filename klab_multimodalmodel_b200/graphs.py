@@ -6,8 +6,10 @@ compiler is not an option here, CUDA graphs are (the kernels are static given th
 
   * a region is `fn(*inputs, *consts) -> tuple of tensors`; `inputs` are activations / gradients, `consts` are parameters,
     prepared bf16 operands, LUTs and non-tensor arguments (addresses assumed stable, verified before every replay);
-  * first call with a new key runs eagerly (warm-up: lazy attribute setup inside the library), the second call captures,
-    later calls replay;
+  * first call with a new key runs eagerly (warm-up: lazy attribute setup inside the library, and the GEMM's per-signature
+    timing of its one-CTA / CTA-pair candidates, which must not happen under capture), the second call captures, later calls
+    replay; a region may fork work onto a second stream (functional._Side: weight gradients) -- the fork and the join are
+    captured as a parallel branch of the graph;
   * outputs (and every activation kept for backward) are static buffers owned by the graph's private memory pool; an input
     that is itself the output of another region is consumed in place, anything else is copied into a staging buffer first;
   * dropout masks come from a device-side counter (klab_seed_advance), so replays draw fresh masks with no host involvement;
