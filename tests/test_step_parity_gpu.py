@@ -255,7 +255,10 @@ def test_kv_cached_decode_matches_prefix_recompute(dtype):
     px, src, _ = seeded_inputs(case["batch"], swin, t5.vocab_size, case["l_src"], case["l_tgt"])
     with torch.no_grad():
         emb, B, Le = model._concat_embeddings({"pixel_values": px.cuda()}, {"input_ids": src.cuda()})
-        a = greedy_generate(model.transformer, emb, B, Le).cpu()
+        a = greedy_generate(model.transformer, emb, B, Le).cpu()          # eager warm-up of the per-position regions
+        for _ in range(2):                                                # CUDA-graph capture, then replay: same ids
+            again = greedy_generate(model.transformer, emb, B, Le).cpu()
+            assert torch.equal(a, again)
         b = greedy_generate_recompute(model.transformer, emb, B, Le).cpu()
     assert a.dtype == torch.int64 and a.shape[0] == case["batch"] and a.shape[1] <= 21
     if dtype == "fp32":
