@@ -100,6 +100,8 @@ class MyModel(nn.Module):
         return emb, B, n_img + src.shape[1]
 
     def forward(self, images, source_encoding, target_encoding=None, return_loss=True):
+        if self._klab_reducer is not None:
+            self._klab_reducer.begin_step()
         if self.transformer.training and not Fn.pending_backward():
             advance_step_seed(images["pixel_values"].device)          # fresh dropout masks for this step (device-side counter)
         emb, B, Le = self._concat_embeddings(images, source_encoding)

@@ -86,6 +86,19 @@ class GradReducer:
             self._in_backward = False
             self.buckets_last_backward = self._count
 
+    def begin_step(self):
+        """Called at the start of every forward: if the previous backward died half way (an exception inside a kernel wrapper,
+        a KeyboardInterrupt), its end-of-backward callback never ran -- drop the stale bookkeeping instead of skipping the
+        callback of every later backward.  A no-op in normal operation."""
+        if self._in_backward or self._pending or self._works:
+            for w in self._works:
+                try:
+                    w.wait()
+                except Exception:                 # noqa: BLE001
+                    pass
+            self._pending, self._pending_bytes, self._works, self._summed = [], 0, [], []
+            self._in_backward = False
+
     # ------------------------------------------------------------------------------------------
     @contextlib.contextmanager
     def no_sync(self):

@@ -83,6 +83,16 @@ def _worker(rank, world, port, q):
         sum((p * (rank + 1.0)).sum() for p in trainable).backward()
         assert model._klab_reducer.buckets_last_backward > 1
         assert all(torch.allclose(p.grad, torch.full_like(p.grad, (1.0 + world) / 2.0)) for p in trainable)
+        # a backward that died half way leaves no stale state behind: begin_step() (called by every forward) clears it
+        red = model._klab_reducer
+        red._in_backward, red._pending = True, [trainable[0].grad]
+        red.begin_step()
+        assert not red._in_backward and not red._pending and not red._works
+        for p in trainable:
+            p.grad = None
+        ddp.reducer.prepare_for_backward([])
+        sum((p * (rank + 1.0)).sum() for p in trainable).backward()
+        assert all(torch.allclose(p.grad, torch.full_like(p.grad, (1.0 + world) / 2.0)) for p in trainable)
         # bench helpers: per-rank shards differ; timing is the max over ranks
         w = dict(bench.WORKLOADS["tiny"])
         px, src, tgt = bench.synth_batch(w, 512, 1234 + rank, pin=False)
