@@ -43,6 +43,22 @@ CASES = {
 }
 
 
+# Closer to the real geometries; the oracle is pinned to the reference on them too (tests/test_oracle_golden.py).  The GPU
+# step-parity tests compare these cases with the oracle only (tests/test_step_parity_gpu.py: EXTRA_CASES).
+EXTRA_CASES = {
+    # window 8 with shift 4, head_dim 32, d_kv 64, 96-token encoder sequence
+    "mid": dict(swin=dict(image_size=128, embed_dim=32, depths=(2, 2, 2), num_heads=(1, 2, 4), window_size=8),
+                t5=dict(vocab_size=1000, d_model=128, d_ff=512, num_layers=2, num_heads=2),
+                batch=2, l_src=16, l_tgt=24, ignore_tail=True, train_swin=True),
+    # BASELINE configs 3 / 4 in miniature: 12 x 12 windows with shift 6 (N = 144: the CUDA-core window-attention kernel), a
+    # 64-token source (encoder length 144 + 64 = 208: the multi-tile T5 attention kernels) and 128-token targets
+    "hires": dict(swin=dict(image_size=96, embed_dim=32, depths=(2, 2), num_heads=(1, 2), window_size=12,
+                            pretrained_window_sizes=(0, 0)),
+                  t5=dict(vocab_size=600, d_model=64, d_ff=128, num_layers=2, num_heads=1),
+                  batch=2, l_src=64, l_tgt=128, ignore_tail=True, train_swin=True),
+}
+
+
 def dims_of(case):
     sw = dict(case["swin"])
     sw.setdefault("pretrained_window_sizes", (0,) * len(sw["depths"]))
@@ -110,5 +126,5 @@ if __name__ == "__main__":
     ap.add_argument("--out", default=os.path.dirname(os.path.abspath(__file__)))
     a = ap.parse_args()
     torch.manual_seed(0)
-    for name, case in CASES.items():
+    for name, case in {**CASES, **EXTRA_CASES}.items():
         np.savez_compressed(os.path.join(a.out, f"{name}.npz"), **run_reference(name, case))

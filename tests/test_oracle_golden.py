@@ -7,14 +7,14 @@ import pytest
 import torch
 
 from oracle.caption_model import caption_embeddings, caption_generate, caption_loss, seeded_inputs, seeded_state_dicts
-from tests.golden.make_golden import CASES, dims_of, sample_index
+from tests.golden.make_golden import CASES, EXTRA_CASES, dims_of, sample_index
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
-@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("name", sorted(CASES) + sorted(EXTRA_CASES))
 def test_oracle_matches_reference_golden(name):
-    case = CASES[name]
+    case = CASES.get(name) or EXTRA_CASES[name]
     gold = np.load(os.path.join(GOLD, f"{name}.npz"))
     swin, t5 = dims_of(case)
     sds = seeded_state_dicts(t5, swin, t5, seed=0)

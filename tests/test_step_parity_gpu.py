@@ -15,18 +15,7 @@ from tests.golden.make_golden import CASES, dims_of, sample_index  # noqa: E402
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
-EXTRA_CASES = {
-    # closer to the real geometry: window 8 with shift 4, head_dim 32, d_kv 64, 96-token encoder sequence
-    "mid": dict(swin=dict(image_size=128, embed_dim=32, depths=(2, 2, 2), num_heads=(1, 2, 4), window_size=8),
-                t5=dict(vocab_size=1000, d_model=128, d_ff=512, num_layers=2, num_heads=2),
-                batch=2, l_src=16, l_tgt=24, ignore_tail=True, train_swin=True),
-    # BASELINE configs 3 / 4 in miniature: 12 x 12 windows with shift 6 (N = 144: the CUDA-core window-attention kernel), a
-    # 64-token source (encoder length 144 + 64 = 208: the multi-tile T5 attention kernels) and 128-token targets
-    "hires": dict(swin=dict(image_size=96, embed_dim=32, depths=(2, 2), num_heads=(1, 2), window_size=12,
-                            pretrained_window_sizes=(0, 0)),
-                  t5=dict(vocab_size=600, d_model=64, d_ff=128, num_layers=2, num_heads=1),
-                  batch=2, l_src=64, l_tgt=128, ignore_tail=True, train_swin=True),
-}
+from tests.golden.make_golden import EXTRA_CASES  # noqa: E402  (geometries closer to the real ones; reference goldens exist for the oracle test)
 
 
 def build(case, dtype, style="hot"):
