@@ -104,6 +104,13 @@ int klab_rmsnorm_fwd(void* stream, int dtype, long long rows, int d, const void*
 int klab_rmsnorm_bwd(void* stream, int dtype, long long rows, int d, const void* dy, long long lddy, const void* x, long long ldx,
                      const float* gamma, const float* rstd, const void* dres, long long lddres, void* dx, long long lddx,
                      float* dgamma, int accumulate_dgamma, void* workspace);
+/* Same, and in the same pass dx_drop[rows, d] = dropout(dx) with the mask klab_dropout_apply(p, seed, seed_ptr) draws for a
+ * contiguous [rows, d] tensor: the consumer of dx (T5LayerSelfAttention / T5LayerCrossAttention backward,
+ * HF/models/t5/modeling_t5.py:375,406) starts by applying its forward dropout mask to its output gradient. */
+int klab_rmsnorm_bwd_dropout(void* stream, int dtype, long long rows, int d, const void* dy, long long lddy, const void* x, long long ldx,
+                             const float* gamma, const float* rstd, const void* dres, long long lddres, void* dx, long long lddx,
+                             float* dgamma, int accumulate_dgamma, void* workspace, void* dx_drop, float p, unsigned long long seed,
+                             const unsigned long long* seed_ptr);
 long long klab_norm_bwd_workspace_bytes(long long rows, int d);
 
 /* ---- K6: LayerNorm, Swin-V2 res-post-norm form (HF/models/swinv2/modeling_swinv2.py:273,386,707-712,969) ----

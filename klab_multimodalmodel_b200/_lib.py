@@ -61,6 +61,7 @@ SIGNATURES = {
     "klab_gemm_simt": [_vp, _i, _i, _i, _i, _vp, _ll, _i, _vp, _ll, _i, _vp, _ll, C.POINTER(GemmEpilogue)],
     "klab_rmsnorm_fwd": [_vp, _i, _ll, _i, _vp, _ll, _vp, _f, _vp, _ll, _i, _ll, _vp],
     "klab_rmsnorm_bwd": [_vp, _i, _ll, _i, _vp, _ll, _vp, _ll, _vp, _vp, _vp, _ll, _vp, _ll, _vp, _i, _vp],
+    "klab_rmsnorm_bwd_dropout": [_vp, _i, _ll, _i, _vp, _ll, _vp, _ll, _vp, _vp, _vp, _ll, _vp, _ll, _vp, _i, _vp, _vp, _f, _ull, _vp],
     "klab_norm_bwd_workspace_bytes": [_ll, _i],
     "klab_layernorm_fwd": [_vp, _i, _ll, _i, _vp, _ll, _vp, _vp, _f, _vp, _ll, _vp, _ll, _i, _ll, _vp, _vp],
     "klab_layernorm_bwd": [_vp, _i, _ll, _i, _vp, _ll, _i, _ll, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _vp, _ll, _vp, _vp, _i, _vp],

@@ -24,6 +24,17 @@ struct RowMap {
     }
 };
 
+// Optional fused "dropout of the output gradient" of the backward norm kernels (vector path): out = dropout(dx) with the mask
+// klab_dropout_apply(seed, seed_ptr, p) would draw for a contiguous [rows, d] tensor.
+struct NormDrop {
+    void* out;
+    long long ld;
+    float p;
+    unsigned long long seed;
+    const unsigned long long* seed_ptr;
+};
+
+
 constexpr int WARPS = 4;
 constexpr int VEC = 4;            // elements per lane per step on the vector path (8 B of bf16 / 16 B of fp32)
 constexpr int MAXV = 8;           // vector path covers d <= 32 * VEC * MAXV = 1024 with d % 128 == 0
@@ -112,10 +123,14 @@ __global__ void __launch_bounds__(WARPS * 32)
 norm_bwd_vec_kernel(const T* __restrict__ dy, RowMap dym, const T* __restrict__ x, RowMap xm, const float* __restrict__ gamma,
                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const T* __restrict__ dres, RowMap drm,
                     T* __restrict__ dx, RowMap dxm, float* __restrict__ part_dgamma, float* __restrict__ part_dbeta,
-                    long long rows, int d) {
+                    long long rows, int d, NormDrop dr) {
     extern __shared__ float sm[];          // [WARPS][d] dgamma (, [WARPS][d] dbeta)
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    // optional second output: dx with the dropout mask of the consumer applied (the layer that receives dx as its output
+    // gradient starts by multiplying it with its forward mask; doing that here saves one pass over the tensor per sub-layer)
+    DropKey dkey = make_drop_key(0, 0.0f);
+    if (dr.out) dkey = make_drop_key(dr.seed + (dr.seed_ptr ? *dr.seed_ptr : 0ull), dr.p);
     float g4[NV][4], ag[NV][4], ab[NV][4];
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
@@ -164,6 +179,19 @@ norm_bwd_vec_kernel(const T* __restrict__ dy, RowMap dym, const T* __restrict__ 
                 for (int t = 0; t < 4; ++t) o[t] += r4[t];
             }
             Vec4<T>::store(dxr + c0, o);
+            if (dr.out) {
+                // same arithmetic as klab_dropout_apply on the STORED dx: round to T first, then mask * 1 / (1 - p)
+                float q[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) q[t] = to_f32(from_f32<T>(o[t]));
+                const uint64_t e0 = static_cast<uint64_t>(row) * static_cast<uint64_t>(d) + static_cast<uint64_t>(c0);    // even
+                const uint32_t h0 = drop_hash_pair(dkey, e0 >> 1), h1 = drop_hash_pair(dkey, (e0 >> 1) + 1);
+                q[0] *= (h0 & 0xFFFFu) < dkey.thr16 ? dkey.inv_keep : 0.0f;
+                q[1] *= (h0 >> 16) < dkey.thr16 ? dkey.inv_keep : 0.0f;
+                q[2] *= (h1 & 0xFFFFu) < dkey.thr16 ? dkey.inv_keep : 0.0f;
+                q[3] *= (h1 >> 16) < dkey.thr16 ? dkey.inv_keep : 0.0f;
+                Vec4<T>::store(reinterpret_cast<T*>(dr.out) + row * dr.ld + c0, q);
+            }
         }
     }
     // combine the 4 warps' register partials through shared memory, one row of partials per CTA
@@ -422,26 +450,28 @@ int norm_fwd_t(cudaStream_t st, const void* x, RowMap xm, const float* gamma, co
 template <typename T, bool IS_LN>
 int norm_bwd_t(cudaStream_t st, const void* dy, RowMap dym, const void* x, RowMap xm, const float* gamma, const float* mean,
                const float* rstd, const void* dres, RowMap drm, void* dx, RowMap dxm, float* dgamma, float* dbeta,
-               int accumulate, float* workspace, long long rows, int d) {
+               int accumulate, float* workspace, long long rows, int d, NormDrop dr = NormDrop{nullptr, 0, 0.0f, 0ull, nullptr}) {
     int grid = static_cast<int>((rows + WARPS - 1) / WARPS);
     const int cap = sm_count() * 4;
     if (grid > cap) grid = cap;
     float* part_dg = workspace;
     float* part_db = workspace + static_cast<long long>(grid) * d;
 #define KLAB_NORM_BWD_ARGS reinterpret_cast<const T*>(dy), dym, reinterpret_cast<const T*>(x), xm, gamma, mean, rstd, reinterpret_cast<const T*>(dres), drm, reinterpret_cast<T*>(dx), dxm, part_dg, part_db, rows, d
+    if (dr.out && (dr.ld % VEC != 0 || (reinterpret_cast<uintptr_t>(dr.out) & (sizeof(T) * VEC - 1)) != 0 || dr.ld != d)) return -1;   // caller falls back
     const bool vec = vec_ok<T>(dy, dym.ld, x, xm.ld, dres, drm.ld, dx, dxm.ld, dym, xm, d) && (d / 128 <= 4 || d / 128 == 6 || d / 128 == 8);
     if (vec) {
         const size_t smem = (IS_LN ? 2 : 1) * WARPS * d * sizeof(float);
         switch (d / 128) {
-            case 1: norm_bwd_vec_kernel<T, IS_LN, 1><<<grid, WARPS * 32, smem, st>>>(KLAB_NORM_BWD_ARGS); break;
-            case 2: norm_bwd_vec_kernel<T, IS_LN, 2><<<grid, WARPS * 32, smem, st>>>(KLAB_NORM_BWD_ARGS); break;
-            case 3: norm_bwd_vec_kernel<T, IS_LN, 3><<<grid, WARPS * 32, smem, st>>>(KLAB_NORM_BWD_ARGS); break;
-            case 4: norm_bwd_vec_kernel<T, IS_LN, 4><<<grid, WARPS * 32, smem, st>>>(KLAB_NORM_BWD_ARGS); break;
-            case 6: norm_bwd_vec_kernel<T, IS_LN, 6><<<grid, WARPS * 32, smem, st>>>(KLAB_NORM_BWD_ARGS); break;
-            default: norm_bwd_vec_kernel<T, IS_LN, 8><<<grid, WARPS * 32, smem, st>>>(KLAB_NORM_BWD_ARGS); break;
+            case 1: norm_bwd_vec_kernel<T, IS_LN, 1><<<grid, WARPS * 32, smem, st>>>(KLAB_NORM_BWD_ARGS, dr); break;
+            case 2: norm_bwd_vec_kernel<T, IS_LN, 2><<<grid, WARPS * 32, smem, st>>>(KLAB_NORM_BWD_ARGS, dr); break;
+            case 3: norm_bwd_vec_kernel<T, IS_LN, 3><<<grid, WARPS * 32, smem, st>>>(KLAB_NORM_BWD_ARGS, dr); break;
+            case 4: norm_bwd_vec_kernel<T, IS_LN, 4><<<grid, WARPS * 32, smem, st>>>(KLAB_NORM_BWD_ARGS, dr); break;
+            case 6: norm_bwd_vec_kernel<T, IS_LN, 6><<<grid, WARPS * 32, smem, st>>>(KLAB_NORM_BWD_ARGS, dr); break;
+            default: norm_bwd_vec_kernel<T, IS_LN, 8><<<grid, WARPS * 32, smem, st>>>(KLAB_NORM_BWD_ARGS, dr); break;
         }
     } else {
         const size_t smem = (IS_LN ? 2 : 1) * d * sizeof(float);
+        if (dr.out) return -1;                                   // generic path has no fused dropout: caller falls back
         norm_bwd_kernel<T, IS_LN><<<grid, WARPS * 32, smem, st>>>(KLAB_NORM_BWD_ARGS);
     }
 #undef KLAB_NORM_BWD_ARGS
@@ -488,6 +518,29 @@ int klab_rmsnorm_bwd(void* stream, int dtype, long long rows, int d, const void*
     return dtype == KLAB_BF16
                ? norm_bwd_t<__nv_bfloat16, false>(st, dy, dym, x, xm, gamma, nullptr, rstd, dres, drm, dx, dxm, dgamma, nullptr, accumulate_dgamma, ws, rows, d)
                : norm_bwd_t<float, false>(st, dy, dym, x, xm, gamma, nullptr, rstd, dres, drm, dx, dxm, dgamma, nullptr, accumulate_dgamma, ws, rows, d);
+}
+
+// klab_rmsnorm_bwd that ALSO writes dx_drop = dropout(dx; p, seed (+ *seed_ptr)) -- the mask klab_dropout_apply draws for a
+// contiguous [rows, d] tensor -- in the same pass.  dx_drop has row stride d.
+int klab_rmsnorm_bwd_dropout(void* stream, int dtype, long long rows, int d, const void* dy, long long lddy, const void* x, long long ldx,
+                             const float* gamma, const float* rstd, const void* dres, long long lddres, void* dx, long long lddx,
+                             float* dgamma, int accumulate_dgamma, void* workspace, void* dx_drop, float p, unsigned long long seed,
+                             const unsigned long long* seed_ptr) {
+    if (int rc = klab_check_device()) return rc;
+    KLAB_REQUIRE(rows > 0 && d > 0 && dx_drop && p >= 0.0f && p < 1.0f, "rmsnorm_bwd_dropout: bad arguments rows=%lld d=%d p=%f", rows, d, p);
+    const RowMap dym{lddy, 0, 0}, xm{ldx, 0, 0}, drm{lddres, 0, 0}, dxm{lddx, 0, 0};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float* ws = static_cast<float*>(workspace);
+    const NormDrop dr{dx_drop, d, p, seed, seed_ptr};
+    int rc = dtype == KLAB_BF16
+                 ? norm_bwd_t<__nv_bfloat16, false>(st, dy, dym, x, xm, gamma, nullptr, rstd, dres, drm, dx, dxm, dgamma, nullptr, accumulate_dgamma, ws, rows, d, dr)
+                 : norm_bwd_t<float, false>(st, dy, dym, x, xm, gamma, nullptr, rstd, dres, drm, dx, dxm, dgamma, nullptr, accumulate_dgamma, ws, rows, d, dr);
+    if (rc != -1) return rc;
+    // shapes the vector kernel does not take: two passes
+    rc = klab_rmsnorm_bwd(stream, dtype, rows, d, dy, lddy, x, ldx, gamma, rstd, dres, lddres, dx, lddx, dgamma, accumulate_dgamma, workspace);
+    if (rc) return rc;
+    KLAB_REQUIRE(lddx == d, "rmsnorm_bwd_dropout: the two-pass fallback needs a contiguous dx (lddx=%lld, d=%d)", lddx, d);
+    return klab_dropout_apply(stream, dtype, rows * d, dx, dx_drop, p, seed, seed_ptr);
 }
 
 int klab_layernorm_fwd(void* stream, int dtype, long long rows, int d, const void* x, long long ldx, const float* gamma,

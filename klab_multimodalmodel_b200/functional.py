@@ -296,12 +296,15 @@ def _t5_attn_fwd(c, n, kv_src, wq_or_qkv, wkv, wo, resid, table, lut, rz, causal
     return h, qkv, kvbuf, ctxt, lse
 
 
-def _t5_attn_bwd(c, dh, n, kv_src, wq_or_qkv, wkv, wo, qkv, kvbuf, ctxt, lse, table, lut, rz, causal, Lq, Lk, seed, dtable):
-    """dh: gradient of the attention layer's output (residual part handled by the caller).
+def _t5_attn_bwd(c, dh, n, kv_src, wq_or_qkv, wkv, wo, qkv, kvbuf, ctxt, lse, table, lut, rz, causal, Lq, Lk, seed, dtable, dh_dropped=None):
+    """dh: gradient of the attention layer's output (residual part handled by the caller); dh_dropped: the same with this
+    layer's output-dropout mask already applied (fused into the norm backward that produced dh).
     Returns dn, dkv_src (or None), dWq(kv), dWkv (or None), dWo."""
     H, dk = c.H, c.dk
     inner = H * dk
-    if c.p > 0.0:                                        # dropout on the o-projection output (:375 / :406)
+    if dh_dropped is not None:
+        dh = dh_dropped
+    elif c.p > 0.0:                                      # dropout on the o-projection output (:375 / :406)
         dh = O.dropout_apply(dh, c.p, seed + 1, c.seed_ptr)
     dctx = O.linear_dgrad(dh, wo)
     dwo = _wgrad(dh, ctxt)
@@ -332,14 +335,19 @@ def _t5_ff_fwd(c, x, ln_w, wi, wo, seed):
     return out, n, rstd, f
 
 
-def _t5_ff_bwd(c, dout, x, ln_w, wi, wo, n, rstd, f, seed):
+def _t5_ff_bwd(c, dout, x, ln_w, wi, wo, n, rstd, f, seed, next_seed):
+    """next_seed: dropout seed of the sub-layer that consumes dx (its output-dropout mask is applied in the same pass).
+    -> dx, dropout(dx) or None, dln, dwi, dwo"""
     dy = O.dropout_apply(dout, c.p, seed + 1, c.seed_ptr) if c.p > 0.0 else dout
     df = O.linear_dgrad(dy, wo, act=L.ACT_RELU_BWD, aux_in=f, dropout_p=c.p, seed=seed, seed_ptr=c.seed_ptr)
     dwo = _wgrad(dy, f)
     dn = O.linear_dgrad(df, wi)
     dwi = _wgrad(df, n)
-    dx, dln = O.rmsnorm_bwd(dn, x, ln_w, rstd, dres=dout)
-    return dx, dln, dwi, dwo
+    if c.p > 0.0:
+        dx, dln, dxd = O.rmsnorm_bwd(dn, x, ln_w, rstd, dres=dout, drop=(c.p, next_seed + 1, c.seed_ptr))
+    else:
+        (dx, dln), dxd = O.rmsnorm_bwd(dn, x, ln_w, rstd, dres=dout), None
+    return dx, dxd, dln, dwi, dwo
 
 
 def _t5_operands(c, params, cd, mode):
@@ -393,17 +401,20 @@ def _t5_block_bwd_body(dout, x, enc_out, *rest):
         n0, rstd0, qkv, ctxt, lse, h1, n1, rstd1, qc, kvbuf, ctx2, lse2, h2, n2, rstd2, f = acts
         ln0, ln1, ln2 = params[0], params[5], params[10]
         wqkv, w_o, w_i, w_ff, w_cq, w_ckv, w_co = ws
-        dh2, dln2, dwi, dwo_ff = _t5_ff_bwd(c, dout, h2, ln2, w_i, w_ff, n2, rstd2, f, seed + 4)
+        dh2, dh2d, dln2, dwi, dwo_ff = _t5_ff_bwd(c, dout, h2, ln2, w_i, w_ff, n2, rstd2, f, seed + 4, seed + 2)
         dn1, denc, dwcq, dwckv, dwco = _t5_attn_bwd(c, dh2, n1, enc_out, w_cq, w_ckv, w_co, qc, kvbuf, ctx2, lse2, None, None, 0,
-                                                    False, c.L, c.Le, seed + 2, None)
-        dh1, dln1 = O.rmsnorm_bwd(dn1, h1, ln1, rstd1, dres=dh2)
+                                                    False, c.L, c.Le, seed + 2, None, dh_dropped=dh2d)
+        if c.p > 0.0:                                    # + the self-attention layer's output-dropout mask for its backward
+            dh1, dln1, dh1d = O.rmsnorm_bwd(dn1, h1, ln1, rstd1, dres=dh2, drop=(c.p, seed + 1, c.seed_ptr))
+        else:
+            (dh1, dln1), dh1d = O.rmsnorm_bwd(dn1, h1, ln1, rstd1, dres=dh2), None
     else:
         n0, rstd0, qkv, ctxt, lse, h1, n2, rstd2, f = acts
         ln0, ln1 = params[0], params[5]
         wqkv, w_o, w_i, w_ff = ws
-        dh1, dln1, dwi, dwo_ff = _t5_ff_bwd(c, dout, h1, ln1, w_i, w_ff, n2, rstd2, f, seed + 4)
+        dh1, dh1d, dln1, dwi, dwo_ff = _t5_ff_bwd(c, dout, h1, ln1, w_i, w_ff, n2, rstd2, f, seed + 4, seed)
     dn0, _, dwqkv, _, dwo = _t5_attn_bwd(c, dh1, n0, None, wqkv, None, w_o, qkv, None, ctxt, lse, table, c.lut, c.rz, dec,
-                                         c.L, c.L, seed, dtable)
+                                         c.L, c.L, seed, dtable, dh_dropped=dh1d)
     dx, dln0 = O.rmsnorm_bwd(dn0, x, ln0, rstd0, dres=dh1)
     _Side.join()
     gq, gk, gv = dwqkv[:inner], dwqkv[inner:2 * inner], dwqkv[2 * inner:]

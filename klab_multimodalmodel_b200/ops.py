@@ -147,16 +147,27 @@ def rmsnorm_fwd(x, gamma, eps, *, out=None, out_rows_per_group=0, out_group_stri
     return y, rstd
 
 
-def rmsnorm_bwd(dy, x, gamma, rstd, dres=None, dgamma=None):
+def rmsnorm_bwd(dy, x, gamma, rstd, dres=None, dgamma=None, drop=None):
+    """-> (dx, dgamma), or (dx, dgamma, dropout(dx)) with drop = (p, seed, seed_ptr): the mask `dropout_apply` would draw."""
     rows, d = x.shape
     dx = torch.empty(rows, d, dtype=x.dtype, device=x.device)
     acc = dgamma is not None
     if dgamma is None:
         dgamma = torch.empty(d, dtype=torch.float32, device=x.device)
     ws = _bytes(L.lib().klab_norm_bwd_workspace_bytes(rows, d), x.device)
+    if drop is not None and drop[0] > 0.0:
+        p, seed, seed_ptr = drop
+        dxd = torch.empty(rows, d, dtype=x.dtype, device=x.device)
+        L.check(L.lib().klab_rmsnorm_bwd_dropout(_stream(), _DT[x.dtype], rows, d, dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0),
+                                                 gamma.data_ptr(), rstd.data_ptr(), _p(dres), dres.stride(0) if dres is not None else 0,
+                                                 dx.data_ptr(), dx.stride(0), dgamma.data_ptr(), int(acc), ws.data_ptr(), dxd.data_ptr(),
+                                                 float(p), int(seed), _p(seed_ptr)))
+        return dx, dgamma, dxd
     L.check(L.lib().klab_rmsnorm_bwd(_stream(), _DT[x.dtype], rows, d, dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0),
                                      gamma.data_ptr(), rstd.data_ptr(), _p(dres), dres.stride(0) if dres is not None else 0,
                                      dx.data_ptr(), dx.stride(0), dgamma.data_ptr(), int(acc), ws.data_ptr()))
+    if drop is not None:
+        return dx, dgamma, dx
     return dx, dgamma
 
 
