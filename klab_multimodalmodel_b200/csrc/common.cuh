@@ -216,6 +216,11 @@ __device__ __forceinline__ void dropout_apply_run(const DropKey& k, uint64_t bas
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// Bytes to add to a dynamic-shared-memory base to reach the next 1024-byte boundary (SWIZZLE_128B tiles need it).  Adding the
+// pad to the __shared__ ARRAY keeps the pointer in the shared address space: rounding it up through uintptr_t makes it a generic
+// pointer, and every tile access becomes a generic LD / ST with 64-bit address arithmetic instead of LDS / STS.
+__device__ __forceinline__ uint32_t smem_align_pad(const void* base) { return (1024u - (smem_u32(base) & 1023u)) & 1023u; }
+
 
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;

@@ -109,7 +109,7 @@ __device__ __forceinline__ float inv_norm32(const float* v, float& norm) {
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) swin_attn_fwd_tc_kernel(SwinTcArgs a, int npairs) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + smem_align_pad(smem_raw);      // 1024-byte aligned, still a __shared__ pointer (LDS / STS, 32-bit addressing)
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + TB;
     uint8_t* sV = sK + TB;
@@ -295,7 +295,7 @@ constexpr int BWD_THREADS = 512;
 
 __global__ void __launch_bounds__(BWD_THREADS, 1) swin_attn_bwd_tc_kernel(SwinTcArgs a, int npairs) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + smem_align_pad(smem_raw);      // 1024-byte aligned, still a __shared__ pointer (LDS / STS, 32-bit addressing)
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + TB;
     uint8_t* sV = sK + TB;
