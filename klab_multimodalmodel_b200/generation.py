@@ -16,7 +16,6 @@ from __future__ import annotations
 import torch
 
 from . import _lib as L
-from . import functional as Fn
 from . import ops as O
 
 

@@ -53,7 +53,6 @@ class MyModel(nn.Module):
             return []
         named = [(n, p) for n, p in self.named_parameters() if p.requires_grad and n != self._DDP_KEEPS]
         if self._klab_reducer is None and named:
-            from .. import _lib as L
             from ..reducer import GradReducer, broadcast_from_rank0
             broadcast_from_rank0([p for _, p in named])                # DDP broadcasts only the parameters it keeps
             self._klab_reducer = GradReducer([p for _, p in named])
