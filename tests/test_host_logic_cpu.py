@@ -93,3 +93,37 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"] and d["metric"].startswith("train samples/sec")
+
+
+def test_checkpoint_save_load_round_trip_in_reference_format(tmp_path):
+    """N4: MyModel.save / .load write and read the reference's file format (/root/reference/models/model.py:30-42):
+    {'transformer': state_dict[, 'image_model': state_dict]} with HF key names, so checkpoints are interchangeable."""
+    import types
+
+    from klab_multimodalmodel_b200.modeling import Swinv2Config, T5Config, init_swin_, init_t5_
+    from klab_multimodalmodel_b200.models.model import MyModel
+    tcfg = T5Config(vocab_size=64, d_model=128, d_ff=64, num_layers=1, num_heads=2)
+    scfg = Swinv2Config(image_size=32, embed_dim=32, depths=(1, 1, 1), num_heads=(1, 2, 4), window_size=4, pretrained_window_sizes=(0, 0, 0))
+
+    def make(train_swin, seed):
+        args = types.SimpleNamespace(result_dir=str(tmp_path), language_model_name=tcfg, image_model_name=scfg,
+                                     image_model_train=train_swin, transformer_model_name=tcfg)
+        m = MyModel(args)
+        init_t5_(m.transformer, seed=seed)
+        init_swin_(m.image_model, seed=seed + 1)
+        return m
+
+    for train_swin in (True, False):
+        a, b = make(train_swin, 10), make(train_swin, 20)
+        a.save(result_name="ckpt.pth")
+        blob = torch.load(os.path.join(str(tmp_path), "ckpt.pth"))
+        assert set(blob) == ({"transformer", "image_model"} if train_swin else {"transformer"})
+        assert "shared.weight" in blob["transformer"] and "lm_head.weight" in blob["transformer"]
+        assert "encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight" in blob["transformer"]
+        if train_swin:
+            assert "encoder.layers.0.blocks.0.attention.self.continuous_position_bias_mlp.0.weight" in blob["image_model"]
+        b.load(result_name="ckpt.pth")
+        for (k, pa), (_, pb) in zip(a.transformer.state_dict().items(), b.transformer.state_dict().items()):
+            assert torch.equal(pa, pb), k
+        same_swin = all(torch.equal(x, y) for x, y in zip(a.image_model.state_dict().values(), b.image_model.state_dict().values()))
+        assert same_swin == train_swin                      # the image model travels only when it is trained (model.py:33-34,41-42)
