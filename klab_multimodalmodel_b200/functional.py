@@ -129,17 +129,26 @@ class Ctx:
 
     def __init__(self, **kw):
         self.busy = False
+        self.gen = 0                                # generation of the forward whose static activations are live
         self.__dict__.update(kw)
 
 
 class _Token:
-    """Clears Ctx.busy when the autograd node that owns it dies without having run backward."""
+    """Clears Ctx.busy when the autograd node that owns it dies without having run backward.  Only the token of the LATEST
+    captured forward may do so: the previous step's autograd node (kept alive by the caller's `loss` variable) usually dies
+    after the next forward has already claimed the Ctx, and must not release it under that forward's pending backward."""
 
     def __init__(self, c):
         self.c = c
+        c.gen += 1
+        self.gen = c.gen
+
+    def release(self):
+        if self.c.gen == self.gen:
+            self.c.busy = False
 
     def __del__(self):
-        self.c.busy = False
+        self.release()
 
 
 class _StepToken:
@@ -457,7 +466,9 @@ class T5BlockFn(torch.autograd.Function):
             _detach_aliased_grads(params if table is None else params + [table])
         outs, graphed = POOL.run(("t5b", id(c)), _t5_block_bwd_body, (dout.contiguous(), x, enc_out) + tuple(acts),
                                  (c, table) + tuple(params), allow_graph=ctx.graphed)
-        c.busy = False
+        tok, ctx.token = getattr(ctx, "token", None), None
+        if tok is not None:
+            tok.release()
         return (None,) + _grad_outputs(outs, graphed)
 
 
@@ -770,5 +781,7 @@ class SwinBlockFn(torch.autograd.Function):
             _detach_aliased_grads(params)
         outs, graphed = POOL.run(("swb", id(c)), _swin_block_bwd_body, (dout.contiguous(), x) + tuple(acts), (c,) + tuple(params),
                                  allow_graph=ctx.graphed)
-        c.busy = False
+        tok, ctx.token = getattr(ctx, "token", None), None
+        if tok is not None:
+            tok.release()
         return (None,) + _grad_outputs(outs, graphed)

@@ -104,6 +104,8 @@ def greedy_generate(tr, embeds, B, Le, max_new_tokens: int = 20):
     st = states.get(key)
     if st is None:
         if len(states) >= 4:                                             # a handful of geometries at most: the caches are large
+            dead = {id(o) for o in states.values()}                      # the per-position regions bake the old buffers in: drop
+            POOL.drop_keys(lambda k: k[0] == "dec" and k[2] in dead)     # them too, or the states would never be freed
             states.clear()
         st = states[key] = _DecodeState(tr, B, Le, T, cd, dev)
     enc = tr.encoder.run_blocks(embeds, B, Le, tr.cache)

@@ -12,6 +12,7 @@ import json
 import math
 import os
 import random
+import warnings
 from dataclasses import asdict, dataclass
 
 import torch
@@ -78,25 +79,87 @@ class Swinv2Config:
     }
 
 
+def _hf_cache_roots() -> list[str]:
+    """Where `transformers` keeps downloaded snapshots (HF_HUB_CACHE / TRANSFORMERS_CACHE / HF_HOME/hub / ~/.cache/huggingface/hub)."""
+    roots = []
+    for var in ("HF_HUB_CACHE", "HUGGINGFACE_HUB_CACHE", "TRANSFORMERS_CACHE"):
+        if os.environ.get(var):
+            roots.append(os.environ[var])
+    home = os.environ.get("HF_HOME") or os.path.join(os.path.expanduser("~"), ".cache", "huggingface")
+    roots.append(os.path.join(home, "hub"))
+    return roots
+
+
+_HUB_ALIASES = {"t5-small": "google-t5/t5-small", "t5-base": "google-t5/t5-base", "t5-large": "google-t5/t5-large",
+                "t5-3b": "google-t5/t5-3b", "t5-11b": "google-t5/t5-11b"}
+
+
+def resolve_snapshot(name: str) -> str | None:
+    """A bare model name -> the newest local snapshot directory of the HF cache that holds its config.json, or None.
+    The reference's `from_pretrained(name)` (/root/reference/models/model.py:14-17) finds its weights the same way when the
+    hub is unreachable (HF_HUB_OFFLINE); nothing is ever downloaded here."""
+    names = [name] + ([_HUB_ALIASES[name]] if name in _HUB_ALIASES else [])
+    best = None
+    for root in _hf_cache_roots():
+        for nm in names:
+            snaps = os.path.join(root, "models--" + nm.replace("/", "--"), "snapshots")
+            if not os.path.isdir(snaps):
+                continue
+            for rev in os.listdir(snaps):
+                d = os.path.join(snaps, rev)
+                if os.path.exists(os.path.join(d, "config.json")):
+                    m = os.path.getmtime(d)
+                    if best is None or m > best[0]:
+                        best = (m, d)
+    return best[1] if best else None
+
+
+def _config_from_dir(cls, path, overrides):
+    fields = {f for f in cls.__dataclass_fields__}
+    with open(os.path.join(path, "config.json")) as fh:
+        raw = json.load(fh)
+    kw = {k: (tuple(v) if isinstance(v, list) else v) for k, v in raw.items() if k in fields}
+    kw.update(overrides)
+    return cls(**kw)
+
+
 def _config_from_source(cls, source, **overrides):
-    """`from_pretrained`-style resolution: a cls instance, a local directory with config.json, or a known model name."""
+    """`from_pretrained`-style resolution -> (config, checkpoint directory or None):
+      * a cls instance: explicit architecture, random initialisation is what the caller asked for (tests, benchmarks);
+      * a local directory with config.json (+ model.safetensors / pytorch_model.bin);
+      * a model name: its snapshot in the local HF cache if there is one; otherwise a KNOWN name gives the architecture but no
+        weights -- the reference would fail here (no network), so this raises unless KLAB_ALLOW_RANDOM_INIT=1 opts in to a
+        randomly initialised model (a loud warning is issued)."""
     if isinstance(source, cls):
         return source, None
-    fields = {f for f in cls.__dataclass_fields__}
     if isinstance(source, str) and os.path.isdir(source) and os.path.exists(os.path.join(source, "config.json")):
-        with open(os.path.join(source, "config.json")) as fh:
-            raw = json.load(fh)
-        kw = {k: (tuple(v) if isinstance(v, list) else v) for k, v in raw.items() if k in fields}
-        kw.update(overrides)
-        return cls(**kw), source
-    if isinstance(source, str) and source in cls.NAMED:
-        kw = dict(cls.NAMED[source])
-        kw.update(overrides)
-        return cls(**kw), None
-    raise FileNotFoundError(f"{source!r} is neither a local checkpoint directory (config.json) nor a known {cls.__name__} name")
+        return _config_from_dir(cls, source, overrides), source
+    if isinstance(source, str):
+        snap = resolve_snapshot(source)
+        if snap is not None:
+            return _config_from_dir(cls, snap, overrides), snap
+        if source in cls.NAMED:
+            if os.environ.get("KLAB_ALLOW_RANDOM_INIT", "0") != "1":
+                raise FileNotFoundError(
+                    f"{source!r}: no local checkpoint directory and no snapshot in the HF cache ({', '.join(_hf_cache_roots())}); "
+                    "pass a directory with config.json + weights, or set KLAB_ALLOW_RANDOM_INIT=1 to get a RANDOMLY INITIALISED "
+                    f"{cls.__name__[:-6]} model of that architecture")
+            warnings.warn(f"klab_multimodalmodel_b200: {source!r} has no weights on this machine -- the model is RANDOMLY INITIALISED "
+                          "(KLAB_ALLOW_RANDOM_INIT=1)", RuntimeWarning, stacklevel=3)
+            kw = dict(cls.NAMED[source])
+            kw.update(overrides)
+            return cls(**kw), None
+    raise FileNotFoundError(f"{source!r} is neither a local checkpoint directory (config.json), a cached snapshot nor a known {cls.__name__} name")
 
 
-def _load_checkpoint_dir(module: nn.Module, path: str) -> bool:
+_BASE_PREFIXES = ("swinv2.", "transformer.", "model.", "encoder_model.")
+
+
+def _load_checkpoint_dir(module: nn.Module, path: str) -> None:
+    """Load model.safetensors / pytorch_model.bin of a checkpoint directory, strict on the module's own keys.  Like HF's
+    `from_pretrained` it strips the base-model prefix when the file was written by a task head (the published
+    microsoft/swinv2-* checkpoints are Swinv2ForImageClassification: 'swinv2.embeddings...' + 'classifier.*') and reports the
+    keys it drops.  A directory without weights is an error: the reference never random-initialises silently."""
     st = os.path.join(path, "model.safetensors")
     pt = os.path.join(path, "pytorch_model.bin")
     if os.path.exists(st):
@@ -105,17 +168,25 @@ def _load_checkpoint_dir(module: nn.Module, path: str) -> bool:
     elif os.path.exists(pt):
         sd = torch.load(pt, map_location="cpu")
     else:
-        return False
+        raise FileNotFoundError(f"{path}: config.json found but neither model.safetensors nor pytorch_model.bin")
     own = module.state_dict()
+    if not any(k in own for k in sd):                     # nothing matches: a task-head checkpoint of the same base model?
+        for pre in _BASE_PREFIXES:
+            stripped = {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
+            if any(k in own for k in stripped):
+                sd = {**{k: v for k, v in sd.items() if not k.startswith(pre)}, **stripped}
+                break
     for k in own:                      # tied tensors are stored once in safetensors files
         if k not in sd:
             for alias in ("shared.weight", "encoder.embed_tokens.weight", "decoder.embed_tokens.weight", "lm_head.weight"):
                 if alias in sd and own[k].shape == sd[alias].shape and k.endswith(("embed_tokens.weight", "lm_head.weight", "shared.weight")):
                     sd[k] = sd[alias]
                     break
-    sd = {k: v for k, v in sd.items() if k in own}
-    module.load_state_dict(sd, strict=True)
-    return True
+    dropped = sorted(k for k in sd if k not in own)
+    if dropped:
+        warnings.warn(f"klab_multimodalmodel_b200: {path}: {len(dropped)} checkpoint tensors are not part of {type(module).__name__} "
+                      f"and were ignored: {', '.join(dropped[:6])}{' ...' if len(dropped) > 6 else ''}", RuntimeWarning, stacklevel=3)
+    module.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=True)
 
 
 class _P(nn.Module):

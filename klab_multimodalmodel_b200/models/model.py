@@ -25,6 +25,7 @@ from torch import nn
 
 from .. import functional as Fn
 from ..generation import greedy_generate
+from ..graphs import POOL
 from ..modeling import Swinv2Model, T5EncoderModel, T5ForConditionalGeneration, _compute_dtype, advance_step_seed
 
 
@@ -100,7 +101,9 @@ class MyModel(nn.Module):
 
     def forward(self, images, source_encoding, target_encoding=None, return_loss=True):
         if self._klab_reducer is not None:
-            self._klab_reducer.begin_step()
+            ddp = getattr(torch.nn.parallel.DistributedDataParallel, "_active_ddp_module", None)      # set while DDP.forward runs
+            self._klab_reducer.begin_step(ddp if ddp is not None and getattr(ddp, "module", None) is self else None)
+        POOL.begin_step()
         if self.transformer.training and not Fn.pending_backward():
             advance_step_seed(images["pixel_values"].device)          # fresh dropout masks for this step (device-side counter)
         emb, B, Le = self._concat_embeddings(images, source_encoding)

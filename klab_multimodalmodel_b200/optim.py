@@ -29,7 +29,7 @@ class Adam(torch.optim.Optimizer):
         """items: list of (p, g, m, v, w16 pointer or 0).  Device tables are rebuilt only when a pointer changed (with CUDA graphs the gradient
         buffers are static, so this happens once).  Rebuilds go through two alternating pinned staging buffers and an event, so
         they never synchronise the device."""
-        sig = tuple((p.data_ptr(), g.data_ptr(), m.data_ptr(), w) for p, g, m, v, w in items)
+        sig = tuple((p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), w) for p, g, m, v, w in items)
         ent = self._tables.get(key)
         if ent is not None and ent["sig"] == sig:
             return ent["table"], ent["blockmap"], ent["nblocks"]

@@ -36,6 +36,7 @@ class GradReducer:
             bucket_bytes = int(float(os.environ.get("KLAB_BUCKET_MB", "64")) * (1 << 20))
         self.bucket_bytes = bucket_bytes
         self.enabled = True
+        self.sync_next_backward = True          # DDP's require_backward_grad_sync at the time of the forward (model.no_sync())
         self._pending: list = []
         self._pending_bytes = 0
         self._works: list = []
@@ -48,8 +49,8 @@ class GradReducer:
 
     # ------------------------------------------------------------------------------------------
     def _on_grad(self, p):
-        if not self.enabled or p.grad is None or not dist.is_initialized():      # (process group already torn down: local run)
-            return
+        if not self.enabled or not self.sync_next_backward or p.grad is None or not dist.is_initialized():
+            return                                # (no_sync(), or the process group is already torn down: local run)
         if not self._in_backward:
             self._in_backward = True
             self._count = 0
@@ -86,8 +87,9 @@ class GradReducer:
             self._in_backward = False
             self.buckets_last_backward = self._count
 
-    def begin_step(self):
-        """Called at the start of every forward: if the previous backward died half way (an exception inside a kernel wrapper,
+    def begin_step(self, ddp=None):
+        """Called at the start of every forward (`ddp`: the DistributedDataParallel wrapper whose forward is running, if any --
+        inside `with ddp_model.no_sync():` it has require_backward_grad_sync = False and this backward must not all-reduce): if the previous backward died half way (an exception inside a kernel wrapper,
         a KeyboardInterrupt), its end-of-backward callback never ran -- drop the stale bookkeeping instead of skipping the
         callback of every later backward.  A no-op in normal operation."""
         if self._in_backward or self._pending or self._works:
@@ -98,6 +100,7 @@ class GradReducer:
                     pass
             self._pending, self._pending_bytes, self._works, self._summed = [], 0, [], []
             self._in_backward = False
+        self.sync_next_backward = True if ddp is None else bool(getattr(ddp, "require_backward_grad_sync", True))
 
     # ------------------------------------------------------------------------------------------
     @contextlib.contextmanager

@@ -75,6 +75,15 @@ def _worker(rank, world, port, q):
         with model._klab_reducer.no_sync(), ddp.no_sync():
             sum((p * (rank + 1.0)).sum() for p in trainable).backward()
         assert all(torch.allclose(p.grad, torch.full_like(p.grad, rank + 1.0)) for p in trainable)
+        # DDP's own no_sync() is honoured too: every forward tells the reducer whether its backward synchronises
+        for p in trainable:
+            p.grad = None
+        with ddp.no_sync():
+            model._klab_reducer.begin_step(ddp)
+            sum((p * (rank + 1.0)).sum() for p in trainable).backward()
+        assert all(torch.allclose(p.grad, torch.full_like(p.grad, rank + 1.0)) for p in trainable)
+        model._klab_reducer.begin_step(ddp)
+        assert model._klab_reducer.sync_next_backward
         # small buckets: several grouped all-reduces per backward, same result
         model._klab_reducer.bucket_bytes = 64 << 10
         for p in trainable:

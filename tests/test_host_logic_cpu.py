@@ -127,3 +127,64 @@ def test_checkpoint_save_load_round_trip_in_reference_format(tmp_path):
             assert torch.equal(pa, pb), k
         same_swin = all(torch.equal(x, y) for x, y in zip(a.image_model.state_dict().values(), b.image_model.state_dict().values()))
         assert same_swin == train_swin                      # the image model travels only when it is trained (model.py:33-34,41-42)
+
+
+def test_from_pretrained_resolution(tmp_path, monkeypatch):
+    """/root/reference/models/model.py:14-17 calls from_pretrained(name).  A bare name resolves through the local HF cache; a
+    task-head checkpoint ('swinv2.' prefix + classifier, what microsoft/swinv2-* publishes) loads into the base model; a name with
+    no weights on disk raises (opt-in: KLAB_ALLOW_RANDOM_INIT=1 warns); a directory with a config but no weights raises."""
+    import json
+
+    import pytest
+    from safetensors.torch import save_file
+
+    from klab_multimodalmodel_b200.modeling import (Swinv2Config, Swinv2Model, T5Config, T5EncoderModel, T5ForConditionalGeneration,
+                                                      config_dict, init_swin_, init_t5_)
+    scfg = Swinv2Config(image_size=32, embed_dim=32, depths=(1, 1), num_heads=(1, 2), window_size=4, pretrained_window_sizes=(0, 0))
+    src = Swinv2Model(scfg)
+    init_swin_(src, seed=5)
+    # (1) HF-style cache layout, keys prefixed as Swinv2ForImageClassification writes them
+    monkeypatch.setenv("HF_HOME", str(tmp_path / "hf"))
+    for var in ("HF_HUB_CACHE", "HUGGINGFACE_HUB_CACHE", "TRANSFORMERS_CACHE", "KLAB_ALLOW_RANDOM_INIT"):
+        monkeypatch.delenv(var, raising=False)
+    snap = tmp_path / "hf" / "hub" / "models--microsoft--swinv2-base-patch4-window8-256" / "snapshots" / "abc123"
+    snap.mkdir(parents=True)
+    (snap / "config.json").write_text(json.dumps(config_dict(scfg)))
+    sd = {"swinv2." + k: v.detach().clone() for k, v in src.state_dict().items()}
+    sd["classifier.weight"] = torch.zeros(10, 64)
+    sd["classifier.bias"] = torch.zeros(10)
+    save_file(sd, str(snap / "model.safetensors"))
+    with pytest.warns(RuntimeWarning, match="classifier"):
+        got = Swinv2Model.from_pretrained("microsoft/swinv2-base-patch4-window8-256")
+    assert got.config.embed_dim == 32 and not got.training
+    for (k, a), (_, b) in zip(src.state_dict().items(), got.state_dict().items()):
+        assert torch.equal(a, b), k
+    # (2) a T5ForConditionalGeneration checkpoint under the legacy name feeds both the frozen encoder and the trainable model
+    tcfg = T5Config(vocab_size=64, d_model=32, d_ff=64, num_layers=1, num_heads=1, d_kv=32)
+    t5 = T5ForConditionalGeneration(tcfg)
+    init_t5_(t5, seed=6)
+    snap5 = tmp_path / "hf" / "hub" / "models--google-t5--t5-small" / "snapshots" / "r1"
+    snap5.mkdir(parents=True)
+    (snap5 / "config.json").write_text(json.dumps(config_dict(tcfg)))
+    torch.save(t5.state_dict(), str(snap5 / "pytorch_model.bin"))
+    full = T5ForConditionalGeneration.from_pretrained("t5-small")
+    assert all(torch.equal(a, b) for a, b in zip(t5.state_dict().values(), full.state_dict().values()))
+    with pytest.warns(RuntimeWarning, match="decoder"):
+        enc = T5EncoderModel.from_pretrained("t5-small")
+    assert torch.equal(enc.shared.weight, t5.shared.weight)
+    assert torch.equal(enc.encoder.block[0].layer[0].SelfAttention.q.weight, t5.encoder.block[0].layer[0].SelfAttention.q.weight)
+    # (3) known name, nothing on disk: the reference would fail; so does the drop-in unless random init is opted into
+    with pytest.raises(FileNotFoundError, match="KLAB_ALLOW_RANDOM_INIT"):
+        T5ForConditionalGeneration.from_pretrained("t5-base")
+    monkeypatch.setenv("KLAB_ALLOW_RANDOM_INIT", "1")
+    with pytest.warns(RuntimeWarning, match="RANDOMLY INITIALISED"):
+        m = T5EncoderModel.from_pretrained("t5-base", num_layers=1)
+    assert m.config.d_model == 768
+    # (4) config without weights
+    bare = tmp_path / "bare"
+    bare.mkdir()
+    (bare / "config.json").write_text(json.dumps(config_dict(tcfg)))
+    with pytest.raises(FileNotFoundError, match="model.safetensors"):
+        T5EncoderModel.from_pretrained(str(bare))
+    with pytest.raises(FileNotFoundError):
+        T5EncoderModel.from_pretrained("no-such-model")
