@@ -87,6 +87,12 @@ int klab_gemm(void* stream, int in_dtype, int M, int N, int K,
               const void* A, long long lda, int a_mn_major,
               const void* B, long long ldb, int b_mn_major,
               void* D, long long ldd, const klab_gemm_epilogue* epi);
+/* Test / tuning aid for the bf16 tensor-core path: pin the kernel kind (cta2: 0 = one-CTA kernel, 1 = CTA-pair kernel with
+ * tcgen05.mma.cta_group::2), the N tile and the split-K count of the klab_gemm calls that follow; -1 leaves a choice to the
+ * library (default; KLAB_GEMM_FORCE_CTA2 / _BN / _SPLITS preset it at load).  A pin the shape cannot honour is ignored.
+ * klab_gemm_last_config reports what the calling thread's last bf16 klab_gemm actually launched. */
+int klab_gemm_set_force(int cta2, int bn, int splits);
+int klab_gemm_last_config(int* bn, int* splits, int* cta2);
 /* Same contract, forced onto the fp32-accumulating SIMT kernel (on-device cross-check of the tensor-core path). */
 int klab_gemm_simt(void* stream, int in_dtype, int M, int N, int K,
                    const void* A, long long lda, int a_mn_major,

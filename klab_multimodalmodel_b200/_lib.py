@@ -58,6 +58,8 @@ SIGNATURES = {
     "klab_sm_budget": [],
     "klab_set_dynamic_sched": [_i],
     "klab_gemm": [_vp, _i, _i, _i, _i, _vp, _ll, _i, _vp, _ll, _i, _vp, _ll, C.POINTER(GemmEpilogue)],
+    "klab_gemm_set_force": [_i, _i, _i],
+    "klab_gemm_last_config": [_vp, _vp, _vp],
     "klab_gemm_simt": [_vp, _i, _i, _i, _i, _vp, _ll, _i, _vp, _ll, _i, _vp, _ll, C.POINTER(GemmEpilogue)],
     "klab_rmsnorm_fwd": [_vp, _i, _ll, _i, _vp, _ll, _vp, _f, _vp, _ll, _i, _ll, _vp],
     "klab_rmsnorm_bwd": [_vp, _i, _ll, _i, _vp, _ll, _vp, _ll, _vp, _vp, _vp, _ll, _vp, _ll, _vp, _i, _vp],

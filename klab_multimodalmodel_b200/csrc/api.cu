@@ -175,6 +175,15 @@ int klab_gemm(void* stream, int in_dtype, int M, int N, int K, const void* A, lo
     return gemm_simt_launch(static_cast<cudaStream_t>(stream), in_dtype, M, N, K, A, lda, a_mn_major, B, ldb, b_mn_major, D, ldd, e);
 }
 
+int klab_gemm_set_force(int cta2, int bn, int splits) {
+    gemm_set_force(cta2, bn, splits);
+    return KLAB_OK;
+}
+int klab_gemm_last_config(int* bn, int* splits, int* cta2) {
+    gemm_last_config(bn, splits, cta2);
+    return KLAB_OK;
+}
+
 int klab_gemm_simt(void* stream, int in_dtype, int M, int N, int K, const void* A, long long lda, int a_mn_major,
                    const void* B, long long ldb, int b_mn_major, void* D, long long ldd, const klab_gemm_epilogue* epi) {
     if (int rc = check_device_impl()) return rc;

@@ -188,6 +188,9 @@ int gemm_tc_launch(cudaStream_t stream, int M, int N, int K, const void* A, long
 int gemm_simt_launch(cudaStream_t stream, int in_dtype, int M, int N, int K, const void* A, long long lda, int a_mn,
                      const void* B, long long ldb, int b_mn, void* D, long long ldd, const klab_gemm_epilogue& epi);
 
+void gemm_set_force(int cta2, int bn, int splits);
+void gemm_last_config(int* bn, int* splits, int* cta2);
+
 int lmhead_ce_num_parts(int V);
 int lmhead_ce_fwd_launch(cudaStream_t stream, int M, int V, int d, const void* h, long long ldh, const void* E, long long lde, float alpha,
                          const long long* labels, float2* partials, float* label_logit);

@@ -35,6 +35,7 @@
 // epilogue -- deterministic, no atomics and no in-kernel fences (a gpu-scope fence inside a CTA that keeps seven TMA stages
 // in flight costs ~15 us per item; fp32 red.global.add tops out at ~0.8 TB/s).
 #include <array>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <map>
@@ -659,9 +660,23 @@ struct GemmCfg {
     bool operator==(const GemmCfg& o) const { return bn == o.bn && splits == o.splits && cta2 == o.cta2; }
 };
 
+thread_local GemmCfg g_last_cfg{0, 0, 0};
+std::atomic<int> g_force_cta2{-2}, g_force_bn{-2}, g_force_splits{-2};      // -2: not initialised (read the environment once); -1: free
+
+int forced(std::atomic<int>& slot, const char* env) {
+    int v = slot.load(std::memory_order_relaxed);
+    if (v == -2) {
+        const char* e = getenv(env);
+        v = e ? atoi(e) : -1;
+        slot.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
 int dispatch_cfg(cudaStream_t stream, int M, int N, int K, const GemmCfg& c, Workspace* w, const void* A, long long lda, int a_mn,
                  const void* B, long long ldb, int b_mn, void* D, long long ldd, const klab_gemm_epilogue& epi) {
     const int bn = c.bn, splits = c.splits;
+    g_last_cfg = c;
     if (c.cta2) {
         if (!a_mn && !b_mn) return launch_cfg<false, false, EPI_STORE, true>(stream, M, N, K, bn, splits, w, A, lda, B, ldb, D, ldd, epi);
         if (!a_mn && b_mn) return launch_cfg<false, true, EPI_STORE, true>(stream, M, N, K, bn, splits, w, A, lda, B, ldb, D, ldd, epi);
@@ -704,19 +719,20 @@ int gemm_tc_launch(cudaStream_t stream, int M, int N, int K, const void* A, long
     const bool can_split = w != nullptr;
     GemmCfg model{};
     pick_config(M, N, K, b_mn != 0, can_split, pair_ok ? 2 : 0, WS_BYTES, epi, &model.bn, &model.splits, &model.cta2);
-    const bool forced = getenv("KLAB_GEMM_FORCE_CTA2") || getenv("KLAB_GEMM_FORCE_BN") || getenv("KLAB_GEMM_FORCE_SPLITS");
-    if (forced) {                                               // development aids: pin the kernel kind / N tile / split count
+    const int f_cta2 = forced(g_force_cta2, "KLAB_GEMM_FORCE_CTA2"), f_bn = forced(g_force_bn, "KLAB_GEMM_FORCE_BN"),
+              f_splits = forced(g_force_splits, "KLAB_GEMM_FORCE_SPLITS");
+    if (f_cta2 >= 0 || f_bn >= 0 || f_splits >= 0) {            // tests / tuning: pin the kernel kind / N tile / split count
         GemmCfg c = model;
-        if (const char* f = getenv("KLAB_GEMM_FORCE_CTA2")) {
-            const int v = atoi(f);
+        if (f_cta2 >= 0) {
+            const int v = f_cta2;
             if (v == 0 || pair_ok) pick_config(M, N, K, b_mn != 0, can_split, v ? 1 : 0, WS_BYTES, epi, &c.bn, &c.splits, &c.cta2);
         }
-        if (const char* f = getenv("KLAB_GEMM_FORCE_BN")) {
-            const int v = atoi(f);
+        if (f_bn >= 0) {
+            const int v = f_bn;
             if (v >= 16 && v <= 256 && v % (b_mn ? 64 : 16) == 0 && (!c.cta2 || v % (b_mn ? 128 : 32) == 0)) { c.bn = v; c.splits = 1; }
         }
-        if (const char* f = getenv("KLAB_GEMM_FORCE_SPLITS")) {
-            const int v = atoi(f), num_k = (K + BK - 1) / BK;
+        if (f_splits >= 0) {
+            const int v = f_splits, num_k = (K + BK - 1) / BK;
             const int tm = c.cta2 ? 2 * BM : BM;
             const size_t tiles = static_cast<size_t>((M + tm - 1) / tm) * ((N + c.bn - 1) / c.bn);
             if (w && v >= 1 && v <= num_k && tiles * v * tm * c.bn * 4 <= WS_BYTES) {
@@ -793,6 +809,18 @@ int gemm_tc_launch(cudaStream_t stream, int M, int N, int K, const void* A, long
         fprintf(stderr, "klab gemm autotune: M=%d N=%d K=%d a_mn=%d b_mn=%d act=%d -> bn=%d splits=%d pair=%d (%.1f us; model: bn=%d splits=%d pair=%d)\n",
                 M, N, K, a_mn, b_mn, epi.act, best.bn, best.splits, best.cta2, best_ms * 1e3f, model.bn, model.splits, model.cta2);
     return dispatch_cfg(stream, M, N, K, best, w, A, lda, a_mn, B, ldb, b_mn, D, ldd, epi);
+}
+
+void gemm_set_force(int cta2, int bn, int splits) {
+    g_force_cta2.store(cta2 < 0 ? -1 : cta2, std::memory_order_relaxed);
+    g_force_bn.store(bn < 0 ? -1 : bn, std::memory_order_relaxed);
+    g_force_splits.store(splits < 0 ? -1 : splits, std::memory_order_relaxed);
+}
+
+void gemm_last_config(int* bn, int* splits, int* cta2) {
+    if (bn) *bn = g_last_cfg.bn;
+    if (splits) *splits = g_last_cfg.splits;
+    if (cta2) *cta2 = g_last_cfg.cta2;
 }
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -14,6 +14,9 @@ from oracle.caption_model import caption_generate, caption_loss, seeded_inputs, 
 from tests.golden.make_golden import CASES, dims_of, sample_index  # noqa: E402
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
+# bf16 at full width, measured on B200 (see the test's printout in profiles/): bounds carry ~2x headroom over the observed values
+FULL_WIDTH_BF16_WHOLE_BOUND = 3e-2
+FULL_WIDTH_BF16_MEDIAN_BOUND = 3e-2
 
 from tests.golden.make_golden import EXTRA_CASES  # noqa: E402  (geometries closer to the real ones; reference goldens exist for the oracle test)
 
@@ -138,6 +141,72 @@ def test_bf16_loss_and_all_gradients(name):
     assert checked >= 50
     print(f"[{name}/bf16] loss {loss.item():.5f} (fp32 ref {ref_loss:.5f}, torch autocast {ac_loss:.5f}); "
           f"median (our err / autocast err) {float(np.median(ratios)):.2f}; {checked} tensors")
+
+
+@pytest.mark.parametrize("name", sorted(CASES) + sorted(EXTRA_CASES))
+def test_fp32_strict_1e4_on_hf_scale_weights(name):
+    """BASELINE.json's fp32 bar with no relaxation: loss AND every parameter-gradient tensor within 1e-4 relative (Frobenius) of
+    the oracle, on HF's own initialiser scales (the well-conditioned weights a real checkpoint has).  The "hot" weights of
+    test_fp32_loss_and_all_gradients stay as the stress test.  Prints the achieved worst per-tensor error."""
+    case = CASES.get(name) or EXTRA_CASES[name]
+    model, sds, swin, t5 = build(case, "fp32", style="hf")
+    px, src, tgt = seeded_inputs(case["batch"], swin, t5.vocab_size, case["l_src"], case["l_tgt"], ignore_tail=case["ignore_tail"])
+    loss = model({"pixel_values": px.cuda()}, {"input_ids": src.cuda()}, {"input_ids": tgt.cuda()})
+    loss.backward()
+    ref_loss, leaves = oracle_grads(case, sds, swin, t5, px, src, tgt)
+    assert abs(loss.item() - ref_loss) <= 1e-4 * abs(ref_loss), (loss.item(), ref_loss)
+    errs = []
+    for scope, mod in (("transformer", model.transformer), ("image_model", model.image_model)):
+        for k, p in mod.named_parameters():
+            ref = leaves[(scope, k)].grad
+            if ref is None:
+                assert p.grad is None
+                continue
+            g = p.grad.detach().float().cpu()
+            errs.append(((g - ref).norm().item() / max(ref.norm().item(), 1e-30), f"{scope}.{k}", ref.norm().item()))
+    errs.sort(reverse=True)
+    print(f"[{name}/fp32 strict] loss rel err {abs(loss.item() - ref_loss) / abs(ref_loss):.1e}; worst gradient rel err {errs[0][0]:.2e} at {errs[0][1]}; "
+          f"median {errs[len(errs) // 2][0]:.1e}; {len(errs)} tensors")
+    bad = [e for e in errs if e[0] > 1e-4]
+    assert not bad, f"{len(bad)}/{len(errs)} gradient tensors beyond 1e-4: " + "; ".join(f"{n}: {e:.2e} (|ref|={r:.2e})" for e, n, r in bad[:12])
+    assert len(errs) >= 50
+
+
+def test_full_width_step_swin_b_t5_large_bf16():
+    """SURVEY.md section 4 "step parity" at BASELINE width: bench workload 2a's model (Swin-B/256/w8 trained jointly + T5-large,
+    32 source + 32 target tokens) at batch 2, bf16 tensor-core path, dropout off, against the fp32 oracle on the host.  These are
+    the CTA-pair / split-K GEMMs, 96-row T5 attention tiles and 64-token windows the benchmark runs.  Loss within 1e-2; the
+    achieved per-tensor gradient errors are printed (sorted) and bounded."""
+    import bench
+    w = dict(bench.WORKLOADS["2a"], batch=2)
+    case = dict(swin=dict(w["swin"]), t5=dict(bench.T5_NAMED[w["t5"]]), batch=2, l_src=w["l_src"], l_tgt=w["l_tgt"], ignore_tail=True,
+                train_swin=True)
+    model, sds, swin, t5 = build(case, "bf16", style="hf")
+    px, src, tgt = seeded_inputs(2, swin, t5.vocab_size, case["l_src"], case["l_tgt"], ignore_tail=True)
+    loss = model({"pixel_values": px.cuda()}, {"input_ids": src.cuda()}, {"input_ids": tgt.cuda()})
+    loss.backward()
+    torch.cuda.synchronize()
+    ref_loss, leaves = oracle_grads(case, sds, swin, t5, px, src, tgt)
+    assert abs(loss.item() - ref_loss) <= 1e-2 * abs(ref_loss), (loss.item(), ref_loss)
+    errs, num, den = [], 0.0, 0.0
+    for scope, mod in (("transformer", model.transformer), ("image_model", model.image_model)):
+        for k, p in mod.named_parameters():
+            ref = leaves[(scope, k)].grad
+            assert ref is not None and p.grad is not None, k
+            g = p.grad.detach().float().cpu()
+            assert torch.isfinite(g).all(), k
+            d2, r2 = (g - ref).double().pow(2).sum().item(), ref.double().pow(2).sum().item()
+            num, den = num + d2, den + r2
+            errs.append(((d2 / max(r2, 1e-60)) ** 0.5, f"{scope}.{k}"))
+    errs.sort(reverse=True)
+    whole = (num / den) ** 0.5
+    within = sum(e <= 1e-2 for e, _ in errs)
+    print(f"[full width 2a, B=2, bf16] loss {loss.item():.5f} vs fp32 oracle {ref_loss:.5f} (rel {abs(loss.item() - ref_loss) / abs(ref_loss):.1e}); "
+          f"all gradients as one vector: rel err {whole:.2e}; per tensor: median {errs[len(errs) // 2][0]:.2e}, {within}/{len(errs)} within 1e-2, "
+          f"worst {errs[0][0]:.2e} at {errs[0][1]}; next {', '.join(f'{e:.1e} {n}' for e, n in errs[1:6])}")
+    assert whole <= FULL_WIDTH_BF16_WHOLE_BOUND, whole
+    assert errs[len(errs) // 2][0] <= FULL_WIDTH_BF16_MEDIAN_BOUND
+    assert len(errs) >= 900
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
