@@ -739,11 +739,31 @@ def run_ours(args, w):
     def resident_step():
         return step(px_d, src_d, tgt_d)
 
+    # e2e: the host input path of train.py:55-59 through the drop-in's N2 pieces (klab_multimodalmodel_b200.data): every step the raw
+    # fp32 [0, 1] images the reference's loader yields (loader.py:15-16) and the token ids travel from PINNED host memory to the
+    # device on a side stream, one step ahead of the step that consumes them, and the image processor's rescale + normalise runs
+    # on the GPU (klab_image_normalize) instead of the host; the loss is read back with .item() every step (train.py:59)
+    from klab_multimodalmodel_b200.data import DevicePrefetcher, GpuImageProcessor
+    raw_h = torch.rand(px_h.shape, generator=torch.Generator().manual_seed(99 + rank)).pin_memory()
+    proc = GpuImageProcessor(size=tuple(px_h.shape[-2:]))
+
+    def host_batches():
+        while True:
+            yield raw_h, src_h, tgt_h
+
+    def to_device(b):
+        raw, src, tgt = b
+        return proc(raw, return_tensors="pt").to(dev), src.to(dev, non_blocking=True), tgt.to(dev, non_blocking=True)
+
+    feed = DevicePrefetcher(host_batches(), dev, to_device)
+
     def e2e_step():
-        return step(px_h.to(dev, non_blocking=True), src_h.to(dev, non_blocking=True), tgt_h.to(dev, non_blocking=True))
+        images, src, tgt = next(feed)
+        return step(images["pixel_values"], src, tgt)
 
     for _ in range(max(args.warmup, 3)):
         resident_step()
+    e2e_step()
     torch.cuda.synchronize()
     if args.profile_range:                                # ncu --profile-from-start off: exactly the timed steps are profiled
         torch.cuda.profiler.start()
@@ -820,7 +840,9 @@ def run_ours(args, w):
                        "l_tgt": w["l_tgt"], "parallelism": f"dp{world}", "optimizer": ("klab_multimodalmodel_b200.optim.Adam (fused multi-tensor kernel, torch.optim.Adam semantics)" if args.optimizer == "klab"
                                      else "torch.optim.Adam") + " over transformer params (train.py:28)",
                        "dropout": "T5 p=0.1 active (train.py:52)", "l2_flush": "256 MiB buffer zeroed between timed iterations"},
-            "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "path": "pinned host batch (raw fp32 images + int64 ids) -> side-stream H2D one step ahead (DevicePrefetcher) -> rescale + "
+                            "normalise on the GPU (GpuImageProcessor / klab_image_normalize) -> MyModel.forward -> loss.item() -> backward -> Adam"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,

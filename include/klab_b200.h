@@ -189,6 +189,13 @@ int klab_embedding_bwd(void* stream, int dtype, int B, int L, const long long* i
 int klab_patchify(void* stream, int out_dtype, int B, int C, int H, int W, int P, const float* pixels, void* out, long long ldo);
 int klab_patch_merge(void* stream, int dtype, int B, int res, int C, const void* in, void* out, int scatter);
 
+/* ---- N2: the arithmetic of the reference's host-side image processor (/root/reference/train.py:39,55:
+ * AutoImageProcessor -> transformers ViTImageProcessor: rescale by 1/255, then (x - mean[c]) / std[c]) on the device.
+ * in: [B, C, H*W] uint8 (in_is_u8 = 1) or fp32; out fp32, same layout.  mean / std are HOST pointers to C floats (has_norm = 0:
+ * rescale only).  Rounding follows the numpy code it replaces: r = float32(double(x) * rescale); y = (r - mean) / std in fp32. */
+int klab_image_normalize(void* stream, int in_is_u8, int B, int C, long long hw, const void* in, double rescale, const float* mean,
+                         const float* std, int has_norm, float* out);
+
 /* ---- K10 (generic path): cross entropy with ignore_index = -100 over materialised logits
  * (HF/models/t5/modeling_t5.py:1114-1117). stats = {mean loss, #non-ignored rows}.  bwd overwrites the logits
  * with d loss / d logits scaled by *gscale (device scalar, may be NULL = 1). */

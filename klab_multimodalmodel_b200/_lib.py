@@ -80,6 +80,7 @@ SIGNATURES = {
     "klab_embedding_fwd": [_vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _ll, _i, _vp, _ll, _vp],
     "klab_embedding_bwd": [_vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _ll, _i, _vp, _ll],
     "klab_patchify": [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _ll],
+    "klab_image_normalize": [_vp, _i, _i, _i, _ll, _vp, _d, _vp, _vp, _i, _vp],
     "klab_patch_merge": [_vp, _i, _i, _i, _i, _vp, _vp, _i],
     "klab_ce_fwd": [_vp, _i, _ll, _i, _vp, _ll, _vp, _vp, _vp, _vp, _vp],
     "klab_ce_bwd": [_vp, _i, _ll, _i, _vp, _ll, _i, _vp, _vp, _vp, _vp],

@@ -99,6 +99,14 @@ static EncodeTiledFn encode_tiled_fn() {
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                       uint32_t box_cols) {
     EncodeTiledFn fn = encode_tiled_fn();
+    // cuTensorMapEncodeTiled is a DRIVER call: it needs a current context in the calling thread.  The first klab call of a
+    // fresh thread (autograd's backward thread: LMHeadLossFn.backward starts with a TMA-fed GEMM) may arrive before any runtime
+    // call has bound the primary context there (CUDA_ERROR_INVALID_CONTEXT, 201) -- bind it once per thread.
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) {
+        cudaFree(nullptr);
+        ctx_bound = true;
+    }
     if (!fn) {
         set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
         return KLAB_ERR_CUDA;

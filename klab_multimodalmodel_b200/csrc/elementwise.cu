@@ -31,6 +31,44 @@ __global__ void cast_f32_bf16_vec_kernel(const float4* __restrict__ in, uint4* _
 // T5 decoder input embedding with _shift_right fused (HF/models/t5/modeling_t5.py:595-614, :682):
 //   token(b,t) = t == 0 ? start_id : (labels[b,t-1] == -100 ? pad_id : labels[b,t-1]);  out[b,t,:] = table[token,:]
 // shift = 0 gives a plain embedding lookup of ids (frozen text encoder input, decode steps).
+// N2 (/root/reference/train.py:55): the arithmetic of the reference's image processor (transformers ViTImageProcessor:
+// rescale by 1/255 then (x - mean[c]) / std[c]) on the device instead of the host.  Same rounding sequence as the numpy code it
+// replaces: r = float32(double(x) * rescale); y = (r - mean) / std in fp32 with IEEE division (no FMA contraction).
+struct ImgNormArgs {
+    double rescale;
+    float mean[8], std[8];
+    long long hw;
+    int C, has_norm;
+};
+
+template <typename TIn, int V>
+__global__ void __launch_bounds__(256) image_normalize_kernel(const TIn* __restrict__ in, float* __restrict__ out, long long nvec, ImgNormArgs a) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long e0 = i * V;
+        const int c = static_cast<int>((e0 / a.hw) % a.C);             // hw % V == 0 on the vector path: one channel per vector
+        float x[V];
+        if constexpr (V == 4) {
+            if constexpr (sizeof(TIn) == 1) {
+                const uchar4 q = reinterpret_cast<const uchar4*>(in)[i];
+                x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
+            } else {
+                const float4 q = reinterpret_cast<const float4*>(in)[i];
+                x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
+            }
+        } else {
+            x[0] = static_cast<float>(in[i]);
+        }
+        float y[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const float r = __double2float_rn(static_cast<double>(x[k]) * a.rescale);
+            y[k] = a.has_norm ? __fdiv_rn(__fsub_rn(r, a.mean[c]), a.std[c]) : r;
+        }
+        if constexpr (V == 4) reinterpret_cast<float4*>(out)[i] = make_float4(y[0], y[1], y[2], y[3]);
+        else out[i] = y[0];
+    }
+}
+
 template <typename T>
 __global__ void embedding_fwd_kernel(const long long* __restrict__ ids, int B, int L, int shift, int start_id, int pad_id,
                                      const T* __restrict__ table, int d, T* __restrict__ out, long long ldo, long long vocab,
@@ -367,6 +405,34 @@ int klab_embedding_bwd(void* stream, int dtype, int B, int L, const long long* i
         embedding_bwd_kernel<__nv_bfloat16><<<B * L, 128, 0, st>>>(ids, B, L, shift_right, start_id, pad_id, reinterpret_cast<const __nv_bfloat16*>(dout), ldo, d, dtable, vocab);
     else
         embedding_bwd_kernel<float><<<B * L, 128, 0, st>>>(ids, B, L, shift_right, start_id, pad_id, reinterpret_cast<const float*>(dout), ldo, d, dtable, vocab);
+    KLAB_LAUNCH_CHECK();
+    count_launch();
+    return KLAB_OK;
+}
+
+int klab_image_normalize(void* stream, int in_is_u8, int B, int C, long long hw, const void* in, double rescale, const float* mean,
+                         const float* std, int has_norm, float* out) {
+    if (int rc = klab_check_device()) return rc;
+    KLAB_REQUIRE(B > 0 && C > 0 && C <= 8 && hw > 0, "image_normalize: bad shape B=%d C=%d hw=%lld", B, C, hw);
+    ImgNormArgs a{};
+    a.rescale = rescale;
+    a.C = C;
+    a.hw = hw;
+    a.has_norm = has_norm;
+    for (int c = 0; c < C; ++c) {
+        a.mean[c] = has_norm ? mean[c] : 0.0f;
+        a.std[c] = has_norm ? std[c] : 1.0f;
+    }
+    const long long total = static_cast<long long>(B) * C * hw;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool vec = (hw % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & (in_is_u8 ? 3 : 15)) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    if (vec) {
+        if (in_is_u8) image_normalize_kernel<uint8_t, 4><<<grid_for(total / 4, 256), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(in), out, total / 4, a);
+        else image_normalize_kernel<float, 4><<<grid_for(total / 4, 256), 256, 0, st>>>(reinterpret_cast<const float*>(in), out, total / 4, a);
+    } else {
+        if (in_is_u8) image_normalize_kernel<uint8_t, 1><<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const uint8_t*>(in), out, total, a);
+        else image_normalize_kernel<float, 1><<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const float*>(in), out, total, a);
+    }
     KLAB_LAUNCH_CHECK();
     count_launch();
     return KLAB_OK;

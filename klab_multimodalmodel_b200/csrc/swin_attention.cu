@@ -385,6 +385,14 @@ int swin_attention_fwd_tc(cudaStream_t st, int B, int res, int heads, int window
 int swin_attention_bwd_tc(cudaStream_t st, int B, int res, int heads, int window, int shift, const void* q, const void* k, const void* v,
                           long long ld, const void* ctx, const void* dctx, long long ldc, void* dq, void* dk, void* dv,
                           const float* logit_scale, const float* bias, const float* lse, float* dbias, float* dlogit_scale);
+// tensor-core path for windows of 65..144 tokens (swin_attention_tc_big.cu)
+bool swin_attention_big_supported(int dtype, int head_dim, int window, long long ld, long long ldc, const void* q, const void* k,
+                                  const void* v, const void* ctx);
+int swin_attention_fwd_big(cudaStream_t st, int B, int res, int heads, int window, int shift, const void* q, const void* k, const void* v,
+                           long long ld, void* ctx, long long ldc, const float* logit_scale, const float* bias, float* lse);
+int swin_attention_bwd_big(cudaStream_t st, int B, int res, int heads, int window, int shift, const void* q, const void* k, const void* v,
+                           long long ld, const void* ctx, const void* dctx, long long ldc, void* dq, void* dk, void* dv,
+                           const float* logit_scale, const float* bias, const float* lse, float* dbias, float* dlogit_scale);
 }  // namespace klab
 
 using namespace klab;
@@ -408,6 +416,8 @@ int klab_swin_attention_fwd(void* stream, int dtype, int B, int res, int heads, 
     KLAB_REQUIRE(head_dim <= 128, "swin_attention: head_dim %d > 128", head_dim);
     if (!swin_force_generic() && swin_attention_tc_supported(dtype, head_dim, window, ld, ldc, q, k, v, ctx))
         return swin_attention_fwd_tc(static_cast<cudaStream_t>(stream), B, res, heads, window, shift, q, k, v, ld, ctx, ldc, logit_scale, bias, lse);
+    if (!swin_force_generic() && swin_attention_big_supported(dtype, head_dim, window, ld, ldc, q, k, v, ctx))
+        return swin_attention_fwd_big(static_cast<cudaStream_t>(stream), B, res, heads, window, shift, q, k, v, ld, ctx, ldc, logit_scale, bias, lse);
     SwinArgs a{};
     a.q = q; a.k = k; a.v = v; a.out = ctx; a.ld = ld; a.ldc = ldc;
     a.B = B; a.res = res; a.heads = heads; a.d = head_dim; a.w = window; a.shift = shift;
@@ -441,6 +451,10 @@ int klab_swin_attention_bwd(void* stream, int dtype, int B, int res, int heads, 
         (reinterpret_cast<uintptr_t>(dctx) & 15) == 0)
         return swin_attention_bwd_tc(static_cast<cudaStream_t>(stream), B, res, heads, window, shift, q, k, v, ld, ctx, dctx, ldc, dq, dk, dv,
                                      logit_scale, bias, lse, dbias, dlogit_scale);
+    if (!swin_force_generic() && swin_attention_big_supported(dtype, head_dim, window, ld, ldc, q, k, v, ctx) &&
+        (reinterpret_cast<uintptr_t>(dctx) & 15) == 0)
+        return swin_attention_bwd_big(static_cast<cudaStream_t>(stream), B, res, heads, window, shift, q, k, v, ld, ctx, dctx, ldc, dq, dk, dv,
+                                      logit_scale, bias, lse, dbias, dlogit_scale);
     SwinArgs a{};
     a.q = q; a.k = k; a.v = v; a.ctx = ctx; a.dctx = dctx; a.dq = dq; a.dk = dk; a.dv = dv; a.ld = ld; a.ldc = ldc;
     a.B = B; a.res = res; a.heads = heads; a.d = head_dim; a.w = window; a.shift = shift;

@@ -275,6 +275,127 @@ __global__ void __launch_bounds__(NW * 32) t5_attn_bwd_dkv_kernel(AttnArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Decode shape (K14, HF/generation/utils.py:2743-2800 + HF/models/t5/modeling_t5.py:281-305): ONE query row per (batch, head)
+// against the cached keys / values.  The work is reading K and V once (cross-attention: B * Le * 2 * inner bf16 per block and
+// token, the largest HBM stream of a decode step), so the kernel is a bandwidth kernel: one warp per (b, h), 16-byte loads,
+// LPR = d_kv / 8 lanes cover one row and 32 / LPR rows are in flight per load instruction; scores go through a per-warp
+// shared-memory row for the softmax; fp32 arithmetic throughout.  A 128-row tensor-core tile would be > 97 % padding here.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int DEC_WARPS = 4;
+
+template <int LPR>
+__global__ void __launch_bounds__(DEC_WARPS * 32) t5_attn_decode_kernel(AttnArgs a) {
+    extern __shared__ float sm[];
+    constexpr int RPI = 32 / LPR;                 // rows per load instruction
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bh = blockIdx.x * DEC_WARPS + warp;
+    if (bh >= a.B * a.H) return;
+    const int b = bh / a.H, h = bh - b * a.H;
+    const int Lk = a.Lk, dk = a.dk_;
+    float* pw = sm + warp * ((Lk + 3) & ~3);
+    const int sub = lane % LPR, grp = lane / LPR;             // this lane covers columns [8 sub, 8 sub + 8) of row (j0 + grp)
+    const __nv_bfloat16* qp = reinterpret_cast<const __nv_bfloat16*>(a.q) + static_cast<long long>(b) * a.ldq + h * dk + 8 * sub;
+    const __nv_bfloat16* kp = reinterpret_cast<const __nv_bfloat16*>(a.k) + static_cast<long long>(b) * Lk * a.ldk + h * dk + 8 * sub;
+    const __nv_bfloat16* vp = reinterpret_cast<const __nv_bfloat16*>(a.v) + static_cast<long long>(b) * Lk * a.ldv + h * dk + 8 * sub;
+    float q[8];
+    {
+        const uint4 raw = *reinterpret_cast<const uint4*>(qp);
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __bfloat1622float2(h2[i]);
+            q[2 * i] = f.x;
+            q[2 * i + 1] = f.y;
+        }
+    }
+    const int jmax = a.causal ? min(Lk, a.q_offset + 1) : Lk;         // keys [0, jmax) are visible to the single query row
+    // ---- scores
+    float mx = -INFINITY;
+#pragma unroll 4
+    for (int j0 = 0; j0 < jmax; j0 += RPI) {
+        const int j = j0 + grp;
+        float s = 0.0f;
+        if (j < jmax) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(kp + static_cast<long long>(j) * a.ldk));
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __bfloat1622float2(h2[i]);
+                s = fmaf(q[2 * i], f.x, s);
+                s = fmaf(q[2 * i + 1], f.y, s);
+            }
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (j < jmax) {
+            if (a.bias_table) s += a.bias_table[a.rel_bucket[(j - a.q_offset) + a.rel_zero] * a.H + h];
+            if (sub == 0) pw[j] = s;
+            mx = fmaxf(mx, s);
+        }
+    }
+    mx = warp_max(mx);
+    __syncwarp();
+    float sum = 0.0f;
+    for (int j = lane; j < jmax; j += 32) {
+        const float e = __expf(pw[j] - mx);
+        pw[j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+    __syncwarp();
+    if (lane == 0) a.lse[bh] = mx + __logf(sum);
+    // ---- out = P V
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int j0 = 0; j0 < jmax; j0 += RPI) {
+        const int j = j0 + grp;
+        if (j < jmax) {
+            const float p = pw[j];
+            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(vp + static_cast<long long>(j) * a.ldv));
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __bfloat1622float2(h2[i]);
+                acc[2 * i] = fmaf(p, f.x, acc[2 * i]);
+                acc[2 * i + 1] = fmaf(p, f.y, acc[2 * i + 1]);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    if (grp == 0) {
+        uint4 outv;
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&outv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h2[i] = __floats2bfloat162_rn(acc[2 * i] * inv, acc[2 * i + 1] * inv);
+        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(a.out) + static_cast<long long>(b) * a.ldo + h * dk + 8 * sub;
+        *reinterpret_cast<uint4*>(op) = outv;
+    }
+}
+
+bool decode_shape_supported(int dtype, int Lq, int Lk, int dk, long long ldq, long long ldk, long long ldv, long long ldo, const void* q,
+                            const void* k, const void* v, const void* o, float dropout_p) {
+    if (dtype != KLAB_BF16 || Lq != 1 || dropout_p > 0.0f || Lk > 8192) return false;
+    if (dk != 32 && dk != 64 && dk != 128) return false;
+    if ((ldq | ldk | ldv | ldo) & 7) return false;
+    return ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(o)) & 15) == 0;
+}
+
+int launch_decode(cudaStream_t st, const AttnArgs& a) {
+    const size_t smem = sizeof(float) * DEC_WARPS * ((a.Lk + 3) & ~3);
+    const int grid = (a.B * a.H + DEC_WARPS - 1) / DEC_WARPS;
+    if (a.dk_ == 64) t5_attn_decode_kernel<8><<<grid, DEC_WARPS * 32, smem, st>>>(a);
+    else if (a.dk_ == 32) t5_attn_decode_kernel<4><<<grid, DEC_WARPS * 32, smem, st>>>(a);
+    else t5_attn_decode_kernel<16><<<grid, DEC_WARPS * 32, smem, st>>>(a);
+    KLAB_LAUNCH_CHECK();
+    count_launch();
+    return KLAB_OK;
+}
+
 // dtable[bucket, h] += sum over (b, chunk) of partial[(b*H + h)*chunks + chunk][bucket]
 __global__ void t5_dbias_reduce_kernel(const float* __restrict__ part, int B, int H, int chunks, int nb, float* __restrict__ dtable) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -342,6 +463,15 @@ int klab_t5_attention_fwd(void* stream, int dtype, int B, int H, int Lq, int Lk,
                           const unsigned long long* seed_ptr) {
     if (int rc = klab_check_device()) return rc;
     KLAB_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk > 0 && d_kv > 0, "t5_attention_fwd: empty problem");
+    if (decode_shape_supported(dtype, Lq, Lk, d_kv, ldq, ldk, ldv, ldo, q, k, v, out, dropout_p)) {      // Lq = 1: bandwidth kernel
+        AttnArgs a{};
+        a.q = q; a.k = k; a.v = v; a.out = out;
+        a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;
+        a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk; a.dk_ = d_kv;
+        a.bias_table = bias_table; a.rel_bucket = rel_bucket; a.rel_zero = rel_zero; a.num_buckets = num_buckets;
+        a.causal = causal; a.q_offset = q_offset; a.lse = lse;
+        return launch_decode(static_cast<cudaStream_t>(stream), a);
+    }
     if (!force_generic_attention() && t5_attention_tc_supported(dtype, Lq, Lk, d_kv, ldq, ldk, ldv, ldo, q, k, v, out))
         return t5_attention_fwd_tc(static_cast<cudaStream_t>(stream), B, H, Lq, Lk, q, ldq, k, ldk, v, ldv, out, ldo, bias_table,
                                    rel_bucket, rel_zero, num_buckets, causal, q_offset, lse, dropout_p, seed, seed_ptr);

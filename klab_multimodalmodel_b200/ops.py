@@ -376,6 +376,19 @@ def patchify(pixels, patch, dtype):
     return out
 
 
+def image_normalize(images, rescale, mean=None, std=None, out=None):
+    """(B, C, H, W) uint8 or fp32 on the device -> fp32 (x * rescale - mean[c]) / std[c]  (klab_image_normalize)."""
+    assert images.is_cuda and images.is_contiguous() and images.dim() == 4 and images.dtype in (torch.uint8, torch.float32)
+    B, Cc, H, W = images.shape
+    y = torch.empty(B, Cc, H, W, dtype=torch.float32, device=images.device) if out is None else out
+    has = mean is not None
+    m = (C.c_float * Cc)(*[float(v) for v in (mean if has else [0.0] * Cc)])
+    s = (C.c_float * Cc)(*[float(v) for v in (std if has else [1.0] * Cc)])
+    L.check(L.lib().klab_image_normalize(_stream(), int(images.dtype == torch.uint8), B, Cc, H * W, images.data_ptr(), float(rescale), C.cast(m, C.c_void_p),
+                                         C.cast(s, C.c_void_p), int(has), y.data_ptr()))
+    return y
+
+
 def patch_merge(x, B, res, Cc, scatter=False):
     """gather: x [B*res*res, C] -> [B*(res/2)^2, 4C];  scatter: the inverse."""
     assert x.is_contiguous()

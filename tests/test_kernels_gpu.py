@@ -212,6 +212,37 @@ def test_t5_attention(dtype, mode, B, H, Lq, Lk, dk):
         close(dtab, tr.grad, dtype, "t5 dbias")
 
 
+@pytest.mark.parametrize("mode,B,H,Lk,dk,t", [("self", 5, 3, 20, 64, 0), ("self", 5, 3, 20, 64, 7), ("self", 3, 2, 20, 64, 19), ("cross", 4, 12, 96, 64, 0),
+                                              ("cross", 3, 2, 177, 64, 0), ("self", 2, 2, 40, 32, 33), ("cross", 2, 1, 50, 128, 0),
+                                              ("cross", 260, 12, 96, 64, 0)])
+def test_t5_attention_decode_shape(mode, B, H, Lk, dk, t):
+    """K14: one query row per (batch, head) against cached keys / values (the single-token decoder step): the bandwidth-shaped
+    kernel.  self: causal with q_offset = t over a [B, T, 3*inner] cache whose rows beyond t hold stale garbage; cross: all keys."""
+    o = ops()
+    dims = ot5.T5Dims(num_heads=H, d_kv=dk)
+    inner = H * dk
+    dtype = torch.bfloat16
+    cache, cacher = rnd(B * Lk, 3 * inner, dtype=dtype, seed=1, scale=0.5)
+    Q, Qr = rnd(B, inner, dtype=dtype, seed=2, scale=0.5)
+    k, v = cache[:, inner:2 * inner], cache[:, 2 * inner:]
+    table = 0.5 * torch.randn(32, H, generator=torch.Generator().manual_seed(3))
+    if mode == "self":
+        lut, rz = o.t5_rel_bucket_lut(Lk, Lk, bidirectional=False, num_buckets=32, max_distance=128)
+        ctx, lse = o.t5_attention_fwd(Q, k, v, B, H, 1, Lk, dk, bias_table=table.cuda(), lut=lut.cuda(), rel_zero=rz, causal=True, q_offset=t)
+        nk = t + 1
+    else:
+        ctx, lse = o.t5_attention_fwd(Q, k, v, B, H, 1, Lk, dk)
+        nk = Lk
+    kr = cacher[:, inner:2 * inner].view(B, Lk, H, dk)[:, :nk].transpose(1, 2)
+    vr = cacher[:, 2 * inner:].view(B, Lk, H, dk)[:, :nk].transpose(1, 2)
+    s = Qr.view(B, 1, H, dk).transpose(1, 2) @ kr.transpose(-1, -2)                       # [B, H, 1, nk]
+    if mode == "self":
+        s = s + ot5.t5_bias(table, Lk, Lk, bidirectional=False, dims=dims)[None, :, t:t + 1, :nk]
+    ref = (torch.softmax(s, -1) @ vr).transpose(1, 2).reshape(B, inner)
+    close(ctx, ref, dtype, "t5 decode attn")
+    close(lse.view(B, H), torch.logsumexp(s, -1).view(B, H), torch.float32, "t5 decode lse", scale=None)
+
+
 def test_t5_bucket_lut_matches_oracle():
     o = ops()
     for bidir in (True, False):
@@ -226,7 +257,10 @@ def test_t5_bucket_lut_matches_oracle():
 @pytest.mark.parametrize("B,res,heads,hd,w,shift", [(2, 8, 2, 32, 4, 2), (1, 8, 1, 32, 8, 0), (2, 14, 2, 32, 7, 3), (1, 16, 3, 16, 4, 0),
                                                     (24, 32, 3, 32, 8, 4),      # 576 (head, pair) items: persistent CTAs loop, prefetch, and change head mid-range
                                                     (3, 7, 1, 32, 7, 0),        # odd window count: padded second slot
-                                                    (2, 24, 2, 32, 12, 6)])     # 12 x 12 windows (384^2 inputs): CUDA-core kernel, N = 144
+                                                    (2, 24, 2, 32, 12, 6),      # 12 x 12 windows (384^2 inputs), N = 144: two query passes per window
+                                                    (3, 12, 1, 32, 12, 0),      # grid == window: one unshifted 144-token window per image
+                                                    (8, 48, 3, 32, 12, 6),      # 384 (head, window) items: CTAs loop over windows and change head
+                                                    (1, 18, 2, 32, 9, 4), (2, 20, 1, 32, 10, 5), (1, 22, 2, 32, 11, 5)])   # 81 / 100 / 121 tokens: one pass
 def test_swin_attention(dtype, B, res, heads, hd, w, shift):
     o = ops()
     Cc = heads * hd
@@ -555,3 +589,54 @@ def test_dynamic_work_distribution_matches_static():
         assert torch.equal(first, last)
     finally:
         lib.lib().klab_set_dynamic_sched(0)
+
+
+# ------------------------------------------------------------------------------------------------ N2: host input path
+@pytest.mark.parametrize("in_dtype", [torch.uint8, torch.float32])
+@pytest.mark.parametrize("shape", [(3, 3, 256, 256), (2, 3, 7, 9)])
+def test_image_normalize_matches_host_processor(in_dtype, shape):
+    """N2: rescale (1/255) + ImageNet normalise on the device (klab_image_normalize) against the host arithmetic it replaces
+    (/root/reference/train.py:55, transformers ViTImageProcessor): bit-exact with the numpy restatement of the slow processor,
+    within 2e-6 of the installed transformers processor itself (its torch path fuses the two steps)."""
+    from klab_multimodalmodel_b200.data import GpuImageProcessor
+    g = torch.Generator().manual_seed(5)
+    x = torch.randint(0, 256, shape, generator=g).to(torch.uint8) if in_dtype == torch.uint8 else torch.rand(shape, generator=g)
+    proc = GpuImageProcessor.from_pretrained("microsoft/swinv2-base-patch4-window8-256", size=shape[-2:])
+    batch = proc(x, return_tensors="pt").to("cuda")
+    got = batch["pixel_values"]
+    assert got.dtype == torch.float32 and got.is_cuda and got.shape == x.shape
+    ref = proc.preprocess_on_host(x)
+    assert torch.equal(got.cpu(), ref), (got.cpu() - ref).abs().max()
+    # a second batch through the same pinned staging pair, channels-last list input
+    y = [im.permute(1, 2, 0) for im in x] if shape[-1] != 3 else None
+    if y is not None:
+        again = proc(y).to(torch.device("cuda"))["pixel_values"]
+        assert torch.equal(again.cpu(), ref)
+    try:
+        from transformers import ViTImageProcessor
+    except ImportError:
+        return
+    hf = ViTImageProcessor(do_resize=False, image_mean=list(proc.image_mean), image_std=list(proc.image_std))
+    want = hf(x, return_tensors="pt")["pixel_values"]
+    assert (got.cpu() - want).abs().max().item() <= 2e-6 * max(1.0, want.abs().max().item())
+
+
+def test_device_prefetcher_overlaps_and_preserves_order():
+    """N2: batches come out in order, already on the device and normalised, one step of look-ahead on a side stream."""
+    from klab_multimodalmodel_b200.data import DevicePrefetcher, GpuImageProcessor
+    proc = GpuImageProcessor(size=(16, 16))
+    g = torch.Generator().manual_seed(9)
+    host = [(torch.rand(4, 3, 16, 16, generator=g).pin_memory(), torch.randint(0, 100, (4, 5), generator=g).pin_memory()) for _ in range(5)]
+    dev = torch.device("cuda", 0)
+
+    def transform(b):
+        px, ids = b
+        return proc(px).to(dev), {"input_ids": ids.to(dev, non_blocking=True)}
+
+    seen = 0
+    for i, (images, src) in enumerate(DevicePrefetcher(host, dev, transform)):
+        torch.cuda.current_stream().synchronize()
+        assert torch.equal(images["pixel_values"].cpu(), proc.preprocess_on_host(host[i][0]))
+        assert torch.equal(src["input_ids"].cpu(), host[i][1])
+        seen += 1
+    assert seen == 5
