@@ -62,11 +62,15 @@ int klab_set_dynamic_sched(int on);
  *   forward  y = x W^T      : A = x  [M,K] (0), B = W [N,K] (0)
  *   dgrad    dx = dy W      : A = dy [M,N'](0), B = W [N',K'] read as B(n=k', k=n') (1)
  *   wgrad    dW = dy^T x    : A = dy read as A(m=n', k=row) (1), B = x read as B(n=k', k=row) (1)
- * epilogue, in order:  v += bias[n];  aux_out[m,n] = v;  v = act(v) or v *= act'(aux_in[m,n]);
+ * epilogue, in order:  v += bias[n];  aux_out[m,n] = v (GELU_SAVE_GRAD: gelu'(v));  v = act(v) or v *= act'(aux_in[m,n]);
  *                      v *= dropout_keep(seed, m*N+n)/(1-p);  v += residual[m,n];  v += D_old (accumulate);
  * in_dtype KLAB_BF16 runs the tcgen05/TMEM/TMA kernel (requires lda, ldb multiples of 8 and 16-byte
  * aligned bases); in_dtype KLAB_F32 runs the fp32 SIMT kernel (strict parity path). */
-enum { KLAB_ACT_NONE = 0, KLAB_ACT_RELU = 1, KLAB_ACT_GELU = 2, KLAB_ACT_RELU_BWD = 3, KLAB_ACT_GELU_BWD = 4 };
+enum { KLAB_ACT_NONE = 0, KLAB_ACT_RELU = 1, KLAB_ACT_GELU = 2, KLAB_ACT_RELU_BWD = 3, KLAB_ACT_GELU_BWD = 4,
+       /* GELU whose DERIVATIVE is saved: forward writes aux_out = gelu'(pre-activation) (instead of the pre-activation) next to
+        * D = gelu(pre-activation) -- both come out of the same erfc / exp evaluation -- and the backward GEMM only multiplies:
+        * KLAB_ACT_MUL_AUX: v *= aux_in.  Saves the ~19-instruction gelu' evaluation per element in an issue-bound epilogue. */
+       KLAB_ACT_GELU_SAVE_GRAD = 5, KLAB_ACT_MUL_AUX = 6 };
 
 typedef struct klab_gemm_epilogue {
     const float* bias;      /* [N] fp32, or NULL */

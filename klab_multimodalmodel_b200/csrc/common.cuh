@@ -128,6 +128,14 @@ __device__ __forceinline__ void gelu_terms(float x, float& half_erfc, float& u) 
     poly = fmaf(poly, t, 0.254829592f);
     half_erfc = 0.5f * poly * t * u;                       // 0.5 * erfc(|x| / sqrt 2) = 1 - Phi(|x|)
 }
+// gelu(x) and gelu'(x) from ONE erfc / exp evaluation (KLAB_ACT_GELU_SAVE_GRAD)
+__device__ __forceinline__ void gelu_and_grad(float x, float& g, float& gp) {
+    float q, u;
+    gelu_terms(x, q, u);
+    const float cdf = x >= 0.0f ? 1.0f - q : q;
+    g = x * cdf;
+    gp = fmaf(x * 0.39894228040143267794f, u, cdf);
+}
 #ifdef KLAB_EXACT_GELU
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {

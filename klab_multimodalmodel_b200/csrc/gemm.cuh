@@ -137,14 +137,21 @@ __device__ __forceinline__ void epilogue_apply_store(const klab_gemm_epilogue& e
                 if (i < nvalid) v[i] += __ldg(bp + i);
         }
     }
-    if (e.aux_out) store_chunk<CH>(e.aux_out, e.out_dtype, row * e.ld_aux_out + col0, nvalid, v);
+    if (e.act == KLAB_ACT_GELU_SAVE_GRAD) {
+        float gp[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) gelu_and_grad(v[i], v[i], gp[i]);
+        if (e.aux_out) store_chunk<CH>(e.aux_out, e.out_dtype, row * e.ld_aux_out + col0, nvalid, gp);
+    } else if (e.aux_out) {
+        store_chunk<CH>(e.aux_out, e.out_dtype, row * e.ld_aux_out + col0, nvalid, v);
+    }
     if (e.act == KLAB_ACT_RELU) {
 #pragma unroll
         for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.0f);
     } else if (e.act == KLAB_ACT_GELU) {
 #pragma unroll
         for (int i = 0; i < CH; ++i) v[i] = gelu_erf(v[i]);
-    } else if (e.act == KLAB_ACT_RELU_BWD || e.act == KLAB_ACT_GELU_BWD) {
+    } else if (e.act == KLAB_ACT_RELU_BWD || e.act == KLAB_ACT_GELU_BWD || e.act == KLAB_ACT_MUL_AUX) {
         float a[CH];
         if (aux_raw) {
 #pragma unroll
@@ -158,6 +165,9 @@ __device__ __forceinline__ void epilogue_apply_store(const klab_gemm_epilogue& e
         if (e.act == KLAB_ACT_RELU_BWD) {
 #pragma unroll
             for (int i = 0; i < CH; ++i) v[i] = a[i] > 0.0f ? v[i] : 0.0f;
+        } else if (e.act == KLAB_ACT_MUL_AUX) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] *= a[i];
         } else {
 #pragma unroll
             for (int i = 0; i < CH; ++i) v[i] *= gelu_erf_grad(a[i]);

@@ -710,7 +710,7 @@ def _swin_block_fwd_body(x, c, save, *params):
     a = O.linear_fwd(ctxt, w_p, bias=pb)
     h, mean1, rstd1 = O.layernorm_fwd(a, g1, be1, c.eps, residual=x, save_stats=save)       # res-post-norm (:707-708)
     m_pre = torch.empty(x.shape[0], 4 * C_, dtype=cd, device=x.device) if save else None
-    m_act = O.linear_fwd(h, w_f1, bias=f1b, act=L.ACT_GELU, aux_out=m_pre)
+    m_act = O.linear_fwd(h, w_f1, bias=f1b, act=L.ACT_GELU_SAVE_GRAD if save else L.ACT_GELU, aux_out=m_pre)   # m_pre := gelu'(fc1 output)
     m2 = O.linear_fwd(m_act, w_f2, bias=f2b)
     out, mean2, rstd2 = O.layernorm_fwd(m2, g2, be2, c.eps, residual=h, save_stats=save)      # :712
     if not save:
@@ -724,7 +724,7 @@ def _swin_block_bwd_body(dout, x, qkv, bias16, hidden, tab, ctxt, lse, a, mean1,
     C_ = x.shape[1]
     wqkv, w_p, w_f1, w_f2 = _swin_operands(c, params, cd, "peek")
     dm2, dg2, dbe2 = O.layernorm_bwd(dout, m2, g2, mean2, rstd2)
-    dm_pre = O.linear_dgrad(dm2, w_f2, act=L.ACT_GELU_BWD, aux_in=m_pre)
+    dm_pre = O.linear_dgrad(dm2, w_f2, act=L.ACT_MUL_AUX, aux_in=m_pre)                  # m_pre holds gelu'(fc1 output), saved by the forward epilogue
     df2w = _wgrad(dm2, m_act)
     df2b = _colsum(dm2)
     dh = O.linear_dgrad(dm_pre, w_f1, residual=dout)                     # + residual path of the second norm

@@ -19,14 +19,16 @@ torch.manual_seed(0)
 B = 64
 
 
-def swin_case(stage):
+def swin_case(stage, big=False):
     res, C, heads = [(64, 128, 4), (32, 256, 8), (16, 512, 16), (8, 1024, 32)][stage]
     w, shift, hd = 8, (4 if res > 8 else 0), 32
+    if big:                                                    # 384^2 inputs, 12 x 12 windows (bench workload 4a)
+        res, w, shift = res * 3 // 2, 12, (6 if res > 8 else 0)
     T = B * res * res
     qkv = torch.randn(T, 3 * C, device=dev).bfloat16()
     q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
     ls = torch.full((heads,), 2.3, device=dev)
-    bias = torch.randn(heads, 64, 64, device=dev)
+    bias = torch.randn(heads, w * w, w * w, device=dev)
     ctx, lse = O.swin_attention_fwd(q, k, v, B, res, heads, hd, w, shift, ls, bias)
     dctx = torch.randn_like(ctx)
     dqkv = torch.empty_like(qkv)
@@ -75,6 +77,15 @@ if a.time:
         f, b = swin_case(st)
         timed(f"swin stage {st + 1} fwd", f)
         timed(f"swin stage {st + 1} bwd", b)
+    for st in range(4):
+        f, b = swin_case(st, big=True)
+        timed(f"swin 384/w12 stage {st + 1} fwd", f)
+        timed(f"swin 384/w12 stage {st + 1} bwd", b)
+    for name, (Lq, Lk, causal, hb) in {"t5 enc self 176x176": (176, 176, False, True), "t5 dec self 128x128 causal": (128, 128, True, True),
+                                       "t5 cross 128x176": (128, 176, False, False)}.items():
+        f, b = t5_case(Lq, Lk, causal, hb)
+        timed(name + " fwd", f)
+        timed(name + " bwd", b)
     for name, (Lq, Lk, causal, hb) in {"t5 enc self 96x96": (96, 96, False, True), "t5 frozen enc 32x32": (32, 32, False, True),
                                        "t5 dec self 32x32 causal": (32, 32, True, True), "t5 cross 32x96": (32, 96, False, False)}.items():
         f, b = t5_case(Lq, Lk, causal, hb)

@@ -85,6 +85,15 @@ def test_gemm_epilogues(dtype):
     x = Hr.clone().requires_grad_(True)
     F.gelu(x).backward(base)
     close(d4, x.grad, dtype, "gelu_bwd")
+    # GELU whose derivative is saved by the forward epilogue, and the multiply-only backward epilogue that consumes it
+    gp = torch.empty(M, N, dtype=dtype, device="cuda")
+    d6 = o.gemm(A, B, M, N, K, bias=bias.cuda(), act=lib.ACT_GELU_SAVE_GRAD, aux_out=gp)
+    xg = (base + bias).clone().requires_grad_(True)
+    F.gelu(xg).sum().backward()
+    close(d6, F.gelu(base + bias), dtype, "gelu (save grad)")
+    close(gp, xg.grad, dtype, "saved gelu'")
+    d7 = o.gemm(A, B, M, N, K, act=lib.ACT_MUL_AUX, aux_in=H)
+    close(d7, base * Hr, dtype, "mul_aux")
     # padded leading dimension (vocab not a multiple of 8)
     d5 = o.gemm(A, B, M, N - 3, K, ldd_pad=N)
     close(d5, base[:, :N - 3], dtype, "ldd_pad")

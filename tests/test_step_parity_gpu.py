@@ -210,15 +210,13 @@ def _hf_gpu_grads(case, sds, swin, t5, px, src, tgt, autocast):
     return out, grads
 
 
-def _grad_errors(get, leaves):
-    """per-tensor Frobenius-relative errors (sorted, worst first) and the error of all gradients taken as one vector"""
+def _grad_errors(grads, leaves):
+    """per-tensor Frobenius-relative errors (sorted, worst first) and the error of all gradients taken as one vector; `grads`:
+    (scope, name) -> gradient of every parameter of the implementation under test (tied tensors appear once)"""
     errs, num, den = [], 0.0, 0.0
-    for key, leaf in leaves.items():
-        ref = leaf.grad
-        if ref is None:
-            continue
-        g = get(key)
-        assert g is not None and torch.isfinite(g).all(), key
+    for key, g in grads.items():
+        ref = leaves[key].grad
+        assert ref is not None and torch.isfinite(g).all(), key
         d2, r2 = (g - ref).double().pow(2).sum().item(), ref.double().pow(2).sum().item()
         num, den = num + d2, den + r2
         errs.append(((d2 / max(r2, 1e-60)) ** 0.5, ".".join(key)))
@@ -252,7 +250,7 @@ def test_full_width_step_swin_b_t5_large_bf16():
     torch.cuda.empty_cache()
     ref_loss, leaves = oracle_grads(case, sds, swin, t5, px, src, tgt)
     assert abs(loss_v - ref_loss) <= 1e-2 * abs(ref_loss), (loss_v, ref_loss)
-    errs, whole = _grad_errors(ours.get, leaves)
+    errs, whole = _grad_errors(ours, leaves)
     within = sum(e <= 1e-2 for e, _ in errs)
     print(f"[full width 2a, B=2, bf16] loss {loss_v:.5f} vs fp32 oracle {ref_loss:.5f} (rel {abs(loss_v - ref_loss) / abs(ref_loss):.1e}); "
           f"all gradients as one vector: rel err {whole:.2e}; per tensor: median {errs[len(errs) // 2][0]:.2e}, {within}/{len(errs)} within 1e-2, "
@@ -266,12 +264,12 @@ def test_full_width_step_swin_b_t5_large_bf16():
         have_hf = False
     if have_hf:
         l32, g32 = _hf_gpu_grads(case, sds, swin, t5, px, src, tgt, autocast=False)
-        e32, w32 = _grad_errors(g32.get, leaves)
+        e32, w32 = _grad_errors(g32, leaves)
         print(f"[full width] transformers fp32 on the GPU vs the host oracle: loss rel {abs(l32 - ref_loss) / abs(ref_loss):.1e}, gradients as one "
               f"vector {w32:.2e}, worst tensor {e32[0][0]:.2e} at {e32[0][1]}")
         assert abs(l32 - ref_loss) <= 1e-4 * abs(ref_loss) and w32 <= 1e-3          # the oracle IS the reference at full width
         l16, g16 = _hf_gpu_grads(case, sds, swin, t5, px, src, tgt, autocast=True)
-        e16, hf_whole = _grad_errors(g16.get, leaves)
+        e16, hf_whole = _grad_errors(g16, leaves)
         hf_median = e16[len(e16) // 2][0]
         print(f"[full width] transformers under torch.autocast(bfloat16) vs the oracle: loss rel {abs(l16 - ref_loss) / abs(ref_loss):.1e}, gradients as "
               f"one vector {hf_whole:.2e}, per tensor median {hf_median:.2e}, {sum(e <= 1e-2 for e, _ in e16)}/{len(e16)} within 1e-2, worst {e16[0][0]:.2e} at {e16[0][1]}")
