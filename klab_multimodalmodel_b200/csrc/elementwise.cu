@@ -315,9 +315,22 @@ __global__ void __launch_bounds__(256) greedy_step_kernel(const float* __restric
     const float* lr = logits + static_cast<long long>(b) * ld;
     float best = -INFINITY;
     int besti = V;
-    for (int c = threadIdx.x; c < V; c += blockDim.x) {
-        const float v = lr[c];
-        if (v > best || (v == best && c < besti)) { best = v; besti = c; }
+    if ((V & 3) == 0 && (reinterpret_cast<uintptr_t>(lr) & 15) == 0) {     // 16-byte loads, four in flight per thread
+        const float4* lr4 = reinterpret_cast<const float4*>(lr);
+        const int n4 = V >> 2;
+#pragma unroll 4
+        for (int c4 = threadIdx.x; c4 < n4; c4 += blockDim.x) {
+            const float4 q = __ldg(lr4 + c4);
+            const float vv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)                                  // indices rise within a thread: strict > keeps the first maximum
+                if (vv[i] > best) { best = vv[i]; besti = 4 * c4 + i; }
+        }
+    } else {
+        for (int c = threadIdx.x; c < V; c += blockDim.x) {
+            const float v = lr[c];
+            if (v > best || (v == best && c < besti)) { best = v; besti = c; }
+        }
     }
     bv[threadIdx.x] = best;
     bi[threadIdx.x] = besti;

@@ -714,8 +714,12 @@ int gemm_tc_launch(cudaStream_t stream, int M, int N, int K, const void* A, long
                  "gemm(bf16): operand base pointers must be 16-byte aligned");
     // split-K is used for weight gradients: an fp32 output and a linear epilogue
     Workspace* w = nullptr;
-    const bool splittable = epi.act == KLAB_ACT_NONE && !epi.bias && !epi.residual && !epi.aux_out && epi.dropout_p == 0.0f &&
-                            epi.out_dtype == KLAB_F32;
+    // ... and for skinny problems (single-token decode: M = batch <= 512): every CTA of a 128-row tile re-reads the same rows of A, so
+    // a long K loop is serial ingest of one SM (0.3 us per k-block: 17 us for K = 3072); splitting K spreads it over the idle
+    // SMs.  The reduce kernel applies the whole epilogue (bias / activation / residual / output dtype) except dropout.
+    const bool skinny = M <= 512 && K >= 1536 && epi.dropout_p == 0.0f && !epi.aux_out && !epi.accumulate;
+    const bool splittable = (epi.act == KLAB_ACT_NONE && !epi.bias && !epi.residual && !epi.aux_out && epi.dropout_p == 0.0f &&
+                             epi.out_dtype == KLAB_F32) || skinny;
     if (splittable) w = get_workspace(stream);
     // the pair kernel distributes work statically: not while the data-parallel reducer has switched dynamic distribution on
     const bool pair_ok = cta_pairs_enabled() && M > BM && sched_slot_enabled() == 0 && sm_count() == sm_count_physical();

@@ -279,95 +279,101 @@ __global__ void __launch_bounds__(NW * 32) t5_attn_bwd_dkv_kernel(AttnArgs a) {
 // Decode shape (K14, HF/generation/utils.py:2743-2800 + HF/models/t5/modeling_t5.py:281-305): ONE query row per (batch, head)
 // against the cached keys / values.  The work is reading K and V once (cross-attention: B * Le * 2 * inner bf16 per block and
 // token, the largest HBM stream of a decode step), so the kernel is a bandwidth kernel: one warp per (b, h), 16-byte loads,
-// LPR = d_kv / 8 lanes cover one row and 32 / LPR rows are in flight per load instruction; scores go through a per-warp
-// shared-memory row for the softmax; fp32 arithmetic throughout.  A 128-row tensor-core tile would be > 97 % padding here.
+// LPR = d_kv / 8 lanes cover one row and 32 / LPR rows are in flight per load instruction; online softmax over chunks of keys
+// whose K and V rows are requested together; fp32 arithmetic throughout.  A 128-row tensor-core tile would be > 97 % padding here.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int DEC_WARPS = 4;
 
+__device__ __forceinline__ void unpack8_bf16(uint4 raw, float* f) {
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t = __bfloat1622float2(h2[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+
 template <int LPR>
 __global__ void __launch_bounds__(DEC_WARPS * 32) t5_attn_decode_kernel(AttnArgs a) {
-    extern __shared__ float sm[];
-    constexpr int RPI = 32 / LPR;                 // rows per load instruction
+    constexpr int RPI = 32 / LPR;                 // key rows covered by one load instruction of the warp
+    constexpr int CH = 8;                         // load instructions per chunk: RPI * CH keys are in flight per warp (K and V together)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bh = blockIdx.x * DEC_WARPS + warp;
     if (bh >= a.B * a.H) return;
     const int b = bh / a.H, h = bh - b * a.H;
     const int Lk = a.Lk, dk = a.dk_;
-    float* pw = sm + warp * ((Lk + 3) & ~3);
-    const int sub = lane % LPR, grp = lane / LPR;             // this lane covers columns [8 sub, 8 sub + 8) of row (j0 + grp)
+    const int sub = lane % LPR, grp = lane / LPR;             // this lane covers columns [8 sub, 8 sub + 8) of row (j0 + c RPI + grp)
     const __nv_bfloat16* qp = reinterpret_cast<const __nv_bfloat16*>(a.q) + static_cast<long long>(b) * a.ldq + h * dk + 8 * sub;
     const __nv_bfloat16* kp = reinterpret_cast<const __nv_bfloat16*>(a.k) + static_cast<long long>(b) * Lk * a.ldk + h * dk + 8 * sub;
     const __nv_bfloat16* vp = reinterpret_cast<const __nv_bfloat16*>(a.v) + static_cast<long long>(b) * Lk * a.ldv + h * dk + 8 * sub;
     float q[8];
-    {
-        const uint4 raw = *reinterpret_cast<const uint4*>(qp);
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2 f = __bfloat1622float2(h2[i]);
-            q[2 * i] = f.x;
-            q[2 * i + 1] = f.y;
-        }
-    }
+    unpack8_bf16(*reinterpret_cast<const uint4*>(qp), q);
     const int jmax = a.causal ? min(Lk, a.q_offset + 1) : Lk;         // keys [0, jmax) are visible to the single query row
-    // ---- scores
-    float mx = -INFINITY;
-#pragma unroll 4
-    for (int j0 = 0; j0 < jmax; j0 += RPI) {
-        const int j = j0 + grp;
-        float s = 0.0f;
-        if (j < jmax) {
-            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(kp + static_cast<long long>(j) * a.ldk));
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = __bfloat1622float2(h2[i]);
-                s = fmaf(q[2 * i], f.x, s);
-                s = fmaf(q[2 * i + 1], f.y, s);
-            }
-        }
-#pragma unroll
-        for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (j < jmax) {
-            if (a.bias_table) s += a.bias_table[a.rel_bucket[(j - a.q_offset) + a.rel_zero] * a.H + h];
-            if (sub == 0) pw[j] = s;
-            mx = fmaxf(mx, s);
-        }
-    }
-    mx = warp_max(mx);
-    __syncwarp();
-    float sum = 0.0f;
-    for (int j = lane; j < jmax; j += 32) {
-        const float e = __expf(pw[j] - mx);
-        pw[j] = e;
-        sum += e;
-    }
-    sum = warp_sum(sum);
-    const float inv = 1.0f / sum;
-    __syncwarp();
-    if (lane == 0) a.lse[bh] = mx + __logf(sum);
-    // ---- out = P V
+    // online softmax over chunks of RPI * CH keys: the K and V rows of a chunk are requested together (one latency per chunk)
+    float m = -INFINITY, l = 0.0f;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-    for (int j0 = 0; j0 < jmax; j0 += RPI) {
-        const int j = j0 + grp;
-        if (j < jmax) {
-            const float p = pw[j];
-            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(vp + static_cast<long long>(j) * a.ldv));
-            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    for (int j0 = 0; j0 < jmax; j0 += RPI * CH) {
+        uint4 kraw[CH], vraw[CH];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = __bfloat1622float2(h2[i]);
-                acc[2 * i] = fmaf(p, f.x, acc[2 * i]);
-                acc[2 * i + 1] = fmaf(p, f.y, acc[2 * i + 1]);
+        for (int c = 0; c < CH; ++c) {
+            const int j = j0 + c * RPI + grp;
+            if (j < jmax) {
+                kraw[c] = __ldg(reinterpret_cast<const uint4*>(kp + static_cast<long long>(j) * a.ldk));
+                vraw[c] = __ldg(reinterpret_cast<const uint4*>(vp + static_cast<long long>(j) * a.ldv));
+            } else {
+                kraw[c] = make_uint4(0, 0, 0, 0);
+                vraw[c] = make_uint4(0, 0, 0, 0);
             }
         }
-    }
+        float sc[CH];
+        float cm = -INFINITY;
 #pragma unroll
-    for (int o = LPR; o < 32; o <<= 1)
+        for (int c = 0; c < CH; ++c) {
+            const int j = j0 + c * RPI + grp;
+            float kf[8];
+            unpack8_bf16(kraw[c], kf);
+            float t = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t = fmaf(q[i], kf[i], t);
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (j < jmax) {
+                if (a.bias_table) t += __ldg(a.bias_table + __ldg(a.rel_bucket + (j - a.q_offset) + a.rel_zero) * a.H + h);
+                cm = fmaxf(cm, t);
+            } else {
+                t = -INFINITY;
+            }
+            sc[c] = t;
+        }
+#pragma unroll
+        for (int o = LPR; o < 32; o <<= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, o));
+        const float m_new = fmaxf(m, cm);                             // finite: every chunk holds at least one visible key
+        const float corr = __expf(m - m_new);                        // first chunk: exp(-inf) = 0
+        l *= corr;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] *= corr;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const float p = __expf(sc[c] - m_new);                   // masked rows: exp(-inf) = 0
+            l += p;
+            float vf[8];
+            unpack8_bf16(vraw[c], vf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaf(p, vf[i], acc[i]);
+        }
+        m = m_new;
+    }
+    // combine the row groups of the warp (lanes with the same `sub` hold partial sums over different keys)
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+        l += __shfl_xor_sync(0xffffffffu, l, o);
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    }
+    if (lane == 0) a.lse[bh] = m + __logf(l);
     if (grp == 0) {
+        const float inv = 1.0f / l;
         uint4 outv;
         __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&outv);
 #pragma unroll
@@ -386,11 +392,10 @@ bool decode_shape_supported(int dtype, int Lq, int Lk, int dk, long long ldq, lo
 }
 
 int launch_decode(cudaStream_t st, const AttnArgs& a) {
-    const size_t smem = sizeof(float) * DEC_WARPS * ((a.Lk + 3) & ~3);
     const int grid = (a.B * a.H + DEC_WARPS - 1) / DEC_WARPS;
-    if (a.dk_ == 64) t5_attn_decode_kernel<8><<<grid, DEC_WARPS * 32, smem, st>>>(a);
-    else if (a.dk_ == 32) t5_attn_decode_kernel<4><<<grid, DEC_WARPS * 32, smem, st>>>(a);
-    else t5_attn_decode_kernel<16><<<grid, DEC_WARPS * 32, smem, st>>>(a);
+    if (a.dk_ == 64) t5_attn_decode_kernel<8><<<grid, DEC_WARPS * 32, 0, st>>>(a);
+    else if (a.dk_ == 32) t5_attn_decode_kernel<4><<<grid, DEC_WARPS * 32, 0, st>>>(a);
+    else t5_attn_decode_kernel<16><<<grid, DEC_WARPS * 32, 0, st>>>(a);
     KLAB_LAUNCH_CHECK();
     count_launch();
     return KLAB_OK;

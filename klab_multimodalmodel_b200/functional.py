@@ -211,6 +211,9 @@ def _backward_phase(fn):
     return wrapped
 
 
+ACCUMULATE_IN_PLACE = os.environ.get("KLAB_GRAD_ACCUMULATE_IN_PLACE", "1") != "0"
+
+
 def _grad_outputs(outs, graphed):
     """Gradients handed back to autograd.  A captured region returns the SAME static tensors on every replay, and its tuple
     keeps a reference to them, so AccumulateGrad (which only adopts a gradient nobody else holds) would clone every parameter
@@ -718,35 +721,57 @@ def _swin_block_fwd_body(x, c, save, *params):
     return (out, qkv, bias16, hidden, tab, ctxt, lse, a, mean1, rstd1, h, m_pre, m_act, m2, mean2, rstd2)
 
 
-def _swin_block_bwd_body(dout, x, qkv, bias16, hidden, tab, ctxt, lse, a, mean1, rstd1, h, m_pre, m_act, m2, mean2, rstd2, c, *params):
+_N_SWIN_ACTS = 15
+_N_SWIN_GRADS = 19            # one per parameter of a block, in flat_params() order
+
+
+def _swin_block_bwd_body(dout, x, *rest):
+    """rest = saved activations (15), [accumulators (21): the static outputs of an earlier run of this region,] c, params (19)
+    -> (dx, 19 parameter gradients, dwqkv, dbqkv).  The last two are the buffers the q / k / v weight and bias gradients are
+    views of.  With accumulators every parameter gradient is ADDED into the given buffer by the kernel that produces it (GEMM
+    epilogue / norm / colsum / CPB kernels all have an accumulate mode) and the same buffers are returned."""
+    (qkv, bias16, hidden, tab, ctxt, lse, a, mean1, rstd1, h, m_pre, m_act, m2, mean2, rstd2), rest = rest[:_N_SWIN_ACTS], rest[_N_SWIN_ACTS:]
+    acc = len(rest) > 1 + _N_SWIN_GRADS
+    if acc:
+        go, rest = rest[:_N_SWIN_GRADS + 2], rest[_N_SWIN_GRADS + 2:]
+        (o_ls, o_w1, o_b1, o_w2, _gq, _gbq, _gk, _gv, _gbv, o_pw, o_pb, o_g1, o_be1, o_f1w, o_f1b, o_f2w, o_f2b, o_g2, o_be2, o_wqkv, o_bqkv) = go
+    c, params = rest[0], rest[1:]
     (ls, w1, b1, w2, qw, qb, kw, vw, vb, pw, pb, g1, be1, f1w, f1b, f2w, f2b, g2, be2) = params
     cd = x.dtype
     C_ = x.shape[1]
     wqkv, w_p, w_f1, w_f2 = _swin_operands(c, params, cd, "peek")
-    dm2, dg2, dbe2 = O.layernorm_bwd(dout, m2, g2, mean2, rstd2)
+
+    def into(t):                                                         # keyword arguments of an accumulating GEMM / colsum
+        return dict(out=t, accumulate=True) if acc else {}
+
+    dm2, dg2, dbe2 = O.layernorm_bwd(dout, m2, g2, mean2, rstd2, **(dict(dgamma=o_g2, dbeta=o_be2) if acc else {}))
     dm_pre = O.linear_dgrad(dm2, w_f2, act=L.ACT_MUL_AUX, aux_in=m_pre)                  # m_pre holds gelu'(fc1 output), saved by the forward epilogue
-    df2w = _wgrad(dm2, m_act)
-    df2b = _colsum(dm2)
+    df2w = _wgrad(dm2, m_act, **(into(o_f2w) if acc else {}))
+    df2b = _Side.run(O.colsum, dm2, **(dict(out=o_f2b) if acc else {}))
     dh = O.linear_dgrad(dm_pre, w_f1, residual=dout)                     # + residual path of the second norm
-    df1w = _wgrad(dm_pre, h)
-    df1b = _colsum(dm_pre)
-    da, dg1, dbe1 = O.layernorm_bwd(dh, a, g1, mean1, rstd1)
+    df1w = _wgrad(dm_pre, h, **(into(o_f1w) if acc else {}))
+    df1b = _Side.run(O.colsum, dm_pre, **(dict(out=o_f1b) if acc else {}))
+    da, dg1, dbe1 = O.layernorm_bwd(dh, a, g1, mean1, rstd1, **(dict(dgamma=o_g1, dbeta=o_be1) if acc else {}))
     dctx = O.linear_dgrad(da, w_p)
-    dpw = _wgrad(da, ctxt)
-    dpb = _colsum(da)
+    dpw = _wgrad(da, ctxt, **(into(o_pw) if acc else {}))
+    dpb = _Side.run(O.colsum, da, **(dict(out=o_pb) if acc else {}))
     dqkv = torch.empty_like(qkv)
     q, k, v = qkv[:, :C_], qkv[:, C_:2 * C_], qkv[:, 2 * C_:]
     lsv = ls.detach().reshape(-1)
     dbias, dls = O.swin_attention_bwd(q, k, v, ctxt, dctx, dqkv[:, :C_], dqkv[:, C_:2 * C_], dqkv[:, 2 * C_:], c.B, c.res,
                                       c.heads, c.hd, c.w, c.shift, lsv, bias16, lse)
+    if acc:
+        O.colsum(dls.view(1, -1), out=o_ls.view(-1))                     # o_ls += dls (a one-row column sum)
+        dls = o_ls.view(-1)
     w2d = w2.detach()                                                    # position-bias MLP gradients: off the critical path
-    dw1, db1, dw2 = _Side.run(lambda *_: O.swin_cpb_bwd(c.coords, c.index, w2d, hidden, tab, dbias, c.heads, c.N), dbias, hidden, tab, w2d)
+    dw1, db1, dw2 = _Side.run(lambda *_: O.swin_cpb_bwd(c.coords, c.index, w2d, hidden, tab, dbias, c.heads, c.N,
+                                                         acc_into=(o_w1, o_b1, o_w2) if acc else None), dbias, hidden, tab, w2d)
     dx = O.linear_dgrad(dqkv, wqkv, residual=dh)                          # + residual path of the first norm
-    dwqkv = _wgrad(dqkv, x)
-    dbqkv = _colsum(dqkv)
+    dwqkv = _wgrad(dqkv, x, **(into(o_wqkv) if acc else {}))
+    dbqkv = _Side.run(O.colsum, dqkv, **(dict(out=o_bqkv) if acc else {}))
     _Side.join()
     return (dx, dls.view(ls.shape), dw1, db1, dw2, dwqkv[:C_], dbqkv[:C_], dwqkv[C_:2 * C_], dwqkv[2 * C_:], dbqkv[2 * C_:],
-            dpw, dpb, dg1, dbe1, df1w, df1b, df2w, df2b, dg2, dbe2)
+            dpw, dpb, dg1, dbe1, df1w, df1b, df2w, df2b, dg2, dbe2, dwqkv, dbqkv)
 
 
 class SwinBlockFn(torch.autograd.Function):
@@ -777,11 +802,28 @@ class SwinBlockFn(torch.autograd.Function):
         c = ctx.c
         x, *params = ctx.saved_tensors
         acts, ctx.acts = ctx.acts, None
-        if ctx.graphed:
-            _detach_aliased_grads(params)
-        outs, graphed = POOL.run(("swb", id(c)), _swin_block_bwd_body, (dout.contiguous(), x) + tuple(acts), (c,) + tuple(params),
-                                 allow_graph=ctx.graphed)
+        # The reference's optimizer does not own the image model (train.py:28), so with --image_model_train its gradients are
+        # never zeroed and accumulate step after step: autograd would run one `grad += new` kernel per
+        # parameter per step (456 tiny launches).  When every parameter's .grad still IS the static gradient buffer this region
+        # handed out last time, the accumulating variant of the region adds the new gradients into those buffers inside the
+        # kernels that produce them, .grad is reset, and autograd re-adopts the very same buffers: no copies, no add kernels,
+        # hooks (the data-parallel reducer) fire as usual.
+        prev = getattr(c, "bwd_static", None)
+        use_acc = (ctx.graphed and prev is not None and ACCUMULATE_IN_PLACE and
+                   all(p.grad is not None and p.grad.data_ptr() == o.data_ptr() and p.grad.shape == o.shape
+                       for p, o in zip(params, prev[1:1 + _N_SWIN_GRADS])))
+        if use_acc:
+            for p in params:
+                p.grad = None
+            outs, graphed = POOL.run(("swba", id(c)), _swin_block_bwd_body, (dout.contiguous(), x) + tuple(acts) + tuple(prev[1:]),
+                                     (c,) + tuple(params), allow_graph=True)
+        else:
+            if ctx.graphed:
+                _detach_aliased_grads(params)
+            outs, graphed = POOL.run(("swb", id(c)), _swin_block_bwd_body, (dout.contiguous(), x) + tuple(acts), (c,) + tuple(params),
+                                     allow_graph=ctx.graphed)
+            c.bwd_static = outs if graphed else None
         tok, ctx.token = getattr(ctx, "token", None), None
         if tok is not None:
             tok.release()
-        return (None,) + _grad_outputs(outs, graphed)
+        return (None,) + _grad_outputs(outs[:1 + _N_SWIN_GRADS], graphed or use_acc)

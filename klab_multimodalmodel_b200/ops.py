@@ -183,16 +183,20 @@ def layernorm_fwd(x, gamma, beta, eps, residual=None, *, out=None, out_rows_per_
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, *, dy_ld=None, dy_rows_per_group=0, dy_group_stride=0):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, *, dy_ld=None, dy_rows_per_group=0, dy_group_stride=0, dgamma=None, dbeta=None):
+    """dgamma / dbeta given: the parameter gradients are ACCUMULATED into them (both or neither)."""
     rows, d = x.shape
     dx = torch.empty(rows, d, dtype=x.dtype, device=x.device)
-    dgamma = torch.empty(d, dtype=torch.float32, device=x.device)
-    dbeta = torch.empty(d, dtype=torch.float32, device=x.device)
+    acc = dgamma is not None
+    assert acc == (dbeta is not None)
+    if not acc:
+        dgamma = torch.empty(d, dtype=torch.float32, device=x.device)
+        dbeta = torch.empty(d, dtype=torch.float32, device=x.device)
     ws = _bytes(L.lib().klab_norm_bwd_workspace_bytes(rows, d), x.device)
     L.check(L.lib().klab_layernorm_bwd(_stream(), _DT[x.dtype], rows, d, dy.data_ptr(), dy.stride(0) if dy_ld is None else dy_ld,
                                        dy_rows_per_group, dy_group_stride, x.data_ptr(), x.stride(0), gamma.data_ptr(),
                                        mean.data_ptr(), rstd.data_ptr(), _p(dres), dres.stride(0) if dres is not None else 0,
-                                       dx.data_ptr(), dx.stride(0), dgamma.data_ptr(), dbeta.data_ptr(), 0, ws.data_ptr()))
+                                       dx.data_ptr(), dx.stride(0), dgamma.data_ptr(), dbeta.data_ptr(), int(acc), ws.data_ptr()))
     return dx, dgamma, dbeta
 
 
@@ -291,16 +295,20 @@ def swin_cpb_fwd(coords, index, w1, b1, w2, heads, n_tokens):
     return bias, hidden, tab
 
 
-def swin_cpb_bwd(coords, index, w2, hidden, tab, dbias, heads, n_tokens):
+def swin_cpb_bwd(coords, index, w2, hidden, tab, dbias, heads, n_tokens, acc_into=None):
+    """acc_into = (dw1, db1, dw2): the gradients are ACCUMULATED into these tensors instead of freshly allocated ones."""
     T, U = coords.shape[0], hidden.shape[1]
     dev = coords.device
     dtab = torch.empty(T, heads, dtype=torch.float32, device=dev)
-    dw1 = torch.empty(U, 2, dtype=torch.float32, device=dev)
-    db1 = torch.empty(U, dtype=torch.float32, device=dev)
-    dw2 = torch.empty(heads, U, dtype=torch.float32, device=dev)
+    if acc_into is None:
+        dw1 = torch.empty(U, 2, dtype=torch.float32, device=dev)
+        db1 = torch.empty(U, dtype=torch.float32, device=dev)
+        dw2 = torch.empty(heads, U, dtype=torch.float32, device=dev)
+    else:
+        dw1, db1, dw2 = acc_into
     L.check(L.lib().klab_swin_cpb_bwd(_stream(), T, U, heads, n_tokens, coords.data_ptr(), index.data_ptr(), w2.data_ptr(),
                                       hidden.data_ptr(), tab.data_ptr(), dbias.data_ptr(), dtab.data_ptr(), dw1.data_ptr(),
-                                      db1.data_ptr(), dw2.data_ptr(), 0))
+                                      db1.data_ptr(), dw2.data_ptr(), int(acc_into is not None)))
     return dw1, db1, dw2
 
 

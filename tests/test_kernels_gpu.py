@@ -99,6 +99,33 @@ def test_gemm_epilogues(dtype):
     close(d5, base[:, :N - 3], dtype, "ldd_pad")
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 768, 3072), (40, 136, 2048), (512, 2304, 1536)])
+def test_gemm_skinny_split_k_with_epilogue(M, N, K):
+    """Single-token decode GEMMs (M = batch): K is split across CTAs and the reduce kernel applies the whole epilogue
+    (bias, ReLU, residual, bf16 output).  Same result as the unsplit kernel, to fp32-accumulation accuracy."""
+    import ctypes as C
+    o, lib = ops(), L()
+    A, Ar = rnd(M, K, dtype=torch.bfloat16, seed=1)
+    B, Br = rnd(N, K, dtype=torch.bfloat16, seed=2, scale=K ** -0.5)
+    R, Rr = rnd(M, N, dtype=torch.bfloat16, seed=3)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(4))
+    ref = torch.relu(Ar @ Br.t() + bias) + Rr
+    outs = {}
+    for name, force in (("auto", (-1, -1, -1)), ("split", (-1, -1, 6)), ("nosplit", (-1, -1, 1))):
+        lib.lib().klab_gemm_set_force(*force)
+        try:
+            outs[name] = o.gemm(A, B, M, N, K, bias=bias.cuda(), act=lib.ACT_RELU, residual=R)
+            bn, sp, c2 = C.c_int(0), C.c_int(0), C.c_int(0)
+            lib.lib().klab_gemm_last_config(C.byref(bn), C.byref(sp), C.byref(c2))
+            if name == "split":
+                assert sp.value >= 2, "split-K was not used for a skinny GEMM"
+            if name == "nosplit":
+                assert sp.value == 1
+        finally:
+            lib.lib().klab_gemm_set_force(-1, -1, -1)
+        close(outs[name], ref, torch.bfloat16, f"skinny gemm ({name})")
+
+
 def test_gemm_dropout_consistency():
     """The epilogue dropout mask depends only on (seed, element index): the bf16 tcgen05 kernel and the fp32 SIMT kernel
     drop the same elements, and about p of them."""
@@ -649,3 +676,33 @@ def test_device_prefetcher_overlaps_and_preserves_order():
         assert torch.equal(src["input_ids"].cpu(), host[i][1])
         seen += 1
     assert seen == 5
+
+
+def test_greedy_step_argmax_ties_and_finished_rows():
+    """K14: ids[b, t] = argmax of the fp32 logits row (LOWEST index on ties, as torch.argmax), pad for finished rows, EOS finishes a row."""
+    lib = L()
+    B, V = 7, 32128
+    g = torch.Generator().manual_seed(11)
+    logits = torch.randn(B, V, generator=g)
+    logits[0, 5] = logits[0, 31000] = 9.0                     # tie: first index wins
+    logits[1, 1] = 20.0                                       # EOS
+    logits[2, V - 1] = 15.0
+    want = logits.argmax(-1)
+    ids = torch.zeros(B, 4, dtype=torch.int64, device="cuda")
+    alive = torch.ones(B, dtype=torch.int32, device="cuda")
+    alive[3] = 0
+    lg = logits.cuda()
+    lib.check(lib.lib().klab_greedy_step(torch.cuda.current_stream().cuda_stream, B, V, lg.data_ptr(), lg.stride(0), ids.data_ptr(),
+                                         ids.stride(0), 2, alive.data_ptr(), 0, 1))
+    got = ids[:, 2].cpu()
+    want[3] = 0
+    assert torch.equal(got, want) and got[0].item() == 5
+    assert alive.cpu().tolist() == [1, 0, 1, 0, 1, 1, 1]
+    # unaligned / odd vocabulary: scalar path
+    lg2 = logits[:, :1001].contiguous().cuda()
+    lib.check(lib.lib().klab_greedy_step(torch.cuda.current_stream().cuda_stream, B, 1001, lg2.data_ptr(), lg2.stride(0), ids.data_ptr(),
+                                         ids.stride(0), 3, alive.data_ptr(), 0, 1))
+    w2 = logits[:, :1001].argmax(-1)
+    w2[1] = 0
+    w2[3] = 0
+    assert torch.equal(ids[:, 3].cpu(), w2)
