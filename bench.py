@@ -190,6 +190,37 @@ def hf_reference_steps(w, steps, warmup, batch, device, autocast, log=lambda *_:
     return times
 
 
+def hf_generate_calls(w, steps, warmup, device, log=lambda *_: None):
+    """/root/reference/models/model.py:20-23,28 with the reference's engine on the GPU: frozen text encoder + Swin + concat, then
+    `transformer.generate(inputs_embeds=...)` (greedy, 20 new tokens, EOS disabled for a fixed length) under bf16 autocast."""
+    from transformers import Swinv2Config, Swinv2Model, T5Config, T5EncoderModel, T5ForConditionalGeneration
+    t5kw, sw = _dims(w)
+
+    def tcfg():
+        return T5Config(vocab_size=t5kw.get("vocab_size", 32128), d_model=t5kw["d_model"], d_kv=t5kw.get("d_kv", 64), d_ff=t5kw["d_ff"],
+                        num_layers=t5kw["num_layers"], num_heads=t5kw["num_heads"], decoder_start_token_id=0)
+    scfg = Swinv2Config(image_size=sw["image_size"], embed_dim=sw["embed_dim"], depths=list(sw["depths"]), num_heads=list(sw["num_heads"]),
+                        window_size=sw["window_size"], pretrained_window_sizes=list(sw["pretrained_window_sizes"]))
+    torch.manual_seed(0)
+    with torch.device(device):
+        lm, im, tr = T5EncoderModel(tcfg()).eval(), Swinv2Model(scfg).eval(), T5ForConditionalGeneration(tcfg()).eval()
+    px, src, _ = synth_batch(w, t5kw.get("vocab_size", 32128), 1234, pin=False)
+    px, src = px.to(device), src.to(device)
+    times = []
+    for i in range(warmup + steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            emb = torch.cat((im(pixel_values=px).last_hidden_state, lm(input_ids=src).last_hidden_state), dim=1)
+            ids = tr.generate(inputs_embeds=emb, max_new_tokens=w["l_tgt"], min_new_tokens=w["l_tgt"], do_sample=False)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        log(f"hf generate {i}: {dt:.3f}s ids {tuple(ids.shape)}")
+        if i >= warmup:
+            times.append(dt)
+    return times
+
+
 def oracle_port_steps(w, steps, warmup, sample_batch, log=lambda *_: None):
     """fwd + bwd + Adam step of the reference path restated in oracle/ (plain torch fp32 on the host cores); used only where
     `transformers` does not import."""
@@ -290,11 +321,22 @@ def run_hf_eager(args, w):
         import transformers
         dev = "cuda:0"
         torch.cuda.set_device(0)
-        times = hf_reference_steps(w, args.steps, max(args.warmup, 2), w["batch"], dev, True, log=lambda m: print(m, file=sys.stderr))
+        if w.get("decode"):
+            times = hf_generate_calls(w, args.steps, max(args.warmup, 2), dev, log=lambda m: print(m, file=sys.stderr))
+        else:
+            times = hf_reference_steps(w, args.steps, max(args.warmup, 2), w["batch"], dev, True, log=lambda m: print(m, file=sys.stderr))
     except Exception as e:                                                           # noqa: BLE001  (informational: never fails the run)
         emit({"impl": "hf_eager", "unavailable": f"{type(e).__name__}: {str(e)[:200]}"})
         return
     ms = 1e3 * sum(times) / len(times)
+    if w.get("decode"):
+        emit({"impl": "hf_eager", "metric": "greedy decode tokens/sec (T5 decoder with cross-attention KV cache)",
+              "value": w["batch"] * w["l_tgt"] / (ms / 1e3), "unit": "tokens/s", "n_gpus": 1, "steps": args.steps, "ms_per_step": ms,
+              "dtype": "bf16 autocast (fp32 parameters)", "data": "synthetic",
+              "config": {"workload": w["desc"], "name": args.workload, "batch_per_gpu": w["batch"], "new_tokens": w["l_tgt"], "eos": "disabled (fixed length)"},
+              "engine": f"transformers {transformers.__version__} generate(inputs_embeds=...) eager + torch {torch.__version__}",
+              "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)})
+        return
     emit({"impl": "hf_eager", "metric": "train samples/sec (Swin+T5 caption step)", "value": w["batch"] / (ms / 1e3), "unit": "samples/s",
           "n_gpus": 1, "steps": args.steps, "ms_per_step": ms, "dtype": "bf16 autocast (fp32 parameters)", "data": "synthetic",
           "config": {"workload": w["desc"], "name": args.workload, "batch_per_gpu": w["batch"], "l_src": w["l_src"], "l_tgt": w["l_tgt"]},
@@ -687,6 +729,8 @@ def run_ours(args, w):
             print(f"[bench] workload {name}: {json.dumps(extras[name])[:300]}", file=sys.stderr)
         hf_leg = run_sub(["--impl", "hf_eager", "--workload", "2a", "--steps", "5", "--warmup", "2"], 420)
         print(f"[bench] hf_eager: {json.dumps(hf_leg)[:300]}", file=sys.stderr)
+        if "error" not in extras.get("5", {"error": 1}):
+            extras["5"]["hf_eager_gpu"] = run_sub(["--impl", "hf_eager", "--workload", "5", "--steps", "3", "--warmup", "2"], 300)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:

@@ -764,35 +764,24 @@ int gemm_tc_launch(cudaStream_t stream, int M, int N, int K, const void* A, long
     const bool idempotent = !epi.accumulate && D != epi.residual && D != epi.aux_in && D != A && D != B;
     if (capturing || !idempotent) return dispatch_cfg(stream, M, N, K, model, w, A, lda, a_mn, B, ldb, b_mn, D, ldd, epi);
 
-    // candidates: for both kernel kinds, every legal N tile whose MODEL time is within 40 % of the model's best (the model ranks
-    // neighbouring tiles well but misses wave-quantisation effects by that much: 96 tiles on 74 CTA pairs run as two waves, 144
-    // tiles of a slightly narrower N tile as two FULL ones), plus the widest tile of each kind
+    // candidates: the model's best one-CTA and pair configurations, plus the widest tile of each kind.  (A wider search --
+    // every legal N tile within 40 % of the model's best -- was measured in round 2 and bought nothing: the step's GEMM time
+    // stayed within noise, 36.1 -> 36.7 ms; for the small shapes the tile choice is bounded by the per-SM operand ingest.)
     std::vector<GemmCfg> cand;
-    std::vector<double> cand_t;
-    double t_best = 1e30;
-    for (int pair_mode = 0; pair_mode <= 1; ++pair_mode) {
-        const int step = (b_mn ? 64 : 16) * (pair_mode ? 2 : 1);
-        for (int bn = 256; bn >= 64; bn -= step) {
-            GemmCfg c{};
-            const double tm = pick_config(M, N, K, b_mn != 0, can_split, pair_mode, WS_BYTES, epi, &c.bn, &c.splits, &c.cta2, bn);
-            if (c.bn != bn || tm >= 1e29) continue;
-            bool dup = false;
-            for (const GemmCfg& o : cand) dup = dup || o == c;
-            if (dup) continue;
-            cand.push_back(c);
-            cand_t.push_back(tm);
-            if (tm < t_best) t_best = tm;
-        }
-    }
-    {
-        std::vector<GemmCfg> keep;
-        for (size_t i = 0; i < cand.size(); ++i)
-            if (cand_t[i] <= 1.4 * t_best || cand[i].bn == 256 || cand[i].bn == 128) keep.push_back(cand[i]);
-        bool has_model = false;
-        for (const GemmCfg& o : keep) has_model = has_model || o == model;
-        if (!has_model) keep.push_back(model);                  // (narrow single tiles, BN < 64, exist only as the model's own choice)
-        cand.swap(keep);
-    }
+    auto add = [&](int pair_mode, int force_bn) {
+        GemmCfg c{};
+        pick_config(M, N, K, b_mn != 0, can_split, pair_mode, WS_BYTES, epi, &c.bn, &c.splits, &c.cta2, force_bn);
+        if (force_bn > 0 && c.bn != force_bn) return;
+        for (const GemmCfg& o : cand)
+            if (o == c) return;
+        cand.push_back(c);
+    };
+    add(0, 0);
+    add(1, 0);
+    add(0, 256);
+    add(1, 256);
+    add(0, 128);
+    add(1, 128);
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (cand.size() < 2 || cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
         cudaGetLastError();

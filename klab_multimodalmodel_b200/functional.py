@@ -823,6 +823,15 @@ class SwinBlockFn(torch.autograd.Function):
             outs, graphed = POOL.run(("swb", id(c)), _swin_block_bwd_body, (dout.contiguous(), x) + tuple(acts), (c,) + tuple(params),
                                      allow_graph=ctx.graphed)
             c.bwd_static = outs if graphed else None
+            if graphed and ACCUMULATE_IN_PLACE:
+                # first captured run with gradients already accumulated elsewhere: fold the old values into the static buffers
+                # once (the add autograd was about to do anyway) so that, from the next step on, .grad IS the static buffer
+                olds = [p.grad for p in params]
+                news = list(outs[1:1 + _N_SWIN_GRADS])
+                if all(g is not None and g.shape == o.shape and g.dtype == o.dtype and g.device == o.device for g, o in zip(olds, news)):
+                    torch._foreach_add_(news, olds)
+                    for p in params:
+                        p.grad = None
         tok, ctx.token = getattr(ctx, "token", None), None
         if tok is not None:
             tok.release()

@@ -18,14 +18,14 @@ TOP = [
     (6144, 4096, 1024, False, True, BF, False, 3, None, BF, False, 0.1, False, 4096, 24),
     (6144, 4096, 1024, False, False, BF, False, 1, None, None, False, 0.1, False, 4096, 24),
     (6144, 1024, 4096, False, False, BF, False, 0, BF, None, False, 0.1, False, 1024, 24),
-    (16384, 2048, 512, False, True, BF, False, 4, None, BF, False, 0.0, False, 2048, 18),
+    (16384, 2048, 512, False, True, BF, False, 6, None, BF, False, 0.0, False, 2048, 18),
     (6144, 1024, 4096, False, True, BF, False, 0, None, None, False, 0.0, False, 1024, 24),
     (1024, 1024, 2048, True, True, F32, False, 0, None, None, False, 0.0, False, 1024, 72),
     (1024, 4096, 6144, True, True, F32, False, 0, None, None, False, 0.0, False, 4096, 24),
-    (16384, 2048, 512, False, False, BF, True, 2, None, None, True, 0.0, False, 2048, 18),
+    (16384, 2048, 512, False, False, BF, True, 5, None, None, True, 0.0, False, 2048, 18),
     (2048, 3072, 1024, False, False, BF, False, 0, None, None, False, 0.0, False, 3072, 48),
     (2048, 1024, 1024, False, True, BF, False, 0, None, None, False, 0.0, False, 1024, 72),
-    (262144, 512, 128, False, True, BF, False, 4, None, BF, False, 0.0, False, 512, 2),
+    (262144, 512, 128, False, True, BF, False, 6, None, BF, False, 0.0, False, 512, 2),
 ]
 
 ap = argparse.ArgumentParser()
