@@ -762,7 +762,18 @@ int gemm_tc_launch(cudaStream_t stream, int M, int N, int K, const void* A, long
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     const bool capturing = cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone;
     const bool idempotent = !epi.accumulate && D != epi.residual && D != epi.aux_in && D != A && D != B;
-    if (capturing || !idempotent) return dispatch_cfg(stream, M, N, K, model, w, A, lda, a_mn, B, ldb, b_mn, D, ldd, epi);
+    if (capturing || !idempotent) {
+        // an accumulating launch cannot be timed (it is not idempotent), but the tile choice does not depend on the final add:
+        // reuse what the same signature without `accumulate` was tuned to (weight gradients accumulated in place)
+        if (epi.accumulate) {
+            std::array<long long, 14> k2 = key;
+            k2[12] = 0;
+            std::lock_guard<std::mutex> lk(g_tune_mu);
+            auto it = g_tuned.find(k2);
+            if (it != g_tuned.end()) return dispatch_cfg(stream, M, N, K, it->second, w, A, lda, a_mn, B, ldb, b_mn, D, ldd, epi);
+        }
+        return dispatch_cfg(stream, M, N, K, model, w, A, lda, a_mn, B, ldb, b_mn, D, ldd, epi);
+    }
 
     // candidates: the model's best one-CTA and pair configurations, plus the widest tile of each kind.  (A wider search --
     // every legal N tile within 40 % of the model's best -- was measured in round 2 and bought nothing: the step's GEMM time

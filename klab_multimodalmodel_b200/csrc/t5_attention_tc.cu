@@ -390,12 +390,20 @@ __global__ void __launch_bounds__(128) t5_attn_bwd_tc_kernel(const __grid_consta
                     const int dd = tid + half * TILE;                 // j_local - i_local + 127
                     if (dd > 2 * TILE - 2) break;
                     const int lo = max(0, TILE - 1 - dd), hi = min(TILE - 1, 2 * TILE - 2 - dd);
-                    float acc = 0.0f;
-                    for (int il = lo; il <= hi; ++il) {
+                    float acc4[4] = {0.0f, 0.0f, 0.0f, 0.0f};            // independent partial sums: the loads overlap
+                    auto elem = [&](int il) -> float {
                         const int jl = il + dd - (TILE - 1);
-                        const __nv_bfloat16 v = *reinterpret_cast<const __nv_bfloat16*>(sdS + (jl >> 6) * T + sw128(il, jl & 63));
-                        acc += __bfloat162float(v);
+                        return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sdS + (jl >> 6) * T + sw128(il, jl & 63)));
+                    };
+                    int il = lo;
+                    for (; il + 3 <= hi; il += 4) {
+                        acc4[0] += elem(il);
+                        acc4[1] += elem(il + 1);
+                        acc4[2] += elem(il + 2);
+                        acc4[3] += elem(il + 3);
                     }
+                    for (; il <= hi; ++il) acc4[0] += elem(il);
+                    const float acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
                     const int r = dd - (TILE - 1) + (kb - qt) * TILE + (Lq - 1);
                     if (r >= 0 && r < Lq + Lk - 1) drel[r] += acc;
                 }
@@ -509,8 +517,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_fwd_tc1_kernel(const __
     uint8_t* sIn = smem;                          // 2 x (Q, K, V)
     uint8_t* sP = sIn + 6 * T;                    // 2 key blocks of 64
     float* brel = reinterpret_cast<float*>(sP + 2 * T);          // [256]
-    float* sred = brel + 256;                                    // [4][128] row max / row sum partials
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sred + 4 * TILE);   // full[2], mma
+    float* sred = brel + 256;                                    // [4][128] row max partials
+    float* ssum = sred + 4 * TILE;                               // [4][128] row sum partials (own array: no barrier between the two uses)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ssum + 4 * TILE);   // full[2], mma
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -638,7 +647,6 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_fwd_tc1_kernel(const __
         sred[cq * TILE + r] = mx;
         __syncthreads();
         mx = fmaxf(fmaxf(sred[r], sred[TILE + r]), fmaxf(sred[2 * TILE + r], sred[3 * TILE + r]));
-        __syncthreads();                                   // sred is reused for the sums
         float sum = 0.0f;
         if (active) {
             const uint64_t base = (static_cast<uint64_t>(bh_row) * Lq + i) * Lk + jb;
@@ -653,7 +661,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_fwd_tc1_kernel(const __
             st_tile16(blk, r, (j0 & 63) >> 4, sv);
             st_tile16(blk, r, ((j0 & 63) >> 4) + 1, sv + 16);
         }
-        sred[cq * TILE + r] = sum;
+        ssum[cq * TILE + r] = sum;
         fence_proxy_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -665,7 +673,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_fwd_tc1_kernel(const __
                           umma_smem_desc_sw128(va + ks * 2048, 8192, 1024), id_o, ks != 0);
             umma_commit(&bars[2]);
         }
-        sum = (sred[r] + sred[TILE + r]) + (sred[2 * TILE + r] + sred[3 * TILE + r]);
+        sum = (ssum[r] + ssum[TILE + r]) + (ssum[2 * TILE + r] + ssum[3 * TILE + r]);
         mbar_wait(&bars[2], mma_phase);
         mma_phase ^= 1;
         tc_fence_after();
@@ -924,12 +932,22 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_bwd_tc1_kernel(const __
         if (has_bias && tid < 2 * TILE - 1) {
             const int dd = tid;                               // j - i + 127
             const int lo = max(0, TILE - 1 - dd), hi = min(min(TILE - 1, 2 * TILE - 2 - dd), (G > 1 ? TILE : Lq) - 1);
-            float acc = 0.0f;
-            for (int il = lo; il <= hi; ++il) {
+            // four independent partial sums: the loads of a diagonal do not depend on one another, a single accumulator made
+            // this a chain of ~100 shared-memory latencies on the critical path behind the (much shorter) gradient MMAs
+            float acc4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            auto elem = [&](int il) -> float {
                 const int jl = il + dd - (TILE - 1);
-                if (jl < lk_pad)
-                    acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sdS + (jl >> 6) * T + sw128(il, jl & 63)));
+                return jl < lk_pad ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sdS + (jl >> 6) * T + sw128(il, jl & 63))) : 0.0f;
+            };
+            int il = lo;
+            for (; il + 3 <= hi; il += 4) {
+                acc4[0] += elem(il);
+                acc4[1] += elem(il + 1);
+                acc4[2] += elem(il + 2);
+                acc4[3] += elem(il + 3);
             }
+            for (; il <= hi; ++il) acc4[0] += elem(il);
+            const float acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
             const int rr = dd - (TILE - 1) + (Lq - 1);
             if (rr >= 0 && rr < Lq + Lk - 1) atomicAdd(&bins[a.rel_bucket[rr - (Lq - 1) - a.q_offset + a.rel_zero]], acc);
         }
@@ -1028,7 +1046,7 @@ int t5_attention_fwd_tc(cudaStream_t st, int B, int H, int Lq, int Lk, const voi
         a.out = out; a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo; a.B = B; a.H = H; a.Lq = Lq; a.Lk = Lk;
         a.bias_table = bias_table; a.rel_bucket = rel_bucket; a.rel_zero = rel_zero; a.num_buckets = num_buckets; a.causal = causal;
         a.q_offset = q_offset; a.lse = lse; a.dropout_p = dropout_p; a.seed = seed; a.seed_ptr = seed_ptr;
-        const size_t smem1 = 1024 + 8 * TILE * 128 + sizeof(float) * (256 + 4 * TILE) + 64;
+        const size_t smem1 = 1024 + 8 * TILE * 128 + sizeof(float) * (256 + 8 * TILE) + 64;
         static bool set1 = false;
         if (!set1) {
             KLAB_CHECK_CUDA(cudaFuncSetAttribute(t5_attn_fwd_tc1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
