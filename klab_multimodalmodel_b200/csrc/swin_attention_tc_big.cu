@@ -11,8 +11,11 @@
 //   * backward keeps S and dP ([128 x 144] each) in TMEM, accumulates dK and dV of the window over both passes in TMEM
 //     (M = keys: two M-tiles, 0..127 and 128..N-1), writes dQ per pass; the position-bias gradient of the rows of pass 0 lives
 //     in registers across all windows a CTA visits for a head, that of the few rows of pass 1 in shared memory.
-// The bias row of a query (N floats) is read from global memory / L2 (a [144 x 144] fp32 table per head does not fit next to
-// the operand tiles).
+// Position bias: a [144 x 144] fp32 table per head does not fit next to the operand tiles, and reading a query's bias row from
+// L2 inside the softmax loop exposes the L2 latency once per 16 keys.  The bias is a function of the relative offset only
+// (bias[i][j] = tab[(yi - yj + w - 1)(2w - 1) + (xi - xj + w - 1)], HF modeling_swinv2.py:512-522), so the kernels rebuild the
+// (2w - 1)^2-entry table of the current head in shared memory (2 KB) from the gathered bias and index it as
+// tab[rowbase(i) - joff[j]] with a per-key offset table.
 #include "swin_tc.cuh"
 
 namespace klab {
@@ -24,19 +27,19 @@ using namespace swintc;
 constexpr int KROWS = 160;                     // staged key rows (rows >= N are zero); 20 groups of 8 rows
 constexpr int KBYTES = KROWS * 128;            // bytes of the K / V tiles
 constexpr int NMAX = 160;                      // TMEM budget of the backward kernel: S + dP = 2 * 160 columns
+constexpr int TABMAX = 640;                    // >= (2w - 1)^2 = 625 entries of the relative-offset bias table (w <= 13); even: the mbarriers behind it stay 8-byte aligned
 
-__device__ __forceinline__ void load_bias16(const float* brow, int c0, int N, bool vec, float* b) {
-    if (vec && c0 + 16 <= N) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(brow + c0) + i);
-            b[4 * i] = q.x; b[4 * i + 1] = q.y; b[4 * i + 2] = q.z; b[4 * i + 3] = q.w;
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) b[i] = c0 + i < N ? __ldg(brow + c0 + i) : 0.0f;
+// relative-offset table of one head from the gathered [N, N] bias: entry d = (dy + w - 1)(2w - 1) + (dx + w - 1) is bias[i][j] of any
+// pair with (yi - yj, xi - xj) = (dy, dx); pick i = (max(dy, 0), max(dx, 0)), j = (max(-dy, 0), max(-dx, 0))
+__device__ __forceinline__ void build_bias_table(float* tab_s, const float* bias_h, int w, int N, int tid, int nthreads) {
+    const int side = 2 * w - 1;
+    for (int d = tid; d < side * side; d += nthreads) {
+        const int dy = d / side - (w - 1), dx = d % side - (w - 1);
+        const int i = max(dy, 0) * w + max(dx, 0), j = max(-dy, 0) * w + max(-dx, 0);
+        tab_s[d] = __ldg(bias_h + static_cast<long long>(i) * N + j);
     }
 }
+__device__ __forceinline__ int bias_rowbase(int n, int w) { return (n / w + w - 1) * (2 * w - 1) + (n % w + w - 1); }
 
 // ------------------------------------------------------------------------------------------------------------------
 // forward: 128 threads, thread t = query row t of the current pass; two CTAs per SM (112 KB of shared memory, 256 TMEM columns
@@ -52,15 +55,17 @@ __global__ void __launch_bounds__(128) swin_attn_fwd_big_kernel(SwinTcArgs a, in
     uint8_t* sV = sK + KBYTES;
     uint8_t* sP = sV + KBYTES;                               // 3 key blocks of 64
     int* sregk = reinterpret_cast<int*>(sP + 3 * TB);        // [KROWS] shift-mask region of every key token
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sregk + KROWS);
+    int* joff = sregk + KROWS;                               // [KROWS] yj (2w - 1) + xj of key token j
+    float* tab_s = reinterpret_cast<float*>(joff + KROWS);   // [(2w - 1)^2] relative-offset bias table of the current head
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tab_s + TABMAX);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
 
     const int N = a.N;
     const int tid = threadIdx.x, warp = tid >> 5;
+    for (int j = tid; j < KROWS; j += 128) joff[j] = (j / a.w) * (2 * a.w - 1) + j % a.w;
     const int nwin = a.B * a.nW;
     const long long T = static_cast<long long>(a.heads) * nwin * passes;
     const long long t_begin = blockIdx.x * T / gridDim.x, t_end = (blockIdx.x + 1) * T / gridDim.x;
-    const bool vec = (N & 3) == 0;
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
@@ -88,8 +93,11 @@ __global__ void __launch_bounds__(128) swin_attn_fwd_big_kernel(SwinTcArgs a, in
         const int rem = static_cast<int>(t - static_cast<long long>(th) * nwin * passes);
         const int bw = rem / passes, pass = rem - bw * passes;
         if (th != h) {
+            // every thread is past the previous item's softmax (its second barrier), so the old table is dead; the staging barrier
+            // below publishes the new one
             h = th;
             scale = __expf(fminf(a.logit_scale[h], LOGIT_MAX));
+            build_bias_table(tab_s, a.bias + static_cast<long long>(h) * N * N, a.w, N, tid, 128);
         }
         // ---- stage this pass's query row, and the window's keys / values if they are not there yet ----
         const int n = pass * TILE + tid;
@@ -147,20 +155,18 @@ __global__ void __launch_bounds__(128) swin_attn_fwd_big_kernel(SwinTcArgs a, in
         tc_fence_after();
 
         // ---- softmax of row tid over the window's N keys, straight out of TMEM: pass A finds the maximum, pass B writes P ----
-        const float* brow = a.bias + (static_cast<long long>(h) * N + (tok >= 0 ? n : 0)) * N;
+        const int rb = bias_rowbase(tok >= 0 ? n : 0, a.w);
         float mx = -INFINITY;
         for (int c0 = 0; c0 < nk; c0 += 16) {
             uint32_t r[16];
             tmem_ld_32x16(trow + c0, r);
             tmem_ld_wait();
             if (tok >= 0) {
-                float b[16];
-                load_bias16(brow, c0, N, vec, b);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int j = c0 + i;
                     if (j < N) {
-                        float sc = fmaf(__uint_as_float(r[i]), scale, b[i]);
+                        float sc = fmaf(__uint_as_float(r[i]), scale, tab_s[rb - joff[j]]);
                         if (sregk[j] != region) sc += -200.0f;
                         mx = fmaxf(mx, sc);
                     }
@@ -174,14 +180,12 @@ __global__ void __launch_bounds__(128) swin_attn_fwd_big_kernel(SwinTcArgs a, in
             tmem_ld_wait();
             float e[16];
             if (tok >= 0) {
-                float b[16];
-                load_bias16(brow, c0, N, vec, b);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int j = c0 + i;
                     float v = 0.0f;
                     if (j < N) {
-                        float sc = fmaf(__uint_as_float(r[i]), scale, b[i]);
+                        float sc = fmaf(__uint_as_float(r[i]), scale, tab_s[rb - joff[j]]);
                         if (sregk[j] != region) sc += -200.0f;
                         v = __expf(sc - mx);
                     }
@@ -255,7 +259,9 @@ __global__ void __launch_bounds__(BIG_BWD_THREADS, 1) swin_attn_bwd_big_kernel(S
     float* dbrem = reinterpret_cast<float*>(sdS + 4 * TB);         // [nrem][N + 1] bias gradient of the rows of pass 1
     int* sreg = reinterpret_cast<int*>(dbrem + nrem * (N + 1));    // [128] region of the pass's query rows, -1 = padding
     int* sregk = sreg + TILE;                                      // [KROWS]
-    float* sqn = reinterpret_cast<float*>(sregk + KROWS);          // [128] |q|
+    int* joff = sregk + KROWS;                                     // [KROWS] yj (2w - 1) + xj of key token j
+    float* tab_s = reinterpret_cast<float*>(joff + KROWS);         // [(2w - 1)^2] relative-offset bias table of the current head
+    float* sqn = tab_s + TABMAX;                                   // [128] |q|
     float* skn = sqn + TILE;                                       // [KROWS] |k|
     float* sD = skn + KROWS;                                       // [4][128]
     float* red = sD + 4 * TILE;                                    // [16]
@@ -269,7 +275,7 @@ __global__ void __launch_bounds__(BIG_BWD_THREADS, 1) swin_attn_bwd_big_kernel(S
     const long long t_begin = blockIdx.x * T / gridDim.x, t_end = (blockIdx.x + 1) * T / gridDim.x;
     const int srow = tid >> 2, part = tid & 3;                     // staging view: 4 threads per token row, 16 bytes each
     const int r = (warp & 3) * 32 + lane, cq = warp >> 2;          // TMEM view
-    const bool vec = (N & 3) == 0;
+    for (int j = tid; j < KROWS; j += BIG_BWD_THREADS) joff[j] = (j / a.w) * (2 * a.w - 1) + j % a.w;
 
     if (tid == 0) {
         mbar_init(&bars[0], 1);
@@ -334,6 +340,7 @@ __global__ void __launch_bounds__(BIG_BWD_THREADS, 1) swin_attn_bwd_big_kernel(S
             dscale_acc = 0.0f;
 #pragma unroll
             for (int i = 0; i < KQ; ++i) dbacc[i] = 0.0f;
+            build_bias_table(tab_s, a.bias + static_cast<long long>(h) * N * N, a.w, N, tid, BIG_BWD_THREADS);     // published by the staging barrier
         }
         // ---- stage the window's keys / values: L2-normalised k as bf16 hi | lo, v, |k|, region ----
         for (int idx = tid; idx < KROWS * 4; idx += BIG_BWD_THREADS) {
@@ -417,7 +424,7 @@ __global__ void __launch_bounds__(BIG_BWD_THREADS, 1) swin_attn_bwd_big_kernel(S
             const int region = sreg[r];
             const bool valid = region >= 0;
             const float lse = valid ? a.lse[(static_cast<long long>(bw) * a.heads + h) * N + n] : 0.0f;
-            const float* brow = a.bias + (static_cast<long long>(h) * N + (valid ? n : 0)) * N;
+            const int rb = bias_rowbase(valid ? n : 0, a.w);
             mbar_wait(&bars[0], phase);
             phase ^= 1;
             tc_fence_after();
@@ -432,13 +439,11 @@ __global__ void __launch_bounds__(BIG_BWD_THREADS, 1) swin_attn_bwd_big_kernel(S
                     tmem_ld_32x16(trow + TM_DP + c0, rp);
                     tmem_ld_wait();
                     if (valid) {
-                        float b[16];
-                        load_bias16(brow, c0, N, vec, b);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const int j = c0 + i;
                             if (j < N) {
-                                float sc = fmaf(__uint_as_float(rs[i]), scale, b[i]);
+                                float sc = fmaf(__uint_as_float(rs[i]), scale, tab_s[rb - joff[j]]);
                                 if (sregk[j] != region) sc += -200.0f;
                                 Dp = fmaf(__expf(sc - lse), __uint_as_float(rp[i]), Dp);
                             }
@@ -462,13 +467,11 @@ __global__ void __launch_bounds__(BIG_BWD_THREADS, 1) swin_attn_bwd_big_kernel(S
 #pragma unroll
                     for (int i = 0; i < 16; ++i) { pv[i] = 0.0f; dsv[i] = 0.0f; }
                     if (valid) {
-                        float b[16];
-                        load_bias16(brow, c0, N, vec, b);
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const int j = c0 + i;
                             if (j < N) {
-                                float sc = fmaf(__uint_as_float(rs[i]), scale, b[i]);
+                                float sc = fmaf(__uint_as_float(rs[i]), scale, tab_s[rb - joff[j]]);
                                 if (sregk[j] != region) sc += -200.0f;
                                 const float p = __expf(sc - lse);
                                 const float ds = p * (__uint_as_float(rp[i]) - Di);
@@ -620,7 +623,7 @@ int swin_attention_fwd_big(cudaStream_t st, int B, int res, int heads, int windo
     SwinTcArgs a = make_big_args(B, res, heads, window, shift, q, k, v, ld, ldc, logit_scale, bias, lse);
     a.out = static_cast<__nv_bfloat16*>(ctx);
     const int N = a.N, passes = (N + TILE - 1) / TILE, nk = (N + 15) & ~15;
-    const size_t smem = 1024 + TB + 2 * KBYTES + 3 * TB + sizeof(int) * KROWS + 64;
+    const size_t smem = 1024 + TB + 2 * KBYTES + 3 * TB + sizeof(int) * 2 * KROWS + sizeof(float) * TABMAX + 64;
     static bool set = false;
     if (!set) {
         KLAB_CHECK_CUDA(cudaFuncSetAttribute(swin_attn_fwd_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -644,8 +647,8 @@ int swin_attention_bwd_big(cudaStream_t st, int B, int res, int heads, int windo
     a.dbias = dbias; a.dlogit_scale = dlogit_scale;
     const int N = a.N, passes = (N + TILE - 1) / TILE, nk = (N + 15) & ~15;
     const int nrem = N > TILE ? N - TILE : 0;
-    const size_t smem = 1024 + 2 * TB + 2 * KBYTES + 8 * TB + sizeof(float) * nrem * (N + 1) + sizeof(int) * (TILE + KROWS) +
-                        sizeof(float) * (TILE + KROWS + 4 * TILE + 16) + 64;
+    const size_t smem = 1024 + 2 * TB + 2 * KBYTES + 8 * TB + sizeof(float) * nrem * (N + 1) + sizeof(int) * (TILE + 2 * KROWS) +
+                        sizeof(float) * (TABMAX + TILE + KROWS + 4 * TILE + 16) + 64;
     KLAB_REQUIRE(smem <= 227 * 1024, "swin_attention_bwd (large windows): %zu bytes of shared memory", smem);
     static size_t set = 0;
     if (smem > set) {
