@@ -126,3 +126,32 @@ class MyModel(nn.Module):
         self.transformer.load_state_dict(checkpoints['transformer'])
         if self.args.image_model_train:
             self.image_model.load_state_dict(checkpoints['image_model'])
+
+    # ---- true resume (the optional half): the reference saves weights only (train.py:88-104 never stores the
+    # optimizer, the scheduler or the epoch, so a run cannot be continued).  `save_state` writes the reference's file format plus
+    # three extra keys -- the reference's own `load` ignores them, so the files stay interchangeable -- and `load_state` restores
+    # everything it finds.
+    def save_state(self, result_name="last.pth", optimizer=None, scheduler=None, epoch=None, step=None):
+        result_path = os.path.join(self.args.result_dir, result_name)
+        checkpoints = {'transformer': self.transformer.state_dict()}
+        if self.args.image_model_train:
+            checkpoints['image_model'] = self.image_model.state_dict()
+        if optimizer is not None:
+            checkpoints['optimizer'] = optimizer.state_dict()
+        if scheduler is not None:
+            checkpoints['scheduler'] = scheduler.state_dict()
+        checkpoints['progress'] = {'epoch': epoch, 'step': step}
+        torch.save(checkpoints, result_path)
+
+    def load_state(self, result_name="last.pth", optimizer=None, scheduler=None):
+        """-> {'epoch': ..., 'step': ...} (None entries for a weights-only file written by the reference)."""
+        result_path = os.path.join(self.args.result_dir, result_name)
+        checkpoints = torch.load(result_path, map_location=next(self.transformer.parameters()).device)
+        self.transformer.load_state_dict(checkpoints['transformer'])
+        if self.args.image_model_train and 'image_model' in checkpoints:
+            self.image_model.load_state_dict(checkpoints['image_model'])
+        if optimizer is not None and 'optimizer' in checkpoints:
+            optimizer.load_state_dict(checkpoints['optimizer'])
+        if scheduler is not None and 'scheduler' in checkpoints:
+            scheduler.load_state_dict(checkpoints['scheduler'])
+        return dict(checkpoints.get('progress') or {'epoch': None, 'step': None})

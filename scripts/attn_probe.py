@@ -13,6 +13,7 @@ from klab_multimodalmodel_b200 import ops as O
 ap = argparse.ArgumentParser()
 ap.add_argument("--time", action="store_true")
 ap.add_argument("--stage", type=int, default=2)
+ap.add_argument("--big", action="store_true", help="profile the 384^2 / 12x12-window Swin kernels and the 176-token T5 kernels instead")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
@@ -92,8 +93,8 @@ if a.time:
         timed(name + " fwd", f)
         timed(name + " bwd", b)
 else:
-    sf, sb = swin_case(a.stage)
-    tf, tb = t5_case(96, 96, False, True)
+    sf, sb = swin_case(a.stage, big=a.big)
+    tf, tb = t5_case(176, 176, False, True) if a.big else t5_case(96, 96, False, True)
     for fn in (sf, sb, tf, tb):
         fn(); fn()
     torch.cuda.synchronize()

@@ -189,3 +189,38 @@ def test_from_pretrained_resolution(tmp_path, monkeypatch):
         T5EncoderModel.from_pretrained(str(bare))
     with pytest.raises(FileNotFoundError):
         T5EncoderModel.from_pretrained("no-such-model")
+
+
+def test_true_resume_round_trip(tmp_path):
+    """N4, optional half: weights + optimizer + scheduler + progress in one file that the reference's own `load` still reads
+    (extra keys only); restoring it continues the optimizer state exactly."""
+    import types
+
+    from klab_multimodalmodel_b200.modeling import Swinv2Config, T5Config, init_t5_
+    from klab_multimodalmodel_b200.models.model import MyModel
+    tcfg = T5Config(vocab_size=64, d_model=128, d_ff=64, num_layers=1, num_heads=2)
+    scfg = Swinv2Config(image_size=32, embed_dim=32, depths=(1, 1, 1), num_heads=(1, 2, 4), window_size=4, pretrained_window_sizes=(0, 0, 0))
+    args = types.SimpleNamespace(result_dir=str(tmp_path), language_model_name=tcfg, image_model_name=scfg, image_model_train=True,
+                                 transformer_model_name=tcfg)
+    a, b = MyModel(args), MyModel(args)
+    init_t5_(a.transformer, seed=1)
+    init_t5_(b.transformer, seed=2)
+    opt_a = torch.optim.Adam(a.transformer.parameters(), lr=1e-3)
+    sch_a = torch.optim.lr_scheduler.StepLR(opt_a, step_size=10, gamma=0.1)
+    for p in a.transformer.parameters():
+        p.grad = torch.full_like(p, 0.01)
+    opt_a.step()
+    sch_a.step()
+    a.save_state("last.pth", optimizer=opt_a, scheduler=sch_a, epoch=3, step=1234)
+    blob = torch.load(os.path.join(str(tmp_path), "last.pth"))
+    assert {"transformer", "image_model", "optimizer", "scheduler", "progress"} <= set(blob)
+    b.load("last.pth")                                              # the reference-format reader ignores the extra keys
+    assert all(torch.equal(x, y) for x, y in zip(a.transformer.state_dict().values(), b.transformer.state_dict().values()))
+    opt_b = torch.optim.Adam(b.transformer.parameters(), lr=1e-3)
+    sch_b = torch.optim.lr_scheduler.StepLR(opt_b, step_size=10, gamma=0.1)
+    prog = b.load_state("last.pth", optimizer=opt_b, scheduler=sch_b)
+    assert prog == {"epoch": 3, "step": 1234} and sch_b.last_epoch == sch_a.last_epoch
+    for pa, pb in zip(a.transformer.parameters(), b.transformer.parameters()):
+        assert torch.equal(opt_a.state[pa]["exp_avg"], opt_b.state[pb]["exp_avg"]) and opt_b.state[pb]["step"] == opt_a.state[pa]["step"]
+    a.save("weights_only.pth")                                      # a weights-only file (the reference's writer) resumes with empty progress
+    assert b.load_state("weights_only.pth") == {"epoch": None, "step": None}
