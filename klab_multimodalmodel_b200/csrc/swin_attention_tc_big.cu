@@ -13,9 +13,9 @@
 //     in registers across all windows a CTA visits for a head, that of the few rows of pass 1 in shared memory.
 // Position bias: a [144 x 144] fp32 table per head does not fit next to the operand tiles, and reading a query's bias row from
 // L2 inside the softmax loop exposes the L2 latency once per 16 keys.  The bias is a function of the relative offset only
-// (bias[i][j] = tab[(yi - yj + w - 1)(2w - 1) + (xi - xj + w - 1)], HF modeling_swinv2.py:512-522), so the kernels rebuild the
-// (2w - 1)^2-entry table of the current head in shared memory (2 KB) from the gathered bias and index it as
-// tab[rowbase(i) - joff[j]] with a per-key offset table.
+// (bias[i][j] = tab[(yi - yj + w - 1)(2w - 1) + (xi - xj + w - 1)], HF modeling_swinv2.py:512-522), so the BACKWARD kernel rebuilds the
+// (2w - 1)^2-entry table of the current head in shared memory (2 KB) from the gathered bias and indexes it as
+// tab[rowbase(i) - joff[j]] with a per-key offset table (the forward kernel keeps the row reads: see load_bias16).
 #include "swin_tc.cuh"
 
 namespace klab {
@@ -41,6 +41,22 @@ __device__ __forceinline__ void build_bias_table(float* tab_s, const float* bias
 }
 __device__ __forceinline__ int bias_rowbase(int n, int w) { return (n / w + w - 1) * (2 * w - 1) + (n % w + w - 1); }
 
+// 16 consecutive entries of a query's bias row straight from global memory (forward kernel: the row is 576 contiguous bytes per
+// thread, read twice and L1-resident the second time -- measured 14 % faster there than the shared-memory table, whose two
+// dependent LDS per key sit on the softmax critical path; the backward kernel, 4 threads per row, is 12 % faster WITH the table)
+__device__ __forceinline__ void load_bias16(const float* brow, int c0, int N, bool vec, float* b) {
+    if (vec && c0 + 16 <= N) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(brow + c0) + i);
+            b[4 * i] = q.x; b[4 * i + 1] = q.y; b[4 * i + 2] = q.z; b[4 * i + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) b[i] = c0 + i < N ? __ldg(brow + c0 + i) : 0.0f;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // forward: 128 threads, thread t = query row t of the current pass; two CTAs per SM (112 KB of shared memory, 256 TMEM columns
 // each).  Work item = (head, window, pass), head-major; a CTA owns a contiguous range of items, so the second pass of a
@@ -55,14 +71,12 @@ __global__ void __launch_bounds__(128) swin_attn_fwd_big_kernel(SwinTcArgs a, in
     uint8_t* sV = sK + KBYTES;
     uint8_t* sP = sV + KBYTES;                               // 3 key blocks of 64
     int* sregk = reinterpret_cast<int*>(sP + 3 * TB);        // [KROWS] shift-mask region of every key token
-    int* joff = sregk + KROWS;                               // [KROWS] yj (2w - 1) + xj of key token j
-    float* tab_s = reinterpret_cast<float*>(joff + KROWS);   // [(2w - 1)^2] relative-offset bias table of the current head
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tab_s + TABMAX);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sregk + KROWS);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2);
 
     const int N = a.N;
     const int tid = threadIdx.x, warp = tid >> 5;
-    for (int j = tid; j < KROWS; j += 128) joff[j] = (j / a.w) * (2 * a.w - 1) + j % a.w;
+    const bool vec = (N & 3) == 0;
     const int nwin = a.B * a.nW;
     const long long T = static_cast<long long>(a.heads) * nwin * passes;
     const long long t_begin = blockIdx.x * T / gridDim.x, t_end = (blockIdx.x + 1) * T / gridDim.x;
@@ -93,11 +107,8 @@ __global__ void __launch_bounds__(128) swin_attn_fwd_big_kernel(SwinTcArgs a, in
         const int rem = static_cast<int>(t - static_cast<long long>(th) * nwin * passes);
         const int bw = rem / passes, pass = rem - bw * passes;
         if (th != h) {
-            // every thread is past the previous item's softmax (its second barrier), so the old table is dead; the staging barrier
-            // below publishes the new one
             h = th;
             scale = __expf(fminf(a.logit_scale[h], LOGIT_MAX));
-            build_bias_table(tab_s, a.bias + static_cast<long long>(h) * N * N, a.w, N, tid, 128);
         }
         // ---- stage this pass's query row, and the window's keys / values if they are not there yet ----
         const int n = pass * TILE + tid;
@@ -155,18 +166,20 @@ __global__ void __launch_bounds__(128) swin_attn_fwd_big_kernel(SwinTcArgs a, in
         tc_fence_after();
 
         // ---- softmax of row tid over the window's N keys, straight out of TMEM: pass A finds the maximum, pass B writes P ----
-        const int rb = bias_rowbase(tok >= 0 ? n : 0, a.w);
+        const float* brow = a.bias + (static_cast<long long>(h) * N + (tok >= 0 ? n : 0)) * N;
         float mx = -INFINITY;
         for (int c0 = 0; c0 < nk; c0 += 16) {
             uint32_t r[16];
             tmem_ld_32x16(trow + c0, r);
             tmem_ld_wait();
             if (tok >= 0) {
+                float b[16];
+                load_bias16(brow, c0, N, vec, b);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int j = c0 + i;
                     if (j < N) {
-                        float sc = fmaf(__uint_as_float(r[i]), scale, tab_s[rb - joff[j]]);
+                        float sc = fmaf(__uint_as_float(r[i]), scale, b[i]);
                         if (sregk[j] != region) sc += -200.0f;
                         mx = fmaxf(mx, sc);
                     }
@@ -180,12 +193,14 @@ __global__ void __launch_bounds__(128) swin_attn_fwd_big_kernel(SwinTcArgs a, in
             tmem_ld_wait();
             float e[16];
             if (tok >= 0) {
+                float b[16];
+                load_bias16(brow, c0, N, vec, b);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int j = c0 + i;
                     float v = 0.0f;
                     if (j < N) {
-                        float sc = fmaf(__uint_as_float(r[i]), scale, tab_s[rb - joff[j]]);
+                        float sc = fmaf(__uint_as_float(r[i]), scale, b[i]);
                         if (sregk[j] != region) sc += -200.0f;
                         v = __expf(sc - mx);
                     }
@@ -623,7 +638,7 @@ int swin_attention_fwd_big(cudaStream_t st, int B, int res, int heads, int windo
     SwinTcArgs a = make_big_args(B, res, heads, window, shift, q, k, v, ld, ldc, logit_scale, bias, lse);
     a.out = static_cast<__nv_bfloat16*>(ctx);
     const int N = a.N, passes = (N + TILE - 1) / TILE, nk = (N + 15) & ~15;
-    const size_t smem = 1024 + TB + 2 * KBYTES + 3 * TB + sizeof(int) * 2 * KROWS + sizeof(float) * TABMAX + 64;
+    const size_t smem = 1024 + TB + 2 * KBYTES + 3 * TB + sizeof(int) * KROWS + 64;
     static bool set = false;
     if (!set) {
         KLAB_CHECK_CUDA(cudaFuncSetAttribute(swin_attn_fwd_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
