@@ -135,8 +135,8 @@ class GpuImageProcessor:
         if self.size and tuple(images.shape[-2:]) != tuple(self.size):
             raise NotImplementedError(f"GpuImageProcessor: images are {tuple(images.shape[-2:])} but the model expects {tuple(self.size)}; "
                                       "resize in the dataset (the reference's loader does, loader.py:15)")
-        if images.is_cuda:
-            return images.contiguous()
+        if images.is_cuda or (images.is_pinned() and images.is_contiguous()):
+            return images.contiguous()                     # already on the device / already page-locked: no staging copy
         key = (tuple(images.shape), images.dtype)
         bufs = self._pinned.get(key)
         if bufs is None:                                   # two pinned staging buffers per geometry: the copy of batch i may still be

@@ -92,6 +92,9 @@ def _decode_operands_peek(tr, cd):
     return out, pk([tr.shared.weight], cd)
 
 
+CHECK_EVERY = 5           # decode steps between two read-backs of the "every row has finished" flag
+
+
 @torch.no_grad()
 def greedy_generate(tr, embeds, B, Le, max_new_tokens: int = 20):
     from .graphs import POOL
@@ -116,15 +119,23 @@ def greedy_generate(tr, embeds, B, Le, max_new_tokens: int = 20):
     st.ids.fill_(cfg.pad_token_id)
     st.ids[:, 0] = cfg.decoder_start_token_id
     st.unfinished.fill_(1)
-    n_out = 1
+    # HF checks the stopping criteria after every token (a host round trip per step).  Finished rows only ever emit pad, so running
+    # on and trimming afterwards gives the same ids: the "all rows finished" flag is read back every CHECK_EVERY steps only (the
+    # queue of captured steps stays ahead of the GPU in between) and the returned length is where the last row finished.
+    n_run = 0
     for t in range(T):
-        # the single-token step is ~14 small kernels per block: launch bound when issued one by one, so it is a captured region
+        # the single-token step is ~11 small kernels per block: launch bound when issued one by one, so it is a captured region
         # per position t (keys beyond t are masked by the causal bound, stale cache rows of an earlier batch never contribute)
         POOL.run(("dec", id(tr), id(st), t), _decode_step_body, (), (tr, st, t, B, Le, T))
-        n_out = t + 2
-        if not bool(st.unfinished.cpu().any()):                           # HF checks the stopping criteria every step too
+        n_run = t + 1
+        if n_run % CHECK_EVERY == 0 and n_run < T and not bool(st.unfinished.cpu().any()):
             break
-    return st.ids[:, :n_out].clone()
+    ids = st.ids[:, :n_run + 1]
+    # length HF would have returned: it stops right after the step in which the last unfinished row emitted EOS
+    is_eos = ids[:, 1:] == cfg.eos_token_id
+    first_eos = torch.where(is_eos.any(1), is_eos.int().argmax(1) + 1, torch.full((B,), n_run, device=dev))     # tokens a row emits
+    n_out = 1 + int(first_eos.max().item())
+    return ids[:, :n_out].clone()
 
 
 @torch.no_grad()
