@@ -63,6 +63,22 @@ if rank == 0:
         a = last_compute_before_adam[0]
         prev = max((e.time_range.end for e in ours if e.time_range.end <= a.time_range.start), default=a.time_range.start)
         print(f"adam starts at +{(a.time_range.start - t_begin) / 1e3:.1f} ms; idle gap before it {(a.time_range.start - prev) / 1e3:.2f} ms")
+    # GPU occupancy of the step: union of the intervals of our kernels (any stream) = busy; the rest of the span = idle
+    iv = sorted((e.time_range.start, e.time_range.end) for e in ours)
+    busy, cur_s, cur_e = 0.0, iv[0][0], iv[0][1]
+    gaps = []
+    for s_, e_ in iv[1:]:
+        if s_ > cur_e:
+            busy += cur_e - cur_s
+            gaps.append((s_ - cur_e, cur_e - t_begin))
+            cur_s, cur_e = s_, e_
+        else:
+            cur_e = max(cur_e, e_)
+    busy += cur_e - cur_s
+    print(f"our kernels: busy (union) {busy / 1e3:.2f} ms, idle inside the span {(t_end - t_begin - busy) / 1e3:.2f} ms over {len(gaps)} gaps; "
+          f"sum of kernel durations {sum(e.device_time for e in ours) / 1e3:.2f} ms")
+    big = sorted(gaps, reverse=True)[:8]
+    print("largest gaps (ms @ offset ms): " + ", ".join(f"{g / 1e3:.2f}@{o / 1e3:.1f}" for g, o in big))
     agg = {}
     for e in evs:
         k = re.sub(r"\(.*", "", e.name).replace("void ", "").replace("klab::(anonymous namespace)::", "")[:60]
