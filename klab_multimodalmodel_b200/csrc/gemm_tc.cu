@@ -89,7 +89,7 @@ struct CeArgs {
 // stages its own 128 rows of A and rows [rank * BN/2, +BN/2) of the B tile, the leader issues tcgen05.mma.cta_group::2 (M = 256)
 // into the TMEM of both SMs, and each CTA runs the epilogue of its own 128 x BN half.  Per SM and k-block that is 16 KiB of A
 // plus BN * 64 B of B instead of BN * 128 B: the L2 -> SM feed, which bounds the one-CTA kernel at ~1.1 PFLOP/s, is relieved.
-// Work distribution is the static stride over pairs (the dynamic counter is a one-CTA feature).
+// Work distribution: static stride over pairs, or the dynamic counter with the leader claiming for the pair (see the producer).
 template <bool A_MN, bool B_MN, int EPI, bool CTA2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -135,7 +135,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         }
         for (int s = 0; s < SQ; ++s) {
             mbar_init(&sq_full[s], 1);
-            mbar_init(&sq_empty[s], 1 + NUM_EPI_WARPS);        // MMA issuer + every epilogue warp
+            // MMA issuer + every epilogue warp; pair: the leader's barrier also collects the peer's producer and epilogue warps
+            mbar_init(&sq_empty[s], CTA2 ? 2 * (1 + NUM_EPI_WARPS) : 1 + NUM_EPI_WARPS);
         }
         fence_barrier_init();
     }
@@ -167,25 +168,43 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             int sq = 0;
             uint32_t sq_phase = 0;
             int item = work_id;                                 // first item: static, no atomic in front of the first load
+            // Pair kernel with dynamic distribution: the LEADER's producer claims the items of the pair and publishes each one to
+            // its own consumers and, through a cluster-scope store + remote mbarrier arrival, to the queue of the peer CTA; the
+            // peer's producer and epilogue warps take their items from there and return the slot by arriving on the leader's
+            // `sq_empty` barrier.  (A pair whose TPC is held by a collective starts late, finds the end marker and leaves.)
+            const bool follower = CTA2 && sched != nullptr && rank == 1;
             while (true) {
-                if (sched) {                                    // publish the claimed item (or the end marker) to the consumers
-                    mbar_wait(&sq_empty[sq], sq_phase ^ 1);
-                    sq_item[sq] = item < num_items ? item : -1;
+                if (follower) {
+                    mbar_wait_cluster(&sq_full[sq], sq_phase);
+                    item = sq_item[sq];
+                    mbar_arrive_leader_release(&sq_empty[sq]);
+                    if (++sq == SQ) { sq = 0; sq_phase ^= 1; }
+                    if (item < 0) break;
+                } else if (sched) {                             // publish the claimed item (or the end marker) to the consumers
+                    if constexpr (CTA2) mbar_wait_cluster(&sq_empty[sq], sq_phase ^ 1);
+                    else mbar_wait(&sq_empty[sq], sq_phase ^ 1);
+                    const int v = item < num_items ? item : -1;
+                    sq_item[sq] = v;
+                    if constexpr (CTA2) {
+                        st_shared_cluster_b32(mapa_shared(smem_u32(&sq_item[sq]), 1), v);
+                        mbar_arrive_cluster(mapa_shared(smem_u32(&sq_full[sq]), 1));
+                    }
                     mbar_arrive(&sq_full[sq]);
                     if (++sq == SQ) { sq = 0; sq_phase ^= 1; }
                 }
                 if (item >= num_items) {
                     // this CTA's claims are over (the result of the last one has been seen): count it as finished now, while
-                    // the MMA and epilogue warps still work; the last CTA to get here re-arms the counters for the next launch /
-                    // graph replay that uses this slot (nobody touches them again during this launch)
-                    if (sched && atomicAdd(&sched[1], 1) == static_cast<int>(gridDim.x) - 1) {
+                    // the MMA and epilogue warps still work; the last CTA (pair: leader) to get here re-arms the counters for the
+                    // next launch / graph replay that uses this slot (nobody touches them again during this launch)
+                    const int units = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+                    if (sched && atomicAdd(&sched[1], 1) == units - 1) {
                         sched[0] = 0;
                         sched[1] = 0;
                     }
                     break;
                 }
                 // claim the next item now: the atomic's round trip hides behind this item's loads
-                const int next_item = (sched ? atomicAdd(&sched[0], 1) : item) + work_stride;
+                const int next_item = follower ? 0 : (sched ? atomicAdd(&sched[0], 1) : item) + work_stride;
                 const int tile = item / splits, split = item - tile * splits;
                 // consecutive items share the m tile (and therefore A) while sweeping n: CTAs running side by side hit the same
                 // A rows in L2
@@ -296,10 +315,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         int item = work_id;
         while (true) {
             if (sched) {
-                mbar_wait(&sq_full[sq], sq_phase);
+                if constexpr (CTA2) mbar_wait_cluster(&sq_full[sq], sq_phase);
+                else mbar_wait(&sq_full[sq], sq_phase);
                 item = sq_item[sq];
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sq_empty[sq]);
+                if (lane == 0) {
+                    if constexpr (CTA2) mbar_arrive_leader_release(&sq_empty[sq]);
+                    else mbar_arrive(&sq_empty[sq]);
+                }
                 if (++sq == SQ) { sq = 0; sq_phase ^= 1; }
                 if (item < 0) break;
             } else if (item >= num_items) {
@@ -609,7 +632,7 @@ int launch_cfg(cudaStream_t stream, int M, int N, int K, int bn, int splits, Wor
         sk.ws = w->ws; sk.n_pad = n_pad; sk.split_stride = m_pad * n_pad;
     }
     const int items = tiles * splits;
-    int* sched = CTA2 ? nullptr : sched_slot(stream);
+    int* sched = sched_slot(stream);
     // dynamic scheduling needs no SM reserve (CTAs that find the SMs taken by a collective simply find no work later)
     const int sms = sched ? sm_count_physical() : sm_count();
     int grid = items < sms ? items : sms;
@@ -721,8 +744,8 @@ int gemm_tc_launch(cudaStream_t stream, int M, int N, int K, const void* A, long
     const bool splittable = (epi.act == KLAB_ACT_NONE && !epi.bias && !epi.residual && !epi.aux_out && epi.dropout_p == 0.0f &&
                              epi.out_dtype == KLAB_F32) || skinny;
     if (splittable) w = get_workspace(stream);
-    // the pair kernel distributes work statically: not while the data-parallel reducer has switched dynamic distribution on
-    const bool pair_ok = cta_pairs_enabled() && M > BM && sched_slot_enabled() == 0 && sm_count() == sm_count_physical();
+    // (the pair kernel distributes work dynamically too; with the static stride it must own every SM)
+    const bool pair_ok = cta_pairs_enabled() && M > BM && (sched_slot_enabled() != 0 || sm_count() == sm_count_physical());
     const bool can_split = w != nullptr;
     GemmCfg model{};
     pick_config(M, N, K, b_mn != 0, can_split, pair_ok ? 2 : 0, WS_BYTES, epi, &model.bn, &model.splits, &model.cta2);

@@ -596,11 +596,34 @@ def test_dynamic_work_distribution_matches_static():
         return outs + [ctx, lse, dQKV, dtab]
 
     static = run_all()
+    # the CTA-pair GEMM (tcgen05.mma.cta_group::2) with its leader-claims-for-the-pair queue: pinned, static vs dynamic
+    def run_pairs():
+        import ctypes as C
+        outs = []
+        lib.lib().klab_gemm_set_force(1, -1, -1)
+        try:
+            for (M, N, K, a_mn, b_mn, od) in [(6144, 1024, 1024, False, True, torch.bfloat16), (4096, 2048, 256, False, False, torch.bfloat16),
+                                              (1024, 4096, 6144, True, True, torch.float32), (300, 520, 136, False, False, torch.bfloat16),
+                                              (40000, 256, 128, False, False, torch.bfloat16)]:
+                A, _ = rnd(K if a_mn else M, M if a_mn else K, dtype=torch.bfloat16, seed=M + 1)
+                B, _ = rnd(K if b_mn else N, N if b_mn else K, dtype=torch.bfloat16, seed=N + 1)
+                outs.append(o.gemm(A, B, M, N, K, a_mn=a_mn, b_mn=b_mn, out_dtype=od))
+                c2 = C.c_int(0)
+                lib.lib().klab_gemm_last_config(None, None, C.byref(c2))
+                assert c2.value == 1, "the CTA-pair kernel was not used"
+        finally:
+            lib.lib().klab_gemm_set_force(-1, -1, -1)
+        return outs
+
+    static_pairs = run_pairs()
     lib.lib().klab_set_dynamic_sched(1)
     try:
         dyn = run_all()
         for s_, d_ in zip(static, dyn):
             assert torch.equal(s_, d_)
+        for rep in range(3):                               # counters re-armed by the last pair: repeated launches agree
+            for s_, d_ in zip(static_pairs, run_pairs()):
+                assert torch.equal(s_, d_)
         # graph replay: the counters must be back at zero after every launch
         A, _ = rnd(2048, 512, dtype=torch.bfloat16, seed=11)
         B, _ = rnd(1024, 512, dtype=torch.bfloat16, seed=12)
