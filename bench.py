@@ -910,7 +910,8 @@ def run_ours(args, w):
             red = getattr(model, "_klab_reducer", None) if cpu is None else None
             line["data_parallel"] = {"weights_identical_across_ranks": dp_sync, "dp_parity": dp_par,
                                      "reducer": "klab GradReducer (grouped in-place NCCL all-reduce per bucket)" if red else "torch DDP",
-                                     "buckets_per_step": getattr(red, "buckets_last_backward", None), "sm_reserve": O.sm_reserve_info(),
+                                     "buckets_per_step": getattr(red, "buckets_last_backward", None),
+                                     "flat_block_buffers_per_step": getattr(red, "flats_last_backward", None), "sm_reserve": O.sm_reserve_info(),
                                      "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS")}
         emit(line)
 

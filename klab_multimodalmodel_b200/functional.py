@@ -11,6 +11,7 @@ autograd graph only.  Citations: HF/ = site-packages/transformers 5.5.0.
 """
 from __future__ import annotations
 
+import math
 import os
 import weakref
 
@@ -273,6 +274,27 @@ class _Side:
             cls.dirty = False
 
 
+def _flat_grads(shapes, device):
+    """One fp32 buffer for all parameter gradients of a block (segments 32-byte aligned) and a view per parameter: the data-parallel
+    reducer then all-reduces ONE large tensor per block instead of a dozen small ones (NCCL's per-operation latency, not its
+    bandwidth, bounds a grouped all-reduce over ~1 000 separate tensors)."""
+    sizes = [(math.prod(s_) + 7) // 8 * 8 for s_ in shapes]
+    flat = torch.empty(sum(sizes), dtype=torch.float32, device=device)
+    views, o = [], 0
+    for s_, n in zip(shapes, sizes):
+        views.append(flat[o:o + math.prod(s_)].view(s_))
+        o += n
+    return flat, views
+
+
+def _publish_flat(params, flat, ok):
+    """Tell the reducer (reducer.GradReducer._on_grad) that the gradients about to be adopted by `params` are slices of `flat`.
+    ok = every parameter's .grad is None right now, i.e. autograd will adopt the slices themselves (no `grad += slice`)."""
+    group = {"left": len(params), "flat": flat} if ok and flat is not None else None
+    for p in params:
+        p._klab_flat = group
+
+
 def _wgrad(dy, x, **kw):
     return _Side.run(O.linear_wgrad, dy, x, **kw)
 
@@ -308,7 +330,8 @@ def _t5_attn_fwd(c, n, kv_src, wq_or_qkv, wkv, wo, resid, table, lut, rz, causal
     return h, qkv, kvbuf, ctxt, lse
 
 
-def _t5_attn_bwd(c, dh, n, kv_src, wq_or_qkv, wkv, wo, qkv, kvbuf, ctxt, lse, table, lut, rz, causal, Lq, Lk, seed, dtable, dh_dropped=None):
+def _t5_attn_bwd(c, dh, n, kv_src, wq_or_qkv, wkv, wo, qkv, kvbuf, ctxt, lse, table, lut, rz, causal, Lq, Lk, seed, dtable, dh_dropped=None,
+                 g_wq=None, g_wkv=None, g_wo=None):
     """dh: gradient of the attention layer's output (residual part handled by the caller); dh_dropped: the same with this
     layer's output-dropout mask already applied (fused into the norm backward that produced dh).
     Returns dn, dkv_src (or None), dWq(kv), dWkv (or None), dWo."""
@@ -319,7 +342,7 @@ def _t5_attn_bwd(c, dh, n, kv_src, wq_or_qkv, wkv, wo, qkv, kvbuf, ctxt, lse, ta
     elif c.p > 0.0:                                      # dropout on the o-projection output (:375 / :406)
         dh = O.dropout_apply(dh, c.p, seed + 1, c.seed_ptr)
     dctx = O.linear_dgrad(dh, wo)
-    dwo = _wgrad(dh, ctxt)
+    dwo = _wgrad(dh, ctxt, out=g_wo)
     dqkv = torch.empty_like(qkv)
     if kv_src is None:
         q, k, v = qkv[:, :inner], qkv[:, inner:2 * inner], qkv[:, 2 * inner:]
@@ -332,11 +355,11 @@ def _t5_attn_bwd(c, dh, n, kv_src, wq_or_qkv, wkv, wo, qkv, kvbuf, ctxt, lse, ta
     O.t5_attention_bwd(q, k, v, ctxt, dctx, lse, dq, dk_, dv, c.B, H, Lq, Lk, dk, bias_table=table, lut=lut, rel_zero=rz,
                        num_buckets=c.num_buckets, causal=causal, dbias_table=dtable, dropout_p=c.p, seed=seed, seed_ptr=c.seed_ptr)
     dn = O.linear_dgrad(dqkv, wq_or_qkv)
-    dwq = _wgrad(dqkv, n)
+    dwq = _wgrad(dqkv, n, out=g_wq)
     if kv_src is None:
         return dn, None, dwq, None, dwo
     dkv_src = _Side.run(O.linear_dgrad, dkvbuf, wkv)    # gradient w.r.t. the encoder output: consumed after the block
-    dwkv = _wgrad(dkvbuf, kv_src)
+    dwkv = _wgrad(dkvbuf, kv_src, out=g_wkv)
     return dn, dkv_src, dwq, dwkv, dwo
 
 
@@ -347,18 +370,18 @@ def _t5_ff_fwd(c, x, ln_w, wi, wo, seed):
     return out, n, rstd, f
 
 
-def _t5_ff_bwd(c, dout, x, ln_w, wi, wo, n, rstd, f, seed, next_seed):
+def _t5_ff_bwd(c, dout, x, ln_w, wi, wo, n, rstd, f, seed, next_seed, g_ln=None, g_wi=None, g_wo=None):
     """next_seed: dropout seed of the sub-layer that consumes dx (its output-dropout mask is applied in the same pass).
     -> dx, dropout(dx) or None, dln, dwi, dwo"""
     dy = O.dropout_apply(dout, c.p, seed + 1, c.seed_ptr) if c.p > 0.0 else dout
     df = O.linear_dgrad(dy, wo, act=L.ACT_RELU_BWD, aux_in=f, dropout_p=c.p, seed=seed, seed_ptr=c.seed_ptr)
-    dwo = _wgrad(dy, f)
+    dwo = _wgrad(dy, f, out=g_wo)
     dn = O.linear_dgrad(df, wi)
-    dwi = _wgrad(df, n)
+    dwi = _wgrad(df, n, out=g_wi)
     if c.p > 0.0:
-        dx, dln, dxd = O.rmsnorm_bwd(dn, x, ln_w, rstd, dres=dout, drop=(c.p, next_seed + 1, c.seed_ptr))
+        dx, dln, dxd = O.rmsnorm_bwd(dn, x, ln_w, rstd, dres=dout, drop=(c.p, next_seed + 1, c.seed_ptr), dgamma_out=g_ln)
     else:
-        (dx, dln), dxd = O.rmsnorm_bwd(dn, x, ln_w, rstd, dres=dout), None
+        (dx, dln), dxd = O.rmsnorm_bwd(dn, x, ln_w, rstd, dres=dout, dgamma_out=g_ln), None
     return dx, dxd, dln, dwi, dwo
 
 
@@ -399,7 +422,8 @@ def _t5_block_fwd_body(x, enc_out, c, save, table, *params):
 
 
 def _t5_block_bwd_body(dout, x, enc_out, *rest):
-    """rest = saved activations (forward order) then consts (c, table, *params) -> (dx, denc | None, dtable | None, *param grads)"""
+    """rest = saved activations (forward order) then consts (c, table, *params)
+    -> (dx, denc | None, dtable | None, *param grads, flat): every parameter gradient is a slice of `flat` (see _flat_grads)"""
     n_acts = 16 if enc_out is not None else 9
     acts, (c, table, *params) = rest[:n_acts], rest[n_acts:]
     cd = x.dtype
@@ -407,34 +431,39 @@ def _t5_block_bwd_body(dout, x, enc_out, *rest):
     ws = _t5_operands(c, params, cd, "peek")
     seed = c.seed
     inner = c.H * c.dk
+    d = x.shape[1]
     dtable = torch.zeros_like(table) if table is not None else None
     denc = None
     if dec:
         n0, rstd0, qkv, ctxt, lse, h1, n1, rstd1, qc, kvbuf, ctx2, lse2, h2, n2, rstd2, f = acts
         ln0, ln1, ln2 = params[0], params[5], params[10]
         wqkv, w_o, w_i, w_ff, w_cq, w_ckv, w_co = ws
-        dh2, dh2d, dln2, dwi, dwo_ff = _t5_ff_bwd(c, dout, h2, ln2, w_i, w_ff, n2, rstd2, f, seed + 4, seed + 2)
+        flat, (g_ln0, g_qkv, g_o, g_ln1, g_cq, g_ckv, g_co, g_ln2, g_wi, g_ff) = _flat_grads(
+            [(d,), (3 * inner, d), (d, inner), (d,), (inner, d), (2 * inner, d), (d, inner), (d,), tuple(w_i.shape), tuple(w_ff.shape)], x.device)
+        dh2, dh2d, dln2, dwi, dwo_ff = _t5_ff_bwd(c, dout, h2, ln2, w_i, w_ff, n2, rstd2, f, seed + 4, seed + 2, g_ln=g_ln2, g_wi=g_wi, g_wo=g_ff)
         dn1, denc, dwcq, dwckv, dwco = _t5_attn_bwd(c, dh2, n1, enc_out, w_cq, w_ckv, w_co, qc, kvbuf, ctx2, lse2, None, None, 0,
-                                                    False, c.L, c.Le, seed + 2, None, dh_dropped=dh2d)
+                                                    False, c.L, c.Le, seed + 2, None, dh_dropped=dh2d, g_wq=g_cq, g_wkv=g_ckv, g_wo=g_co)
         if c.p > 0.0:                                    # + the self-attention layer's output-dropout mask for its backward
-            dh1, dln1, dh1d = O.rmsnorm_bwd(dn1, h1, ln1, rstd1, dres=dh2, drop=(c.p, seed + 1, c.seed_ptr))
+            dh1, dln1, dh1d = O.rmsnorm_bwd(dn1, h1, ln1, rstd1, dres=dh2, drop=(c.p, seed + 1, c.seed_ptr), dgamma_out=g_ln1)
         else:
-            (dh1, dln1), dh1d = O.rmsnorm_bwd(dn1, h1, ln1, rstd1, dres=dh2), None
+            (dh1, dln1), dh1d = O.rmsnorm_bwd(dn1, h1, ln1, rstd1, dres=dh2, dgamma_out=g_ln1), None
     else:
         n0, rstd0, qkv, ctxt, lse, h1, n2, rstd2, f = acts
         ln0, ln1 = params[0], params[5]
         wqkv, w_o, w_i, w_ff = ws
-        dh1, dh1d, dln1, dwi, dwo_ff = _t5_ff_bwd(c, dout, h1, ln1, w_i, w_ff, n2, rstd2, f, seed + 4, seed)
+        flat, (g_ln0, g_qkv, g_o, g_ln1, g_wi, g_ff) = _flat_grads(
+            [(d,), (3 * inner, d), (d, inner), (d,), tuple(w_i.shape), tuple(w_ff.shape)], x.device)
+        dh1, dh1d, dln1, dwi, dwo_ff = _t5_ff_bwd(c, dout, h1, ln1, w_i, w_ff, n2, rstd2, f, seed + 4, seed, g_ln=g_ln1, g_wi=g_wi, g_wo=g_ff)
     dn0, _, dwqkv, _, dwo = _t5_attn_bwd(c, dh1, n0, None, wqkv, None, w_o, qkv, None, ctxt, lse, table, c.lut, c.rz, dec,
-                                         c.L, c.L, seed, dtable, dh_dropped=dh1d)
-    dx, dln0 = O.rmsnorm_bwd(dn0, x, ln0, rstd0, dres=dh1)
+                                         c.L, c.L, seed, dtable, dh_dropped=dh1d, g_wq=g_qkv, g_wo=g_o)
+    dx, dln0 = O.rmsnorm_bwd(dn0, x, ln0, rstd0, dres=dh1, dgamma_out=g_ln0)
     _Side.join()
     gq, gk, gv = dwqkv[:inner], dwqkv[inner:2 * inner], dwqkv[2 * inner:]
     if dec:
         grads = (dln0, gq, gk, gv, dwo, dln1, dwcq, dwckv[:inner], dwckv[inner:], dwco, dln2, dwi, dwo_ff)
     else:
         grads = (dln0, gq, gk, gv, dwo, dln1, dwi, dwo_ff)
-    return (dx, denc, dtable) + grads
+    return (dx, denc, dtable) + grads + (flat,)
 
 
 class T5BlockFn(torch.autograd.Function):
@@ -472,7 +501,8 @@ class T5BlockFn(torch.autograd.Function):
         tok, ctx.token = getattr(ctx, "token", None), None
         if tok is not None:
             tok.release()
-        return (None,) + _grad_outputs(outs, graphed)
+        _publish_flat(params, outs[-1], all(p.grad is None for p in params))
+        return (None,) + _grad_outputs(outs[:-1], graphed)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -726,52 +756,59 @@ _N_SWIN_GRADS = 19            # one per parameter of a block, in flat_params() o
 
 
 def _swin_block_bwd_body(dout, x, *rest):
-    """rest = saved activations (15), [accumulators (21): the static outputs of an earlier run of this region,] c, params (19)
-    -> (dx, 19 parameter gradients, dwqkv, dbqkv).  The last two are the buffers the q / k / v weight and bias gradients are
-    views of.  With accumulators every parameter gradient is ADDED into the given buffer by the kernel that produces it (GEMM
-    epilogue / norm / colsum / CPB kernels all have an accumulate mode) and the same buffers are returned."""
+    """rest = saved activations (15), [accumulators (22): the static outputs of an earlier run of this region,] c, params (19)
+    -> (dx, 19 parameter gradients, dwqkv, dbqkv, flat).  Every parameter gradient is a slice of `flat` (see _flat_grads); dwqkv /
+    dbqkv are the slices the q / k / v weight and bias gradients are views of.  With accumulators every parameter gradient is ADDED
+    into the given buffer by the kernel that produces it (GEMM epilogue / norm / colsum / CPB kernels all have an accumulate mode)
+    and the same buffers are returned."""
     (qkv, bias16, hidden, tab, ctxt, lse, a, mean1, rstd1, h, m_pre, m_act, m2, mean2, rstd2), rest = rest[:_N_SWIN_ACTS], rest[_N_SWIN_ACTS:]
     acc = len(rest) > 1 + _N_SWIN_GRADS
     if acc:
-        go, rest = rest[:_N_SWIN_GRADS + 2], rest[_N_SWIN_GRADS + 2:]
-        (o_ls, o_w1, o_b1, o_w2, _gq, _gbq, _gk, _gv, _gbv, o_pw, o_pb, o_g1, o_be1, o_f1w, o_f1b, o_f2w, o_f2b, o_g2, o_be2, o_wqkv, o_bqkv) = go
+        go, rest = rest[:_N_SWIN_GRADS + 3], rest[_N_SWIN_GRADS + 3:]
+        (o_ls, o_w1, o_b1, o_w2, _gq, _gbq, _gk, _gv, _gbv, o_pw, o_pb, o_g1, o_be1, o_f1w, o_f1b, o_f2w, o_f2b, o_g2, o_be2, o_wqkv, o_bqkv,
+         flat) = go
     c, params = rest[0], rest[1:]
     (ls, w1, b1, w2, qw, qb, kw, vw, vb, pw, pb, g1, be1, f1w, f1b, f2w, f2b, g2, be2) = params
     cd = x.dtype
     C_ = x.shape[1]
     wqkv, w_p, w_f1, w_f2 = _swin_operands(c, params, cd, "peek")
+    if not acc:
+        flat, (o_ls, o_w1, o_b1, o_w2, o_wqkv, o_bqkv, o_pw, o_pb, o_g1, o_be1, o_f1w, o_f1b, o_f2w, o_f2b, o_g2, o_be2) = _flat_grads(
+            [(c.heads,), tuple(w1.shape), tuple(b1.shape), tuple(w2.shape), (3 * C_, C_), (3 * C_,), (C_, C_), (C_,), (C_,), (C_,),
+             (4 * C_, C_), (4 * C_,), (C_, 4 * C_), (C_,), (C_,), (C_,)], x.device)
 
-    def into(t):                                                         # keyword arguments of an accumulating GEMM / colsum
-        return dict(out=t, accumulate=True) if acc else {}
+    def wg(t):                                                           # keyword arguments of a weight-gradient GEMM into `t`
+        return dict(out=t, accumulate=acc)
 
-    dm2, dg2, dbe2 = O.layernorm_bwd(dout, m2, g2, mean2, rstd2, **(dict(dgamma=o_g2, dbeta=o_be2) if acc else {}))
+    dm2, dg2, dbe2 = O.layernorm_bwd(dout, m2, g2, mean2, rstd2, dgamma=o_g2, dbeta=o_be2, accumulate=acc)
     dm_pre = O.linear_dgrad(dm2, w_f2, act=L.ACT_MUL_AUX, aux_in=m_pre)                  # m_pre holds gelu'(fc1 output), saved by the forward epilogue
-    df2w = _wgrad(dm2, m_act, **(into(o_f2w) if acc else {}))
-    df2b = _Side.run(O.colsum, dm2, **(dict(out=o_f2b) if acc else {}))
+    df2w = _wgrad(dm2, m_act, **wg(o_f2w))
+    df2b = _Side.run(O.colsum, dm2, out=o_f2b, accumulate=acc)
     dh = O.linear_dgrad(dm_pre, w_f1, residual=dout)                     # + residual path of the second norm
-    df1w = _wgrad(dm_pre, h, **(into(o_f1w) if acc else {}))
-    df1b = _Side.run(O.colsum, dm_pre, **(dict(out=o_f1b) if acc else {}))
-    da, dg1, dbe1 = O.layernorm_bwd(dh, a, g1, mean1, rstd1, **(dict(dgamma=o_g1, dbeta=o_be1) if acc else {}))
+    df1w = _wgrad(dm_pre, h, **wg(o_f1w))
+    df1b = _Side.run(O.colsum, dm_pre, out=o_f1b, accumulate=acc)
+    da, dg1, dbe1 = O.layernorm_bwd(dh, a, g1, mean1, rstd1, dgamma=o_g1, dbeta=o_be1, accumulate=acc)
     dctx = O.linear_dgrad(da, w_p)
-    dpw = _wgrad(da, ctxt, **(into(o_pw) if acc else {}))
-    dpb = _Side.run(O.colsum, da, **(dict(out=o_pb) if acc else {}))
+    dpw = _wgrad(da, ctxt, **wg(o_pw))
+    dpb = _Side.run(O.colsum, da, out=o_pb, accumulate=acc)
     dqkv = torch.empty_like(qkv)
     q, k, v = qkv[:, :C_], qkv[:, C_:2 * C_], qkv[:, 2 * C_:]
     lsv = ls.detach().reshape(-1)
     dbias, dls = O.swin_attention_bwd(q, k, v, ctxt, dctx, dqkv[:, :C_], dqkv[:, C_:2 * C_], dqkv[:, 2 * C_:], c.B, c.res,
-                                      c.heads, c.hd, c.w, c.shift, lsv, bias16, lse)
+                                      c.heads, c.hd, c.w, c.shift, lsv, bias16, lse, dls_out=None if acc else o_ls.view(-1))
     if acc:
         O.colsum(dls.view(1, -1), out=o_ls.view(-1))                     # o_ls += dls (a one-row column sum)
-        dls = o_ls.view(-1)
+    dls = o_ls.view(-1)
     w2d = w2.detach()                                                    # position-bias MLP gradients: off the critical path
+    trio = (o_w1, o_b1, o_w2)
     dw1, db1, dw2 = _Side.run(lambda *_: O.swin_cpb_bwd(c.coords, c.index, w2d, hidden, tab, dbias, c.heads, c.N,
-                                                         acc_into=(o_w1, o_b1, o_w2) if acc else None), dbias, hidden, tab, w2d)
+                                                         acc_into=trio if acc else None, out=None if acc else trio), dbias, hidden, tab, w2d)
     dx = O.linear_dgrad(dqkv, wqkv, residual=dh)                          # + residual path of the first norm
-    dwqkv = _wgrad(dqkv, x, **(into(o_wqkv) if acc else {}))
-    dbqkv = _Side.run(O.colsum, dqkv, **(dict(out=o_bqkv) if acc else {}))
+    dwqkv = _wgrad(dqkv, x, **wg(o_wqkv))
+    dbqkv = _Side.run(O.colsum, dqkv, out=o_bqkv, accumulate=acc)
     _Side.join()
     return (dx, dls.view(ls.shape), dw1, db1, dw2, dwqkv[:C_], dbqkv[:C_], dwqkv[C_:2 * C_], dwqkv[2 * C_:], dbqkv[2 * C_:],
-            dpw, dpb, dg1, dbe1, df1w, df1b, df2w, df2b, dg2, dbe2, dwqkv, dbqkv)
+            dpw, dpb, dg1, dbe1, df1w, df1b, df2w, df2b, dg2, dbe2, dwqkv, dbqkv, flat)
 
 
 class SwinBlockFn(torch.autograd.Function):
@@ -835,4 +872,5 @@ class SwinBlockFn(torch.autograd.Function):
         tok, ctx.token = getattr(ctx, "token", None), None
         if tok is not None:
             tok.release()
+        _publish_flat(params, outs[-1], all(p.grad is None for p in params))
         return (None,) + _grad_outputs(outs[:1 + _N_SWIN_GRADS], graphed or use_acc)

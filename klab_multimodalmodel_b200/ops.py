@@ -147,13 +147,14 @@ def rmsnorm_fwd(x, gamma, eps, *, out=None, out_rows_per_group=0, out_group_stri
     return y, rstd
 
 
-def rmsnorm_bwd(dy, x, gamma, rstd, dres=None, dgamma=None, drop=None):
-    """-> (dx, dgamma), or (dx, dgamma, dropout(dx)) with drop = (p, seed, seed_ptr): the mask `dropout_apply` would draw."""
+def rmsnorm_bwd(dy, x, gamma, rstd, dres=None, dgamma=None, drop=None, dgamma_out=None):
+    """-> (dx, dgamma), or (dx, dgamma, dropout(dx)) with drop = (p, seed, seed_ptr): the mask `dropout_apply` would draw.
+    dgamma given: the gain gradient is ACCUMULATED into it; dgamma_out given: it is WRITTEN there (a slice of a flat gradient buffer)."""
     rows, d = x.shape
     dx = torch.empty(rows, d, dtype=x.dtype, device=x.device)
     acc = dgamma is not None
     if dgamma is None:
-        dgamma = torch.empty(d, dtype=torch.float32, device=x.device)
+        dgamma = dgamma_out if dgamma_out is not None else torch.empty(d, dtype=torch.float32, device=x.device)
     ws = _bytes(L.lib().klab_norm_bwd_workspace_bytes(rows, d), x.device)
     if drop is not None and drop[0] > 0.0:
         p, seed, seed_ptr = drop
@@ -183,13 +184,15 @@ def layernorm_fwd(x, gamma, beta, eps, residual=None, *, out=None, out_rows_per_
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, *, dy_ld=None, dy_rows_per_group=0, dy_group_stride=0, dgamma=None, dbeta=None):
-    """dgamma / dbeta given: the parameter gradients are ACCUMULATED into them (both or neither)."""
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, *, dy_ld=None, dy_rows_per_group=0, dy_group_stride=0, dgamma=None, dbeta=None,
+                  accumulate=True):
+    """dgamma / dbeta given (both or neither): the parameter gradients are accumulated into them (`accumulate`) or written there."""
     rows, d = x.shape
     dx = torch.empty(rows, d, dtype=x.dtype, device=x.device)
-    acc = dgamma is not None
-    assert acc == (dbeta is not None)
-    if not acc:
+    given = dgamma is not None
+    assert given == (dbeta is not None)
+    acc = given and accumulate
+    if not given:
         dgamma = torch.empty(d, dtype=torch.float32, device=x.device)
         dbeta = torch.empty(d, dtype=torch.float32, device=x.device)
     ws = _bytes(L.lib().klab_norm_bwd_workspace_bytes(rows, d), x.device)
@@ -200,9 +203,10 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, *, dy_ld=None, dy_rows_pe
     return dx, dgamma, dbeta
 
 
-def colsum(x, out=None):
+def colsum(x, out=None, accumulate=True):
+    """out given: the column sums are accumulated into it (`accumulate`) or written there."""
     rows, d = x.shape
-    acc = out is not None
+    acc = out is not None and accumulate
     if out is None:
         out = torch.empty(d, dtype=torch.float32, device=x.device)
     ws = _bytes(L.lib().klab_colsum_workspace_bytes(rows, d), x.device)
@@ -295,17 +299,20 @@ def swin_cpb_fwd(coords, index, w1, b1, w2, heads, n_tokens):
     return bias, hidden, tab
 
 
-def swin_cpb_bwd(coords, index, w2, hidden, tab, dbias, heads, n_tokens, acc_into=None):
-    """acc_into = (dw1, db1, dw2): the gradients are ACCUMULATED into these tensors instead of freshly allocated ones."""
+def swin_cpb_bwd(coords, index, w2, hidden, tab, dbias, heads, n_tokens, acc_into=None, out=None):
+    """acc_into = (dw1, db1, dw2): the gradients are ACCUMULATED into these tensors; out = (dw1, db1, dw2): they are WRITTEN there;
+    neither: freshly allocated."""
     T, U = coords.shape[0], hidden.shape[1]
     dev = coords.device
     dtab = torch.empty(T, heads, dtype=torch.float32, device=dev)
-    if acc_into is None:
+    if acc_into is not None:
+        dw1, db1, dw2 = acc_into
+    elif out is not None:
+        dw1, db1, dw2 = out
+    else:
         dw1 = torch.empty(U, 2, dtype=torch.float32, device=dev)
         db1 = torch.empty(U, dtype=torch.float32, device=dev)
         dw2 = torch.empty(heads, U, dtype=torch.float32, device=dev)
-    else:
-        dw1, db1, dw2 = acc_into
     L.check(L.lib().klab_swin_cpb_bwd(_stream(), T, U, heads, n_tokens, coords.data_ptr(), index.data_ptr(), w2.data_ptr(),
                                       hidden.data_ptr(), tab.data_ptr(), dbias.data_ptr(), dtab.data_ptr(), dw1.data_ptr(),
                                       db1.data_ptr(), dw2.data_ptr(), int(acc_into is not None)))
@@ -324,11 +331,11 @@ def swin_attention_fwd(q, k, v, B, res, heads, hd, window, shift, logit_scale, b
     return ctx, lse
 
 
-def swin_attention_bwd(q, k, v, ctx, dctx, dq, dk, dv, B, res, heads, hd, window, shift, logit_scale, bias, lse):
+def swin_attention_bwd(q, k, v, ctx, dctx, dq, dk, dv, B, res, heads, hd, window, shift, logit_scale, bias, lse, dls_out=None):
     n = window * window
     assert dq.stride(0) == q.stride(0) == dk.stride(0) == dv.stride(0) and dctx.stride(0) == ctx.stride(0)
     dbias = torch.empty(heads, n, n, dtype=torch.float32, device=q.device)
-    dls = torch.empty(heads, dtype=torch.float32, device=q.device)
+    dls = torch.empty(heads, dtype=torch.float32, device=q.device) if dls_out is None else dls_out
     L.check(L.lib().klab_swin_attention_bwd(_stream(), _DT[q.dtype], B, res, heads, hd, window, shift, q.data_ptr(), k.data_ptr(),
                                             v.data_ptr(), q.stride(0), ctx.data_ptr(), dctx.data_ptr(), ctx.stride(0), dq.data_ptr(),
                                             dk.data_ptr(), dv.data_ptr(), logit_scale.data_ptr(), bias.data_ptr(), lse.data_ptr(),

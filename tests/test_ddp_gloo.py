@@ -102,6 +102,38 @@ def _worker(rank, world, port, q):
         ddp.reducer.prepare_for_backward([])
         sum((p * (rank + 1.0)).sum() for p in trainable).backward()
         assert all(torch.allclose(p.grad, torch.full_like(p.grad, (1.0 + world) / 2.0)) for p in trainable)
+        # flat per-block gradient buffers (functional._flat_grads): the gradients of a block are slices of one buffer, which is
+        # reduced as ONE tensor once its last parameter has reported; a parameter that accumulated elsewhere is reduced on its own
+        from klab_multimodalmodel_b200 import functional as Fn
+
+        class FlatBlock(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, scale, *ps):
+                ctx.ps, ctx.scale = ps, scale
+                return torch.zeros((), requires_grad=True) + sum(p.detach().sum() for p in ps) * 0
+
+            @staticmethod
+            def backward(ctx, g):
+                flat, views = Fn._flat_grads([tuple(p.shape) for p in ctx.ps], "cpu")
+                flat.zero_()
+                for v in views:
+                    v.fill_(ctx.scale)
+                Fn._publish_flat(ctx.ps, flat, all(p.grad is None for p in ctx.ps))
+                return (None,) + tuple(v.detach() for v in views)
+
+        model._klab_reducer.bucket_bytes = 1 << 30
+        group_ps = trainable[:5]
+        for p in trainable:
+            p.grad = None
+        ddp.reducer.prepare_for_backward([])
+        FlatBlock.apply(rank + 1.0, *group_ps).backward()
+        assert model._klab_reducer.flats_last_backward == 1, model._klab_reducer.flats_last_backward
+        assert all(torch.allclose(p.grad, torch.full_like(p.grad, (1.0 + world) / 2.0)) for p in group_ps)
+        # second backward without zeroing: autograd adds into the existing .grad, the flat buffer is NOT what gets reduced
+        ddp.reducer.prepare_for_backward([])
+        FlatBlock.apply(10.0 * (rank + 1.0), *group_ps).backward()
+        assert model._klab_reducer.flats_last_backward == 0
+        assert all(torch.allclose(p.grad, torch.full_like(p.grad, 11.0 * (1.0 + world) / 2.0)) for p in group_ps)
         # bench helpers: per-rank shards differ; timing is the max over ranks
         w = dict(bench.WORKLOADS["tiny"])
         px, src, tgt = bench.synth_batch(w, 512, 1234 + rank, pin=False)
