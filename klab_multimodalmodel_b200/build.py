@@ -2,12 +2,14 @@
 
     python -m klab_multimodalmodel_b200.build [--force] [--verbose]
 
-Object files are cached under csrc/build/ keyed on source + header mtimes, so a rebuild after touching one
-kernel only recompiles that translation unit.
+Object files are cached under csrc/build/ keyed on a HASH of (source, every header, compiler flags) stored next to each
+object, so a rebuild after touching one kernel only recompiles that translation unit and a stale cache under a fresh checkout
+(mtimes say nothing there) is never reused.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import os
 import shutil
 import subprocess
@@ -39,27 +41,40 @@ def sources() -> list[str]:
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _headers_mtime() -> float:
-    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+def _headers_digest() -> bytes:
+    hs = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
     hs.append(os.path.join(os.path.dirname(HERE), "include", "klab_b200.h"))
-    return max(os.path.getmtime(h) for h in hs)
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for path in hs:
+        with open(path, "rb") as fh:
+            h.update(path.encode() + b"\0" + fh.read())
+    return h.digest()
+
+
+def _stamp(src: str, hdr: bytes) -> str:
+    with open(src, "rb") as fh:
+        return hashlib.sha256(hdr + fh.read()).hexdigest()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
-    hdr_m = _headers_mtime()
+    hdr = _headers_digest()
     jobs = []
     objs = []
+    stamps = {}
     for src in sources():
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        stale = force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_m)
+        want = _stamp(src, hdr)
+        have = open(obj + ".sha256").read().strip() if os.path.exists(obj + ".sha256") else ""
+        stale = force or not os.path.exists(obj) or have != want
         if stale:
             cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append(cmd)
+            stamps[obj] = want
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -72,6 +87,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
                     sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
                 if r.returncode != 0:
                     raise RuntimeError(f"nvcc failed on {cmd[-3]}")
+                with open(cmd[-1] + ".sha256", "w") as fh:
+                    fh.write(stamps[cmd[-1]])
     if jobs or not os.path.exists(LIB):
         cmd = [nvcc, "-shared", "-o", LIB, *objs, "-cudart", "static"]
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -27,6 +27,9 @@ import torch
 import torch.distributed as dist
 
 
+_HAS_COALESCING = hasattr(dist, "_coalescing_manager")          # private API of torch.distributed (present in 2.1 ... 2.11)
+
+
 class GradReducer:
     def __init__(self, params, group=None, bucket_bytes: int | None = None):
         self.group = group
@@ -89,10 +92,13 @@ class GradReducer:
         tensors, self._pending, self._pending_bytes = self._pending, [], 0
         op = dist.ReduceOp.AVG if self._native_avg else dist.ReduceOp.SUM
         dev = tensors[0].device if tensors[0].is_cuda else None
-        with dist._coalescing_manager(self.group, dev, async_ops=True) as cm:
-            for t in tensors:
-                dist.all_reduce(t, op=op, group=self.group)
-        self._works.append(cm)
+        if _HAS_COALESCING:
+            with dist._coalescing_manager(self.group, dev, async_ops=True) as cm:          # one ncclGroupStart / End around the bucket
+                for t in tensors:
+                    dist.all_reduce(t, op=op, group=self.group)
+            self._works.append(cm)
+        else:                                             # torch without the (private) coalescing manager: one async collective per tensor
+            self._works.extend(dist.all_reduce(t, op=op, group=self.group, async_op=True) for t in tensors)
         if not self._native_avg:
             self._summed.extend(tensors)
         self._count += 1
