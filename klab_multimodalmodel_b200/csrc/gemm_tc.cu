@@ -66,6 +66,7 @@ struct SplitK {
     long long n_pad;      // row stride of a partial matrix
     long long split_stride;   // m_pad * n_pad
     int splits;
+    int epi_prefetch;     // L2 prefetch of the operands the epilogue reads (see the epilogue warps); KLAB_GEMM_EPI_PREFETCH=0 -> off
 };
 
 // Epilogue modes of the kernel.  EPI_STORE is the generic fused epilogue (gemm.cuh).  The two CE modes turn the LM-head GEMM
@@ -308,6 +309,38 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if constexpr (CTA2) mbar_arrive_leader(bar);
             else mbar_arrive(bar);
         };
+        // Operands the epilogue READS once per output element (saved activation, residual, the output itself when accumulating)
+        // arrive through dependent per-chunk loads: one 32-byte request per thread in flight, i.e. 16 KiB per SM per HBM round
+        // trip, so a 128 x 256 tile with a bf16 aux operand (64 KiB) costs four serial DRAM latencies -- ~9 us per tile where the
+        // K <= 1024 main loop needs 2-6 us (profiles/r02_gemm_top_ncu.txt: 25-47 % tensor pipe on exactly those signatures).
+        // Every thread therefore asks L2 for its row's lines of the whole tile up front (thread of chunk quarter q: lines q, q + 4,
+        // ...), with the static schedule one item AHEAD; the chunk loop's loads then hit L2.
+        const bool epi_reads = EPI == EPI_STORE && splits == 1 && sk.epi_prefetch != 0 &&
+                               ((epi.aux_in != nullptr && epi.act >= KLAB_ACT_RELU_BWD) || epi.residual != nullptr || epi.accumulate);
+        auto prefetch_item = [&](int it) {
+            const long long prow = static_cast<long long>(it / num_n) * TM + rank * BM + sub * 32 + lane;
+            const int pn0 = (it % num_n) * BN;
+            const int cols = prow < M ? min(BN, N - pn0) : 0;
+            const int o0 = quarter * 128;                          // a tile row is at most 256 fp32 = 8 lines: two per thread
+            if (epi.aux_in && epi.act >= KLAB_ACT_RELU_BWD) {       // (aux_in is read by the activation-backward modes only)
+                const int es = epi.aux_in_dtype == KLAB_BF16 ? 2 : 4;
+                const char* p = reinterpret_cast<const char*>(epi.aux_in) + (prow * epi.ld_aux_in + pn0) * es + o0;
+                if (o0 < cols * es) prefetch_l2(p);
+                if (o0 + 512 < cols * es) prefetch_l2(p + 512);
+            }
+            if (epi.residual) {
+                const int es = epi.res_dtype == KLAB_BF16 ? 2 : 4;
+                const char* p = reinterpret_cast<const char*>(epi.residual) + (prow * epi.ldr + pn0) * es + o0;
+                if (o0 < cols * es) prefetch_l2(p);
+                if (o0 + 512 < cols * es) prefetch_l2(p + 512);
+            }
+            if (epi.accumulate) {
+                const int es = epi.out_dtype == KLAB_BF16 ? 2 : 4;
+                const char* p = reinterpret_cast<const char*>(D) + (prow * ldd + pn0) * es + o0;
+                if (o0 < cols * es) prefetch_l2(p);
+                if (o0 + 512 < cols * es) prefetch_l2(p + 512);
+            }
+        };
         int acc = 0;
         uint32_t acc_phase = 0;
         int sq = 0;
@@ -327,6 +360,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (item < 0) break;
             } else if (item >= num_items) {
                 break;
+            }
+            if (epi_reads) {
+                if (sched || item == work_id) prefetch_item(item);                       // (dynamic distribution: the next item is not known yet)
+                if (!sched && item + work_stride < num_items) prefetch_item(item + work_stride);
             }
             const int tile = item / splits, split = item - tile * splits;
             const int m0 = (tile / num_n) * TM + rank * BM;
@@ -626,7 +663,8 @@ int launch_cfg(cudaStream_t stream, int M, int N, int K, int bn, int splits, Wor
         attr_set = true;
     }
     const int tiles = ((M + TM - 1) / TM) * ((N + bn - 1) / bn);
-    SplitK sk{nullptr, 0, 0, splits};
+    static const bool epi_pf = []() { const char* e = getenv("KLAB_GEMM_EPI_PREFETCH"); return !(e && e[0] == '0'); }();
+    SplitK sk{nullptr, 0, 0, splits, epi_pf ? 1 : 0};
     if (splits > 1) {
         const long long m_pad = 1ll * ((M + TM - 1) / TM) * TM, n_pad = 1ll * ((N + bn - 1) / bn) * bn;
         sk.ws = w->ws; sk.n_pad = n_pad; sk.split_stride = m_pad * n_pad;

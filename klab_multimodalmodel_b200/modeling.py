@@ -395,6 +395,18 @@ class T5ForConditionalGeneration(nn.Module):
             _load_checkpoint_dir(m, path)
         return m.eval()
 
+    def state_dict(self, *args, **kwargs):
+        from .optim import wait_pending_updates
+        if torch.cuda.is_available():
+            wait_pending_updates(self.shared.weight.device if self.shared.weight.is_cuda else None)
+        return super().state_dict(*args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        from .optim import wait_pending_updates
+        if torch.cuda.is_available():
+            wait_pending_updates(self.shared.weight.device if self.shared.weight.is_cuda else None)
+        return super().load_state_dict(*args, **kwargs)
+
     def loss_from_embeds(self, embeds, B, Le, labels):
         """embeds: [B*Le, d] encoder inputs_embeds (compute dtype); labels [B, Lt] int64 -> 0-dim fp32 loss
         (T5ForConditionalGeneration.forward(inputs_embeds, labels).loss, HF/models/t5/modeling_t5.py:1070-1117)."""

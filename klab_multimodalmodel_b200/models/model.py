@@ -27,6 +27,7 @@ from .. import functional as Fn
 from ..generation import greedy_generate
 from ..graphs import POOL
 from ..modeling import Swinv2Model, T5EncoderModel, T5ForConditionalGeneration, _compute_dtype, advance_step_seed
+from ..optim import wait_pending_updates
 
 
 class MyModel(nn.Module):
@@ -107,6 +108,7 @@ class MyModel(nn.Module):
         if self.transformer.training and not Fn.pending_backward():
             advance_step_seed(images["pixel_values"].device)          # fresh dropout masks for this step (device-side counter)
         emb, B, Le = self._concat_embeddings(images, source_encoding)
+        wait_pending_updates(emb.device)          # a fused-Adam step still running on its side stream wrote the transformer's weights
         if return_loss:
             return self.transformer.loss_from_embeds(emb, B, Le, target_encoding["input_ids"])
         else:

@@ -9,14 +9,36 @@ sm_100 device.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib as L
 
+# The update of step i only has to be complete before the TRAINABLE transformer runs in step i + 1; the image tower and the frozen
+# text tower that open every forward (/root/reference/models/model.py:20-22) do not read what Adam writes (train.py:28: the
+# optimizer owns model.transformer only).  The fused kernel is pure HBM traffic (3.4 ms for T5-large), so it is issued on a side
+# stream and overlaps the next step's towers; whoever is about to touch the transformer's weights on the compute stream calls
+# `wait_pending_updates()` first (MyModel.forward before the transformer, T5ForConditionalGeneration.state_dict / load_state_dict,
+# greedy decoding).  KLAB_ADAM_OVERLAP=0 keeps everything on the current stream.
+OVERLAP = os.environ.get("KLAB_ADAM_OVERLAP", "1") != "0"
+_SIDE: dict = {}
+_DONE: dict = {}
+
+
+def wait_pending_updates(device=None) -> None:
+    """Make the current stream wait (on the device, not the host) for optimizer steps still running on the side stream."""
+    if not _DONE:
+        return
+    idx = torch.cuda.current_device() if device is None or device.index is None else device.index
+    ev = _DONE.pop(idx, None)
+    if ev is not None:
+        torch.cuda.current_stream(idx).wait_event(ev)
+
 
 class Adam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=False, *, maximize=False,
-                 grad_scale=1.0):
+                 grad_scale=1.0, overlap=True):
         if amsgrad or maximize:
             raise NotImplementedError("klab Adam: amsgrad / maximize are not used by the reference and not implemented")
         if not 0.0 <= lr or not 0.0 <= eps or not 0.0 <= betas[0] < 1.0 or not 0.0 <= betas[1] < 1.0 or not 0.0 <= weight_decay:
@@ -24,6 +46,7 @@ class Adam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False, maximize=False,
                                       grad_scale=grad_scale))
         self._tables: dict = {}
+        self.overlap = overlap              # run the update on a side stream (see wait_pending_updates); False: on the current stream
 
     def _table(self, key, items):
         """items: list of (p, g, m, v, w16 pointer or 0).  Device tables are rebuilt only when a pointer changed (with CUDA graphs the gradient
@@ -97,10 +120,27 @@ class Adam(torch.optim.Optimizer):
             b1, b2 = group["betas"]
             for t, items in by_step.items():
                 table, blockmap, nblocks = self._table((gi, len(by_step) > 1 and t), items)
-                stream = torch.cuda.current_stream(items[0][0].device).cuda_stream
-                L.check(L.lib().klab_adam_step(stream, table.data_ptr(), blockmap.data_ptr(), nblocks, float(group["lr"]), float(b1),
+                dev = items[0][0].device
+                main = torch.cuda.current_stream(dev)
+                if OVERLAP and self.overlap:
+                    side = _SIDE.get(dev.index)
+                    if side is None:
+                        side = _SIDE[dev.index] = torch.cuda.Stream(dev)
+                    wait_pending_updates(dev)                      # (an earlier update nobody waited for: keep the steps ordered)
+                    side.wait_stream(main)                         # gradients (and the device tables) are ready
+                    for it in items:
+                        it[1].record_stream(side)                  # zero_grad(set_to_none) may free the gradient right after this call
+                    table.record_stream(side)
+                    run_on = side
+                else:
+                    run_on = main
+                L.check(L.lib().klab_adam_step(run_on.cuda_stream, table.data_ptr(), blockmap.data_ptr(), nblocks, float(group["lr"]), float(b1),
                                                float(b2), float(group["eps"]), float(group["weight_decay"]), t,
                                                float(group.get("grad_scale", 1.0))))
+                if run_on is not main:
+                    ev = torch.cuda.Event()
+                    ev.record(run_on)
+                    _DONE[dev.index] = ev
                 # the kernel wrote the masters through raw pointers: tell autograd (and every operand cache) that they changed
                 torch.autograd.graph.increment_version([it[0] for it in items])
             mark_operands_fresh([e for e, ids in written.values() if ids == set(e[5])])
