@@ -319,8 +319,6 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&r)[8]) {
                  "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
-// Pull the 128-byte line that holds `p` into L2 (no register, no scoreboard entry: fire and forget).
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start while its
 // predecessor is still running; it must not touch global memory the predecessor reads or writes before pdl_wait().
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -55,8 +55,7 @@ constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;     // 576
 constexpr int A_TILE_BYTES = BM * BK * 2;                // 16 KiB
 constexpr int MAX_STAGES = 8;
 constexpr int CTRL_BYTES = 1024;                         // barriers + tmem pointer + split-K flag
-constexpr int SMEM_BYTES = 227 * 1024;                   // everything an SM has: one CTA per SM
-constexpr int RING_BYTES = SMEM_BYTES - 1024 /*align slack*/ - CTRL_BYTES;
+constexpr int SMEM_BYTES_MAX = 227 * 1024;               // everything an SM has: one CTA per SM
 constexpr int ACC_STRIDE = 256;                          // TMEM columns between the two accumulator stages
 constexpr int CH = 16;                                   // epilogue chunk (columns per tcgen05.ld)
 constexpr int SQ = 4;                                    // depth of the in-CTA work-item queue
@@ -66,7 +65,6 @@ struct SplitK {
     long long n_pad;      // row stride of a partial matrix
     long long split_stride;   // m_pad * n_pad
     int splits;
-    int epi_prefetch;     // L2 prefetch of the operands the epilogue reads (see the epilogue warps); KLAB_GEMM_EPI_PREFETCH=0 -> off
 };
 
 // Epilogue modes of the kernel.  EPI_STORE is the generic fused epilogue (gemm.cuh).  The two CE modes turn the LM-head GEMM
@@ -309,38 +307,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             if constexpr (CTA2) mbar_arrive_leader(bar);
             else mbar_arrive(bar);
         };
-        // Operands the epilogue READS once per output element (saved activation, residual, the output itself when accumulating)
-        // arrive through dependent per-chunk loads: one 32-byte request per thread in flight, i.e. 16 KiB per SM per HBM round
-        // trip, so a 128 x 256 tile with a bf16 aux operand (64 KiB) costs four serial DRAM latencies -- ~9 us per tile where the
-        // K <= 1024 main loop needs 2-6 us (profiles/r02_gemm_top_ncu.txt: 25-47 % tensor pipe on exactly those signatures).
-        // Every thread therefore asks L2 for its row's lines of the whole tile up front (thread of chunk quarter q: lines q, q + 4,
-        // ...), with the static schedule one item AHEAD; the chunk loop's loads then hit L2.
-        const bool epi_reads = EPI == EPI_STORE && splits == 1 && sk.epi_prefetch != 0 &&
-                               ((epi.aux_in != nullptr && epi.act >= KLAB_ACT_RELU_BWD) || epi.residual != nullptr || epi.accumulate);
-        auto prefetch_item = [&](int it) {
-            const long long prow = static_cast<long long>(it / num_n) * TM + rank * BM + sub * 32 + lane;
-            const int pn0 = (it % num_n) * BN;
-            const int cols = prow < M ? min(BN, N - pn0) : 0;
-            const int o0 = quarter * 128;                          // a tile row is at most 256 fp32 = 8 lines: two per thread
-            if (epi.aux_in && epi.act >= KLAB_ACT_RELU_BWD) {       // (aux_in is read by the activation-backward modes only)
-                const int es = epi.aux_in_dtype == KLAB_BF16 ? 2 : 4;
-                const char* p = reinterpret_cast<const char*>(epi.aux_in) + (prow * epi.ld_aux_in + pn0) * es + o0;
-                if (o0 < cols * es) prefetch_l2(p);
-                if (o0 + 512 < cols * es) prefetch_l2(p + 512);
-            }
-            if (epi.residual) {
-                const int es = epi.res_dtype == KLAB_BF16 ? 2 : 4;
-                const char* p = reinterpret_cast<const char*>(epi.residual) + (prow * epi.ldr + pn0) * es + o0;
-                if (o0 < cols * es) prefetch_l2(p);
-                if (o0 + 512 < cols * es) prefetch_l2(p + 512);
-            }
-            if (epi.accumulate) {
-                const int es = epi.out_dtype == KLAB_BF16 ? 2 : 4;
-                const char* p = reinterpret_cast<const char*>(D) + (prow * ldd + pn0) * es + o0;
-                if (o0 < cols * es) prefetch_l2(p);
-                if (o0 + 512 < cols * es) prefetch_l2(p + 512);
-            }
-        };
         int acc = 0;
         uint32_t acc_phase = 0;
         int sq = 0;
@@ -360,10 +326,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                 if (item < 0) break;
             } else if (item >= num_items) {
                 break;
-            }
-            if (epi_reads) {
-                if (sched || item == work_id) prefetch_item(item);                       // (dynamic distribution: the next item is not known yet)
-                if (!sched && item + work_stride < num_items) prefetch_item(item + work_stride);
             }
             const int tile = item / splits, split = item - tile * splits;
             const int m0 = (tile / num_n) * TM + rank * BM;
@@ -557,8 +519,25 @@ Workspace* get_workspace(cudaStream_t stream) {
     return &w;
 }
 
+// Dynamic shared memory of a GEMM CTA (KLAB_GEMM_SMEM_KB, 100..227, default 225).  An SM has 228 KiB and every resident CTA reserves
+// 1 KiB, so at 227 KiB NOTHING else -- not even a kernel without shared memory on another stream -- can share an SM with a GEMM CTA;
+// at 225 KiB a small streaming kernel (the fused Adam on its side stream, optim.py) fits next to it.  Measured on workload 2a:
+// 59.76 ms per step at 227, 59.20 at 225, 59.14 at 221; the GEMM family itself is unchanged (the CTA-pair kernel keeps 6 instead of
+// 7 stages of 32 KiB).
+int smem_bytes() {
+    static const int v = []() {
+        const char* e = getenv("KLAB_GEMM_SMEM_KB");
+        int kb = e ? atoi(e) : 225;
+        if (kb < 100) kb = 100;
+        if (kb > 227) kb = 227;
+        return kb * 1024;
+    }();
+    return v;
+}
+
 int stages_for(int bn_local) {                                // bn_local: B rows staged per CTA (BN, or BN / 2 in a CTA pair)
-    const int s = RING_BYTES / (A_TILE_BYTES + bn_local * BK * 2);
+    const int ring = smem_bytes() - 1024 /*align slack*/ - CTRL_BYTES;
+    const int s = ring / (A_TILE_BYTES + bn_local * BK * 2);
     return s > MAX_STAGES ? MAX_STAGES : s;
 }
 
@@ -659,12 +638,11 @@ int launch_cfg(cudaStream_t stream, int M, int N, int K, int bn, int splits, Wor
     auto kern = gemm_bf16_tc_kernel<A_MN, B_MN, EPI, CTA2>;
     static bool attr_set = false;   // per instantiation
     if (!attr_set) {
-        KLAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        KLAB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_MAX));
         attr_set = true;
     }
     const int tiles = ((M + TM - 1) / TM) * ((N + bn - 1) / bn);
-    static const bool epi_pf = []() { const char* e = getenv("KLAB_GEMM_EPI_PREFETCH"); return !(e && e[0] == '0'); }();
-    SplitK sk{nullptr, 0, 0, splits, epi_pf ? 1 : 0};
+    SplitK sk{nullptr, 0, 0, splits};
     if (splits > 1) {
         const long long m_pad = 1ll * ((M + TM - 1) / TM) * TM, n_pad = 1ll * ((N + bn - 1) / bn) * bn;
         sk.ws = w->ws; sk.n_pad = n_pad; sk.split_stride = m_pad * n_pad;
@@ -678,7 +656,7 @@ int launch_cfg(cudaStream_t stream, int M, int N, int K, int bn, int splits, Wor
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.dynamicSmemBytes = smem_bytes();
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     int na = 0;

@@ -8,6 +8,7 @@
 //   g' = g + wd * p;  m = b1 m + (1 - b1) g';  v = b2 v + (1 - b2) g'^2;
 //   p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -16,7 +17,6 @@ void count_launch(int n = 1);
 namespace {
 
 constexpr int ADAM_CHUNK = 16384;     // elements per CTA
-constexpr int ADAM_THREADS = 256;
 
 struct AdamArgs {
     float lr, beta1, beta2, eps, weight_decay;
@@ -36,8 +36,12 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 }
 
 // table[t] = {p, g, m, v, bf16 copy (or 0), numel}; blockmap[b] = {tensor index, chunk index}
-__global__ void __launch_bounds__(ADAM_THREADS) adam_multi_kernel(const long long* __restrict__ table, const int* __restrict__ blockmap,
-                                                                  AdamArgs a) {
+// (<= 40 registers per thread, small blocks: a block then fits into what resident CTAs of the step's big kernels leave free on an SM
+//  -- 10 240 registers next to a tcgen05 GEMM CTA (576 threads x 96), ~7 000 next to two Swin attention CTAs -- so the update, issued
+//  on a side stream by optim.py, can make progress WHILE the next step's kernels run, not only in the gaps between them)
+template <int ADAM_THREADS>
+__global__ void __launch_bounds__(ADAM_THREADS, 1536 / ADAM_THREADS) adam_multi_kernel(const long long* __restrict__ table, const int* __restrict__ blockmap,
+                                                                                      AdamArgs a) {
     const int t = blockmap[2 * blockIdx.x], chunk = blockmap[2 * blockIdx.x + 1];
     const long long* e = table + 6ll * t;
     float* __restrict__ p = reinterpret_cast<float*>(e[0]);
@@ -106,7 +110,9 @@ int klab_adam_step(void* stream, const long long* table_dev, const int* blockmap
     a.lr = static_cast<float>(lr / (1.0 - pow(beta1, static_cast<double>(step))));      // step size lr / (1 - b1^t), formed in double
     a.inv_bc1 = 1.0f;
     a.inv_sqrt_bc2 = static_cast<float>(1.0 / sqrt(1.0 - pow(beta2, static_cast<double>(step))));
-    adam_multi_kernel<<<n_blocks, ADAM_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(table_dev, blockmap_dev, a);
+    static const int threads = []() { const char* e = getenv("KLAB_ADAM_THREADS"); return e && atoi(e) == 256 ? 256 : 128; }();
+    if (threads == 256) adam_multi_kernel<256><<<n_blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(table_dev, blockmap_dev, a);
+    else adam_multi_kernel<128><<<n_blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(table_dev, blockmap_dev, a);
     KLAB_LAUNCH_CHECK();
     count_launch();
     return KLAB_OK;

@@ -623,7 +623,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_fwd_tc1_kernel(const __
         const int jb = j0 - sub * Lk;                      // ... at key index jb of it
         const float* br = brel + (Lq - 1 - i) + jb;
         const bool bias_on = has_bias && row_ok && own;
-        const bool active = j0 < lk_pad;                   // warp-uniform
+        // warp-uniform: the warp's 32 keys exist, and at least one of its 32 rows is a query (cross-attention with 32 targets: one
+        // row-warp in four; the others used to run both softmax passes on padding rows)
+        const bool active = j0 < lk_pad && (warp & 3) * 32 < (G > 1 ? TILE : Lq);
         float sv[32];
         float mx = -INFINITY;
         if (active) {
@@ -677,7 +679,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_fwd_tc1_kernel(const __
         mbar_wait(&bars[2], mma_phase);
         mma_phase ^= 1;
         tc_fence_after();
-        if (cq < 2) {                                      // warps 0-3: output columns 0-31, warps 4-7: 32-63
+        if (cq < 2 && (warp & 3) * 32 < (G > 1 ? TILE : Lq)) {      // warps 0-3: output columns 0-31, warps 4-7: 32-63 (row-warps with queries)
             uint32_t ro[32];
             tmem_ld_32x32(trow + O_COL + cq * 32, ro);
             tmem_ld_wait();
@@ -840,7 +842,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_bwd_tc1_kernel(const __
         const int jb = j0 - sub * Lk;                      // ... at key index jb of it
         const int jmax = own ? (a.causal ? min(Lk, i + a.q_offset + 1) : Lk) : -(1 << 30);      // foreign keys: P = dS = 0
         const float* br = brel + (Lq - 1 - i) + jb;
-        const bool active = j0 < lk_pad;                   // warp-uniform
+        const bool active = j0 < lk_pad && (warp & 3) * 32 < lq_pad;      // warp-uniform: keys exist and the warp owns rows of the P / dS tiles
         // pass 1: P~ = P * dropout multiplier (what the forward multiplied into V) and the partial D_i = sum_j P~_ij dP_ij
         uint32_t keep = 0xFFFFFFFFu;                       // dropout keep bits of the 32 keys
         uint8_t* pb = sP + (j0 >> 6) * T;
@@ -889,7 +891,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_bwd_tc1_kernel(const __
         const float Di = (sred[r] + sred[TILE + r]) + (sred[2 * TILE + r] + sred[3 * TILE + r]);
         // pass 2: dS_ij = P_ij (m_ij dP_ij - D_i) with P = P~ / m on kept elements; dropped elements keep P_ij D_i, which needs the
         // un-dropped probability -> recompute it from S for those (rare: p = 0.1)
-        if (active && (warp & 3) * 32 < lq_pad) {           // warp-uniform (tcgen05.ld is warp-collective); stores are per lane
+        if (active) {                                       // warp-uniform (tcgen05.ld is warp-collective); stores are per lane
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
                 float dsv[16];
@@ -1002,14 +1004,352 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_bwd_tc1_kernel(const __
     }
 }
 
-// dtable[bucket, h] += sum_b partial[(b*H + h), bucket]      (one thread per (bucket, h); B is small)
-__global__ void t5_dbias_reduce_tc_kernel(const float* __restrict__ part, int B, int H, int nb, float* __restrict__ dtable) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nb * H) return;
-    const int bucket = idx / H, h = idx % H;
+// ------------------------------------------------------------------------------------------------------------------
+// Single-tile BACKWARD kernel, TWO CTAs PER SM (256 threads each).
+//
+// The 512-thread kernels above keep one problem per SM in flight, and one problem is a serial chain of latencies (TMA -> MMA ->
+// commit -> tcgen05.ld -> softmax -> st.shared -> fence -> MMA -> ...): profiles/r02_attn_ncu.txt shows >= 55 % of their warp
+// samples at CTA barriers / mbarrier waits.  This variant halves every per-CTA resource so that two CTAs are resident per SM
+// and one CTA's chain fills the other's bubbles:
+//   * 256 threads: TMEM lane (row) = (warp & 3) * 32 + lane, key half = warp >> 2, up to 64 keys per thread walked in 16-key
+//     chunks (chunks interleaved between the halves: 96 keys split 3 + 3); both passes read S and dP from TMEM;
+//   * operand tiles are as tall as the problem (rows padded to 16, not to 128) and SINGLE buffered; the loads of the CTA's next
+//     problem are issued the moment the gradient MMAs have retired, so they travel under the write-out and the next preamble;
+//     UMMA A operands always span 128 rows: rows past the tile are whatever follows in shared memory (the layout keeps those
+//     reads inside the allocation); they only reach TMEM lanes that are never read (an MMA row depends on its own A row only);
+//   * 256 TMEM columns per CTA: dV | dK | dQ overwrite S | dP once every thread has consumed them.
+// Measured (B = 64, H = 16, us per launch, this kernel | 512-thread kernel): 96 x 96 self-attention 84.9 | 87.2, 32 x 96
+// cross-attention 52.2 | 65.7 (profiles/r02_t5_attn_2cta.txt).  The same scheme for the FORWARD kernel was built and measured at
+// parity or worse (45.4 | 45.3, 41.1 | 42.1, 128 x 128: 57.4 | 53.8) and removed: with the same number of resident warps each
+// thread's serial share of a problem doubles, which cancels the overlap.  Used when the footprint allows two CTAs per SM
+// (<= 113 KiB: not the packed 128-row tiles); KLAB_T5_ATTN_2CTA=0 switches it off.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int S2_THREADS = 256;
+constexpr int S2_MAX_SMEM = 113 * 1024;
+
+struct S2Layout {
+    int tq, tk, nkb;          // bytes of a query-side tile (lq_pad rows), of a key-side tile (lk_pad rows), 64-key blocks of P / dS
+    int q, dO, dS, p, k, v;   // byte offsets of the tiles
+    int fl;                   // float scratch
+    int total;                // bytes to allocate (without the 1 KiB alignment slack)
+};
+
+__host__ __device__ inline S2Layout s2_layout(int lq_pad, int lk_pad) {
+    S2Layout L;
+    L.tq = lq_pad * 128;
+    L.tk = lk_pad * 128;
+    L.nkb = (lk_pad + 63) / 64;
+    // K-major A operands (128 rows are read whatever the tile height) first, so that the over-read lands in the tiles behind them
+    L.q = 0;                                                 // A of S = Q K^T
+    L.dO = L.q + L.tq;                                       // A of dP = dO V^T
+    L.dS = L.dO + L.tq;                                      // A of dQ = dS K: block b is read up to b * tq + 16 KiB
+    L.p = L.dS + L.nkb * L.tq;
+    L.k = L.p + L.nkb * L.tq;
+    L.v = L.k + L.tk;
+    L.fl = L.v + L.tk;
+    int o = L.fl + static_cast<int>(sizeof(float)) * (256 + 64 + 4 * TILE) + 128;    // brel | bins | [2][128] partial D (+ spare) | barriers, tmem pointer, next item
+    // P^T / dS^T are MN-major A operands with M = 128 keys = two 64-key blocks even when only one is stored: the second then reads
+    // the tq bytes behind the first
+    const int need1 = L.dS + (L.nkb - 1) * L.tq + TILE * 128, need2 = L.p + 2 * L.tq, need3 = L.dO + TILE * 128;
+    if (o < need1) o = need1;
+    if (o < need2) o = need2;
+    if (o < need3) o = need3;
+    L.total = o;
+    return L;
+}
+
+// TMEM: S 0.. | dP 128..  ->  dV 0..63 | dK 64..127 | dQ 128..191 (overwrite S / dP after the softmax backward)
+__global__ void __launch_bounds__(S2_THREADS, 2) t5_attn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmq, const __grid_constant__ CUtensorMap tmk,
+                                                                        const __grid_constant__ CUtensorMap tmv, const __grid_constant__ CUtensorMap tmdo,
+                                                                        TcArgs a, int lq_pad, int lk_pad) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + smem_align_pad(smem_raw);
+    const S2Layout L = s2_layout(lq_pad, lk_pad);
+    uint8_t* sQ = smem + L.q;
+    uint8_t* sdO = smem + L.dO;
+    uint8_t* sdS = smem + L.dS;
+    uint8_t* sP = smem + L.p;
+    uint8_t* sK = smem + L.k;
+    uint8_t* sV = smem + L.v;
+    float* brel = reinterpret_cast<float*>(smem + L.fl);         // [256] bias per relative position
+    float* bins = brel + 256;                                    // [64]
+    float* sred = bins + 64;                                     // [2][128] partial D_i
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sred + 4 * TILE);   // operands full, mma
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
+    int* s_next = reinterpret_cast<int*>(tmem_ptr + 1);
+    constexpr int TM_S = 0, TM_DP = 128, TM_DV = 0, TM_DK = 64, TM_DQ = 128;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r = (warp & 3) * 32 + lane, ch = warp >> 2;
+    const int Lq = a.Lq, Lk = a.Lk;
+    const int G = a.pack;
+    const int nprob = ((a.B + G - 1) / G) * a.H;
+
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tmem_alloc(tmem_ptr, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+    const uint32_t trow = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const uint64_t seed = a.seed + (a.seed_ptr ? *a.seed_ptr : 0ull);
+    const DropKey dkey = make_drop_key(seed, a.dropout_p);
+    const uint32_t id_s = umma_idesc_bf16(TILE, lk_pad, false, false);   // S / dP : A K-major, B K-major, N = lk_pad
+    const uint32_t id_t = umma_idesc_bf16(TILE, DK, true, true);         // dV / dK: A MN-major (P^T), B MN-major, N = 64
+    const uint32_t id_q = umma_idesc_bf16(TILE, DK, false, true);        // dQ     : A K-major (dS), B MN-major (K), N = 64
+    const int nqs = lq_pad / 16, nks = lk_pad / 16;
+    const bool has_bias = a.bias_table != nullptr;
+
+    auto issue_loads = [&](int bh) {
+        const int bg = bh / a.H, h = bh - bg * a.H, b = bg * G;
+        mbar_arrive_expect_tx(&bars[0], 2 * L.tq + 2 * L.tk);
+        tma_load_2d(sQ, &tmq, &bars[0], h * DK, b * Lq);
+        tma_load_2d(sdO, &tmdo, &bars[0], h * DK, b * Lq);
+        tma_load_2d(sK, &tmk, &bars[0], h * DK, b * Lk);
+        tma_load_2d(sV, &tmv, &bars[0], h * DK, b * Lk);
+    };
+    WorkClaim wc;
+    wc.init(a.sched);
+    int n1 = nprob, n2 = nprob;
+    if (tid == 0) {
+        const int first = wc.first();
+        *s_next = first;
+        if (first < nprob) {
+            issue_loads(first);
+            n1 = wc.claim();
+        }
+    }
+    __syncthreads();
+
+    uint32_t mma_phase = 0;
+    int it = 0;
+    for (int bh = *s_next; bh < nprob; ++it) {
+        const int h = bh % a.H, b = (bh / a.H) * G;
+        if (has_bias && tid < Lq + Lk - 1) {
+            const int rel = tid - (Lq - 1) - a.q_offset;
+            brel[tid] = a.bias_table[a.rel_bucket[rel + a.rel_zero] * a.H + h];
+        }
+        if (tid < 64) bins[tid] = 0.0f;
+        const int sub = G > 1 ? r / Lq : 0;                   // row r = query i of sub-problem `sub`
+        const int i = r - sub * Lq;
+        const bool row_ok = G > 1 ? b + sub < a.B : i < Lq;
+        const long long bh_row = static_cast<long long>(b + sub) * a.H + h;
+        const float lse = row_ok ? a.lse[bh_row * Lq + i] : 0.0f;
+        if (tid == 0) {
+            if (n1 < nprob) {
+                n2 = wc.claim();
+            } else {
+                wc.finish_begin();
+                n2 = nprob;
+            }
+            mbar_wait(&bars[0], it & 1);
+            tc_fence_after();
+            const uint32_t qa = smem_u32(sQ), doa = smem_u32(sdO), ka = smem_u32(sK), va = smem_u32(sV);
+#pragma unroll
+            for (int k = 0; k < DK / 16; ++k)
+                umma_bf16(tmem + TM_S, umma_smem_desc_sw128(qa + k * 32, 16, 1024), umma_smem_desc_sw128(ka + k * 32, 16, 1024), id_s, k != 0);
+#pragma unroll
+            for (int k = 0; k < DK / 16; ++k)
+                umma_bf16(tmem + TM_DP, umma_smem_desc_sw128(doa + k * 32, 16, 1024), umma_smem_desc_sw128(va + k * 32, 16, 1024), id_s, k != 0);
+            umma_commit(&bars[1]);
+        }
+        __syncthreads();                                   // brel / bins visible; every thread has read s_next (= bh)
+        mbar_wait(&bars[1], mma_phase);
+        mma_phase ^= 1;
+        tc_fence_after();
+        if (tid == 0) *s_next = n1;                        // read after the last barrier of this iteration
+
+        const int jmax_p = a.causal ? min(Lk, i + a.q_offset + 1) : Lk;
+        const float* br0 = brel + (Lq - 1 - i);
+        const bool lanes_live = (warp & 3) * 32 < lq_pad;  // warp-uniform: this warp owns at least one row of the P / dS tiles
+        // pass 1: P~ = P * dropout multiplier (what the forward multiplied into V) and the partial D_i = sum_j P~_ij dP_ij
+        unsigned long long keep = ~0ull;                   // dropout keep bits of this thread's 64 keys
+        float Dp = 0.0f;
+#pragma unroll 1
+        for (int c = 0; c < (lanes_live ? 4 : 0); ++c) {
+            const int j0 = (2 * c + ch) * 16;                // tile column of the chunk (warp-uniform); halves interleaved: balanced for 96 keys
+            if (j0 >= lk_pad) break;
+            const bool own = G == 1 || j0 / Lk == sub;      // the 16 keys lie inside one problem (Lk is 32 or 64 when packed) ...
+            const int jb = j0 - sub * Lk;                   // ... at key index jb of it
+            const int jmax = own ? jmax_p : -(1 << 30);     // foreign keys: P = dS = 0
+            uint32_t kbits = 0xFFFFu;
+            if (dkey.on) {
+                const uint64_t base = (static_cast<uint64_t>(bh_row) * Lq + i) * Lk + (own ? jb : 0);
+                kbits = 0;
+                if ((base & 1) == 0) {
+#pragma unroll
+                    for (int t = 0; t < 16; t += 2) {
+                        const uint32_t hsh = drop_hash_pair(dkey, (base + t) >> 1);
+                        kbits |= ((hsh & 0xFFFFu) < dkey.thr16 ? 1u : 0u) << t;
+                        kbits |= ((hsh >> 16) < dkey.thr16 ? 1u : 0u) << (t + 1);
+                    }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) kbits |= (dropout_mult(dkey, base + t) != 0.0f ? 1u : 0u) << t;
+                }
+                keep = (keep & ~(0xFFFFull << (c * 16))) | (static_cast<unsigned long long>(kbits) << (c * 16));
+            }
+            uint32_t rs[16], rp[16];
+            tmem_ld_32x16(trow + TM_S + j0, rs);
+            tmem_ld_32x16(trow + TM_DP + j0, rp);
+            tmem_ld_wait();
+            float pm[16];                                  // P~
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                const int j = jb + t;
+                float p = 0.0f;
+                if (row_ok && j < jmax) {
+                    p = __expf(__uint_as_float(rs[t]) + (has_bias ? br0[j] : 0.0f) - lse);
+                    p = (kbits >> t) & 1u ? p * dkey.inv_keep : 0.0f;
+                    Dp = fmaf(p, __uint_as_float(rp[t]), Dp);
+                }
+                pm[t] = p;
+            }
+            if (r < lq_pad) st_tile16(sP + (j0 >> 6) * L.tq, r, (j0 & 63) >> 4, pm);
+        }
+        sred[ch * TILE + r] = Dp;
+        __syncthreads();
+        const float Di = sred[r] + sred[TILE + r];
+        // pass 2: dS_ij = P_ij (m_ij dP_ij - D_i); dropped elements keep -P_ij D_i with the UN-dropped probability, recomputed from S
+        if (lanes_live) {
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int j0 = (2 * c + ch) * 16;
+                if (j0 >= lk_pad) break;
+                const bool own = G == 1 || j0 / Lk == sub;
+                const int jb = j0 - sub * Lk;
+                const int jmax = own ? jmax_p : -(1 << 30);
+                const uint32_t kbits = static_cast<uint32_t>(keep >> (c * 16)) & 0xFFFFu;
+                uint32_t rs[16], rp[16];
+                tmem_ld_32x16(trow + TM_S + j0, rs);
+                tmem_ld_32x16(trow + TM_DP + j0, rp);
+                tmem_ld_wait();
+                float dsv[16];
+#pragma unroll
+                for (int t = 0; t < 16; ++t) {
+                    const int j = jb + t;
+                    float ds = 0.0f;
+                    if (row_ok && j < jmax) {
+                        const bool kept = (kbits >> t) & 1u;
+                        const float pr = __expf(__uint_as_float(rs[t]) + (has_bias ? br0[j] : 0.0f) - lse);
+                        ds = pr * ((kept ? __uint_as_float(rp[t]) * dkey.inv_keep : 0.0f) - Di);
+                    }
+                    dsv[t] = ds;
+                }
+                if (r < lq_pad) st_tile16(sdS + (j0 >> 6) * L.tq, r, (j0 & 63) >> 4, dsv);
+            }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();                                   // every thread is done with S / dP in TMEM: the gradients may overwrite them
+        tc_fence_after();
+        if (tid == 0) {
+            const uint32_t pa = smem_u32(sP), dsa = smem_u32(sdS);
+            const uint32_t qa = smem_u32(sQ), doa = smem_u32(sdO), ka = smem_u32(sK);
+            // dV = P~^T dO ; dK = dS^T Q : M = 128 keys (MN-major A: the two 64-key blocks are tq bytes apart), contraction over lq_pad queries
+            for (int ks = 0; ks < nqs; ++ks) {
+                umma_bf16(tmem + TM_DV, umma_smem_desc_sw128(pa + ks * 2048, L.tq, 1024), umma_smem_desc_sw128(doa + ks * 2048, 8192, 1024), id_t, ks != 0);
+                umma_bf16(tmem + TM_DK, umma_smem_desc_sw128(dsa + ks * 2048, L.tq, 1024), umma_smem_desc_sw128(qa + ks * 2048, 8192, 1024), id_t, ks != 0);
+            }
+            // dQ = dS K : A K-major (64-key blocks tq bytes apart), B = K MN-major, contraction over lk_pad keys
+            for (int ks = 0; ks < nks; ++ks)
+                umma_bf16(tmem + TM_DQ, umma_smem_desc_sw128(dsa + (ks >> 2) * L.tq + (ks & 3) * 32, 16, 1024),
+                          umma_smem_desc_sw128(ka + ks * 2048, 8192, 1024), id_q, ks != 0);
+            umma_commit(&bars[1]);
+        }
+        // bias gradient, overlapped with the MMAs: sum the dS tile along its diagonals (j - i = const); thread t owns diagonal t
+        if (has_bias && tid < 2 * TILE - 1) {
+            const int dd = tid;                               // j - i + 127
+            const int lo = max(0, TILE - 1 - dd), hi = min(min(TILE - 1, 2 * TILE - 2 - dd), (G > 1 ? TILE : Lq) - 1);
+            float acc4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            auto elem = [&](int il) -> float {
+                const int jl = il + dd - (TILE - 1);
+                return jl < lk_pad ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sdS + (jl >> 6) * L.tq + sw128(il, jl & 63))) : 0.0f;
+            };
+            int il = lo;
+            for (; il + 3 <= hi; il += 4) {
+                acc4[0] += elem(il);
+                acc4[1] += elem(il + 1);
+                acc4[2] += elem(il + 2);
+                acc4[3] += elem(il + 3);
+            }
+            for (; il <= hi; ++il) acc4[0] += elem(il);
+            const float acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
+            const int rr = dd - (TILE - 1) + (Lq - 1);
+            if (rr >= 0 && rr < Lq + Lk - 1) atomicAdd(&bins[a.rel_bucket[rr - (Lq - 1) - a.q_offset + a.rel_zero]], acc);
+        }
+        mbar_wait(&bars[1], mma_phase);
+        mma_phase ^= 1;
+        tc_fence_after();
+        if (tid == 0 && n1 < nprob) issue_loads(n1);       // the gradient MMAs have retired: all four operand tiles are free
+        // write-out (row = TMEM lane): key half 0 stores columns 0..31 of dq, dk, dv, half 1 columns 32..63
+#pragma unroll 1
+        for (int which = 0; which < 3; ++which) {
+            const int rows = which == 0 ? Lq : Lk;
+            const int rows_ok = G > 1 ? min(TILE, (a.B - b) * rows) : rows;      // valid rows of the tile
+            const uint32_t col = which == 0 ? TM_DQ : (which == 1 ? TM_DK : TM_DV);
+            __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(which == 0 ? a.dq : (which == 1 ? a.dk : a.dv));
+            const long long ld = which == 0 ? a.ldq : (which == 1 ? a.ldk : a.ldv);
+            uint32_t ro[32];
+            tmem_ld_32x32(trow + col + ch * 32, ro);
+            tmem_ld_wait();
+            if (r < rows_ok) {
+                uint4* dst = reinterpret_cast<uint4*>(base + (static_cast<long long>(b) * rows + r) * ld + h * DK + ch * 32);
+#pragma unroll
+                for (int gq = 0; gq < 4; ++gq) {
+                    uint4 q;
+                    q.x = pack_bf16(__uint_as_float(ro[8 * gq]), __uint_as_float(ro[8 * gq + 1]));
+                    q.y = pack_bf16(__uint_as_float(ro[8 * gq + 2]), __uint_as_float(ro[8 * gq + 3]));
+                    q.z = pack_bf16(__uint_as_float(ro[8 * gq + 4]), __uint_as_float(ro[8 * gq + 5]));
+                    q.w = pack_bf16(__uint_as_float(ro[8 * gq + 6]), __uint_as_float(ro[8 * gq + 7]));
+                    dst[gq] = q;
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();                                   // TMEM, sP / sdS, brel / bins are reused by the next problem
+        tc_fence_after();
+        // partial bias gradient of the tile: into the slot of its first (batch, head); the other packed problems' slots get zeros
+        if (has_bias && tid < a.num_buckets) {
+            for (int g = 0; g < G && b + g < a.B; ++g)
+                a.dbias_partial[(static_cast<long long>(b + g) * a.H + h) * a.num_buckets + tid] = g == 0 ? bins[tid] : 0.0f;
+        }
+        bh = *s_next;
+        n1 = n2;
+    }
+    if (tid == 0) wc.finish_end();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 256);
+    }
+}
+
+bool two_cta_enabled() {
+    static const bool on = []() { const char* e = getenv("KLAB_T5_ATTN_2CTA"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
+// dtable[bucket, h] += sum_b partial[(b*H + h), bucket]: one WARP per (bucket, h), lanes stride over the batch, shuffle reduction
+// (fixed order: deterministic).  One thread per output with a serial loop over B = 64 cost 12.5 us per launch -- pure dependent-load
+// latency on the backward critical path, 48 launches per step.
+__global__ void __launch_bounds__(256) t5_dbias_reduce_tc_kernel(const float* __restrict__ part, int B, int H, int nb, float* __restrict__ dtable) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= nb * H) return;                                 // (warp-uniform)
+    const int bucket = w / H, h = w % H;
     float s = 0.0f;
-    for (int b = 0; b < B; ++b) s += part[(static_cast<long long>(b) * H + h) * nb + bucket];
-    dtable[idx] += s;
+    for (int b = lane; b < B; b += 32) s += part[(static_cast<long long>(b) * H + h) * nb + bucket];
+    s = warp_sum(s);
+    if (lane == 0) dtable[w] += s;
 }
 
 // Problems per 128-row tile of the single-tile kernels: self-attention shapes whose length divides the tile (the 32 keys a
@@ -1106,6 +1446,36 @@ int t5_attention_bwd_tc(cudaStream_t st, int B, int H, int Lq, int Lk, const voi
     a.bias_table = bias_table; a.rel_bucket = rel_bucket; a.rel_zero = rel_zero; a.num_buckets = num_buckets; a.causal = causal;
     a.q_offset = q_offset; a.lse = const_cast<float*>(lse); a.dropout_p = dropout_p; a.seed = seed; a.seed_ptr = seed_ptr;
     a.dbias_partial = static_cast<float*>(workspace);
+    if (Lq <= TILE && Lk <= TILE && num_buckets <= 64 && !getenv("KLAB_T5_ATTN_MULTI") && two_cta_enabled()) {
+        const int pack = pack_factor(Lq, Lk, q_offset);
+        const int lqp = pack > 1 ? TILE : (Lq + 15) / 16 * 16, lkp = pack > 1 ? TILE : (Lk + 15) / 16 * 16;
+        const S2Layout l2 = s2_layout(lqp, lkp);
+        if (l2.total + 1024 <= S2_MAX_SMEM) {                                    // two CTAs per SM (tiles as tall as the problem)
+            if (int rc = make_head_map(&tq, q, 1ll * B * Lq, H, ldq, lqp)) return rc;
+            if (int rc = make_head_map(&tk, k, 1ll * B * Lk, H, ldk, lkp)) return rc;
+            if (int rc = make_head_map(&tv, v, 1ll * B * Lk, H, ldv, lkp)) return rc;
+            if (int rc = make_head_map(&tdo, dout, 1ll * B * Lq, H, ldo, lqp)) return rc;
+            static bool set2 = false;
+            if (!set2) {
+                KLAB_CHECK_CUDA(cudaFuncSetAttribute(t5_attn_bwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_MAX_SMEM));
+                set2 = true;
+            }
+            a.pack = pack;
+            const int nprob = ((B + pack - 1) / pack) * H;
+            a.sched = sched_slot(st);
+            const int slots = 2 * (a.sched ? sm_count_physical() : sm_count());
+            t5_attn_bwd_tc2_kernel<<<nprob < slots ? nprob : slots, S2_THREADS, l2.total + 1024, st>>>(tq, tk, tv, tdo, a, lqp, lkp);
+            KLAB_LAUNCH_CHECK();
+            count_launch();
+            if (bias_table && dbias_table) {
+                const int n = num_buckets * H;
+                t5_dbias_reduce_tc_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(a.dbias_partial, B, H, num_buckets, dbias_table);
+                KLAB_LAUNCH_CHECK();
+                count_launch();
+            }
+            return KLAB_OK;
+        }
+    }
     if (Lq <= TILE && Lk <= TILE && num_buckets <= 64 && !getenv("KLAB_T5_ATTN_MULTI")) {      // persistent single-tile kernel
         const size_t smem1 = 1024 + 12 * TILE * 128 + sizeof(float) * (256 + 256 + 64 + 4 * TILE) + 64;
         static bool set1 = false;
@@ -1123,7 +1493,7 @@ int t5_attention_bwd_tc(cudaStream_t st, int B, int H, int Lq, int Lk, const voi
         count_launch();
         if (bias_table && dbias_table) {
             const int n = num_buckets * H;
-            t5_dbias_reduce_tc_kernel<<<(n + 127) / 128, 128, 0, st>>>(a.dbias_partial, B, H, num_buckets, dbias_table);
+            t5_dbias_reduce_tc_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(a.dbias_partial, B, H, num_buckets, dbias_table);
             KLAB_LAUNCH_CHECK();
             count_launch();
         }
@@ -1144,7 +1514,7 @@ int t5_attention_bwd_tc(cudaStream_t st, int B, int H, int Lq, int Lk, const voi
     count_launch();
     if (bias_table && dbias_table) {
         const int n = num_buckets * H;
-        t5_dbias_reduce_tc_kernel<<<(n + 127) / 128, 128, 0, st>>>(a.dbias_partial, B, H, num_buckets, dbias_table);
+        t5_dbias_reduce_tc_kernel<<<(n * 32 + 255) / 256, 256, 0, st>>>(a.dbias_partial, B, H, num_buckets, dbias_table);
         KLAB_LAUNCH_CHECK();
         count_launch();
     }
