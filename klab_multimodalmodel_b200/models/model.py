@@ -27,7 +27,7 @@ from .. import functional as Fn
 from ..generation import greedy_generate
 from ..graphs import POOL
 from ..modeling import Swinv2Model, T5EncoderModel, T5ForConditionalGeneration, _compute_dtype, advance_step_seed
-from ..optim import wait_pending_updates
+from ..optim import allow_overlap, wait_pending_updates
 
 
 class MyModel(nn.Module):
@@ -40,6 +40,9 @@ class MyModel(nn.Module):
         self.image_model = Swinv2Model.from_pretrained(args.image_model_name).requires_grad_(args.image_model_train)
 
         self.transformer = T5ForConditionalGeneration.from_pretrained(args.transformer_model_name)
+        # forward() reads these only after wait_pending_updates(): an optimizer over exactly them (train.py:28) may run its update
+        # on a side stream, under the towers of the next step
+        allow_overlap(self.transformer.parameters())
         self.compute_dtype = _compute_dtype(getattr(args, "compute_dtype", None))
         self._klab_reducer = None
         self._tower_streams = {}

@@ -10,6 +10,7 @@ sm_100 device.
 from __future__ import annotations
 
 import os
+import weakref
 
 import torch
 
@@ -24,6 +25,24 @@ from . import _lib as L
 OVERLAP = os.environ.get("KLAB_ADAM_OVERLAP", "1") != "0"
 _SIDE: dict = {}
 _DONE: dict = {}
+# Parameters whose owner has declared that it waits (wait_pending_updates) before it reads them: only a step made of such
+# parameters alone may leave the compute stream.  An optimizer built over anything else -- say over model.parameters(), image
+# tower included, whose forward runs BEFORE the wait -- stays on the current stream, as torch.optim.Adam would.
+_OVERLAP_SAFE: dict = {}
+
+
+def allow_overlap(params) -> None:
+    """Called by a model for the parameters it only reads after `wait_pending_updates()` (MyModel: the trainable transformer)."""
+    for p in params:
+        _OVERLAP_SAFE[id(p)] = weakref.ref(p)
+
+
+def _overlap_ok(params) -> bool:
+    for p in params:
+        r = _OVERLAP_SAFE.get(id(p))
+        if r is None or r() is not p:
+            return False
+    return True
 
 
 def wait_pending_updates(device=None) -> None:
@@ -122,7 +141,7 @@ class Adam(torch.optim.Optimizer):
                 table, blockmap, nblocks = self._table((gi, len(by_step) > 1 and t), items)
                 dev = items[0][0].device
                 main = torch.cuda.current_stream(dev)
-                if OVERLAP and self.overlap:
+                if OVERLAP and self.overlap and _overlap_ok(it[0] for it in items):
                     side = _SIDE.get(dev.index)
                     if side is None:
                         side = _SIDE[dev.index] = torch.cuda.Stream(dev)

@@ -209,7 +209,10 @@ def test_norm_grouped_output():
                                                ("enc", 2, 2, 96, 96, 64), ("enc", 1, 2, 176, 176, 64), ("dec", 2, 2, 130, 130, 64),
                                                ("cross", 1, 2, 32, 200, 64), ("cross", 2, 1, 150, 96, 64), ("dec", 3, 2, 32, 32, 64),
                                                # packed single-tile path: 128 / L problems per tile, partial last tile, both mask kinds
-                                               ("enc", 9, 2, 32, 32, 64), ("dec", 8, 3, 32, 32, 64), ("dec", 5, 3, 64, 64, 64), ("enc", 2, 2, 64, 64, 64)])
+                                               ("enc", 9, 2, 32, 32, 64), ("dec", 8, 3, 32, 32, 64), ("dec", 5, 3, 64, 64, 64), ("enc", 2, 2, 64, 64, 64),
+                                               # backward kernel choice: 32 x 96 (decoder cross-attention of workload 2a) and 96 x 96 take the two-CTA-per-SM
+                                               # kernel, 128 x 128 / 120 x 100 do not fit twice per SM and take the 512-thread kernel unpacked
+                                               ("cross", 3, 2, 32, 96, 64), ("enc", 2, 2, 128, 128, 64), ("cross", 3, 2, 120, 100, 64), ("dec", 2, 2, 113, 113, 64)])
 def test_t5_attention(dtype, mode, B, H, Lq, Lk, dk):
     o = ops()
     dims = ot5.T5Dims(num_heads=H, d_kv=dk)
@@ -469,6 +472,42 @@ def test_fused_adam_refreshes_bf16_operands():
         p.grad = torch.randn_like(p)
     topt.step()
     assert torch.equal(cache.get(ps[:3], torch.bfloat16), torch.cat([p.detach() for p in ps[:3]]).bfloat16())
+
+
+def test_fused_adam_side_stream_only_for_declared_parameters():
+    """The update leaves the compute stream only when EVERY parameter of the step was declared by its owner with allow_overlap()
+    (MyModel: the trainable transformer, which forward() reads after wait_pending_updates()).  Anything else -- a plain tensor
+    list, an optimizer over model.parameters() -- runs on the current stream like torch.optim.Adam; either way the values a
+    consumer sees after wait_pending_updates() are the updated ones."""
+    from klab_multimodalmodel_b200 import optim as KO
+    torch.manual_seed(3)
+    ps = [torch.randn(300, 257, device="cuda").requires_grad_() for _ in range(4)]
+    ref = [p.detach().clone().requires_grad_() for p in ps]
+    oa, ob = KO.Adam(ps, lr=1e-2), torch.optim.Adam(ref, lr=1e-2)
+
+    def one_step():
+        for p, r in zip(ps, ref):
+            p.grad = torch.randn_like(p)
+            r.grad = p.grad.clone()
+        oa.step(); ob.step()
+
+    KO._DONE.clear()
+    one_step()
+    assert not KO._DONE, "an optimizer over undeclared parameters must stay on the current stream"
+    KO.allow_overlap(ps[:3])
+    one_step()
+    assert not KO._DONE, "one undeclared parameter in the step keeps it on the current stream"
+    KO.allow_overlap(ps)
+    one_step()
+    if KO.OVERLAP:
+        assert KO._DONE, "all parameters declared: the update runs on the side stream"
+    one_step()                                                # a second update while the first is still pending: ordered
+    KO.wait_pending_updates(ps[0].device)
+    assert not KO._DONE
+    for p, r in zip(ps, ref):                                 # read on the compute stream after the wait
+        assert (p.detach() - r.detach()).abs().max().item() <= 1e-6 * max(1.0, r.detach().abs().max().item())
+    for p in ps:
+        KO._OVERLAP_SAFE.pop(id(p), None)
 
 
 def test_fused_adam_matches_torch_adam():
