@@ -62,6 +62,24 @@ __device__ __forceinline__ float drop_mult(const TcArgs& a, const DropKey& key, 
     return dropout_mult(key, idx);
 }
 
+// Bias gradient of the single-tile backward kernels: dBias[bucket(j - i)] += dS_ij, i.e. sums of the dS tile along its diagonals.
+// A warp holds a 32 x 16 block of dS in registers (lane = row, v[t] = column t of the chunk): lane m collects diagonal m (elements with
+// row <= column) and diagonal m - 32 (row > column) -- at step t it takes column t from lane (t - m) mod 32, every element is taken by
+// exactly one lane -- and adds the two sums to drel[], indexed by tile column - tile row + 127.  16 shuffles per chunk, no shared-memory
+// reads.  (The sums used to be formed after the fact by one thread per diagonal walking the swizzled bf16 dS tile: 30 % of the
+// kernel's executed instructions, and the longest diagonals set the critical path -- profiles/r02_t5_attn_final_ncu.txt.)
+__device__ __forceinline__ void diag_accumulate16(float* drel, const float (&v)[16], int dd0, int lane) {
+    float acc_p = 0.0f, acc_n = 0.0f;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const float x = __shfl_sync(0xffffffffu, v[t], (t - lane) & 31);
+        if (lane <= t) acc_p += x;
+        else acc_n += x;
+    }
+    if (lane < 16) atomicAdd(&drel[dd0 + lane], acc_p);
+    if (lane >= 1) atomicAdd(&drel[dd0 + lane - 32], acc_n);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // forward: grid (ceil(Lq/128), H, B), 128 threads; thread t owns query row q0 + t (TMEM lane t)
 // smem: Q 16K | K <=32K | V <=32K | P <=64K (k-blocks of 64 keys, 16K each) | brel | barriers
@@ -234,11 +252,12 @@ __global__ void __launch_bounds__(128) t5_attn_bwd_tc_kernel(const __grid_consta
     float* brel = reinterpret_cast<float*>(sdS + 2 * T);                     // [Lq + Lk] bias per relative position
     float* drel = brel + ((a.Lq + a.Lk + 3) & ~3);                           // [Lq + Lk] dS summed per relative position
     float* bins = drel + ((a.Lq + a.Lk + 3) & ~3);                           // [num_buckets] per-bucket sums
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bins + ((a.num_buckets + 3) & ~3));
+    float* dtile = bins + ((a.num_buckets + 3) & ~3);                        // [2][256] diagonal sums of the current dS tile (double buffered)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dtile + 512);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
 
     const int h = blockIdx.x, b = blockIdx.y, bh = b * a.H + h;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Lq = a.Lq, Lk = a.Lk;
     constexpr int TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;   // + 64 per query tile
 
@@ -268,6 +287,7 @@ __global__ void __launch_bounds__(128) t5_attn_bwd_tc_kernel(const __grid_consta
             brel[r] = a.bias_table[a.rel_bucket[rel + a.rel_zero] * a.H + h];
             drel[r] = 0.0f;
         }
+    for (int r = tid; r < 512; r += blockDim.x) dtile[r] = 0.0f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -312,8 +332,13 @@ __global__ void __launch_bounds__(128) t5_attn_bwd_tc_kernel(const __grid_consta
     const uint32_t id_t = umma_idesc_bf16(TILE, DK, true, true);         // dV / dK: A MN-major (P^T), B MN-major, N = 64
     const uint32_t id_q = umma_idesc_bf16(TILE, DK, false, true);        // dQ     : A K-major (dS), B MN-major (K), N = 64
 
+    int tile_no = 0;
     for (int kb = 0; kb < nk; ++kb) {
-        for (int qt = 0; qt < nq; ++qt) {
+        for (int qt = 0; qt < nq; ++qt, ++tile_no) {
+            // Diagonal sums of this dS tile (bias gradient), formed from the registers of the softmax backward (diag_accumulate16).
+            // Two buffers: a thread clears its two slots of buffer n & 1 after the barrier that ends tile n's softmax phase, and
+            // the buffer is written again only after the same barrier of tile n + 1.
+            float* dt = dtile + (tile_no & 1) * 256;
             if (tid == 0) {
                 const uint32_t qa = smem_u32(sQ + qt * T), doa = smem_u32(sdO + qt * T);
                 const uint32_t ka = smem_u32(sK + kb * T), va = smem_u32(sV + kb * T);
@@ -359,6 +384,13 @@ __global__ void __launch_bounds__(128) t5_attn_bwd_tc_kernel(const __grid_consta
                     st_tile8(pb, tid, ((c0 & 63) >> 3) + g, pv + 8 * g);
                     st_tile8(db, tid, ((c0 & 63) >> 3) + g, dsv + 8 * g);
                 }
+                if (has_bias) {
+                    float lo16[16], hi16[16];
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) { lo16[t] = dsv[t]; hi16[t] = dsv[16 + t]; }
+                    diag_accumulate16(dt, lo16, c0 - warp * 32 + (TILE - 1), lane);
+                    diag_accumulate16(dt, hi16, c0 + 16 - warp * 32 + (TILE - 1), lane);
+                }
             }
             fence_proxy_async_smem();
             tc_fence_before();
@@ -382,28 +414,15 @@ __global__ void __launch_bounds__(128) t5_attn_bwd_tc_kernel(const __grid_consta
                               umma_smem_desc_sw128(ka + ks * 2048, 8192, 1024), id_q, (kb | ks) != 0);
                 umma_commit(&bars[1]);
             }
-            // bias gradient, overlapped with the MMAs: sum the dS tile along its diagonals (j - i = const).  Thread t owns
-            // diagonals t and t + 128 of this tile, so the adds into drel[] are race free; at a fixed row the 32 lanes of a
-            // warp read 32 consecutive bf16 of that row (no bank conflicts) -- replaces 128 shared atomics per thread.
+            // bias gradient, overlapped with the MMAs: thread t moves diagonals t and t + 128 of this tile (j_local - i_local + 127)
+            // to their relative position in the problem; it is the only writer of those drel[] slots
             if (has_bias) {
+#pragma unroll
                 for (int half = 0; half < 2; ++half) {
-                    const int dd = tid + half * TILE;                 // j_local - i_local + 127
+                    const int dd = tid + half * TILE;
                     if (dd > 2 * TILE - 2) break;
-                    const int lo = max(0, TILE - 1 - dd), hi = min(TILE - 1, 2 * TILE - 2 - dd);
-                    float acc4[4] = {0.0f, 0.0f, 0.0f, 0.0f};            // independent partial sums: the loads overlap
-                    auto elem = [&](int il) -> float {
-                        const int jl = il + dd - (TILE - 1);
-                        return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sdS + (jl >> 6) * T + sw128(il, jl & 63)));
-                    };
-                    int il = lo;
-                    for (; il + 3 <= hi; il += 4) {
-                        acc4[0] += elem(il);
-                        acc4[1] += elem(il + 1);
-                        acc4[2] += elem(il + 2);
-                        acc4[3] += elem(il + 3);
-                    }
-                    for (; il <= hi; ++il) acc4[0] += elem(il);
-                    const float acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
+                    const float acc = dt[dd];
+                    dt[dd] = 0.0f;
                     const int r = dd - (TILE - 1) + (kb - qt) * TILE + (Lq - 1);
                     if (r >= 0 && r < Lq + Lk - 1) drel[r] += acc;
                 }
@@ -812,8 +831,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_bwd_tc1_kernel(const __
         if (has_bias && tid < Lq + Lk - 1) {
             const int rel = tid - (Lq - 1) - a.q_offset;
             brel[tid] = a.bias_table[a.rel_bucket[rel + a.rel_zero] * a.H + h];
-            drel[tid] = 0.0f;
         }
+        if (tid < 256) drel[tid] = 0.0f;                      // dS summed per diagonal (tile column - tile row + 127)
         if (tid < 64) bins[tid] = 0.0f;
         const int sub = G > 1 ? r / Lq : 0;                   // row r = query i of sub-problem `sub`
         const int i = r - sub * Lq;
@@ -911,6 +930,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_bwd_tc1_kernel(const __
                     dsv[t] = ds;
                 }
                 if (r < lq_pad) st_tile16(db, r, c16 + hf, dsv);
+                if (has_bias) diag_accumulate16(drel, dsv, j0 + hf * 16 - (warp & 3) * 32 + (TILE - 1), lane);
             }
         }
         fence_proxy_async_smem();
@@ -931,29 +951,11 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_bwd_tc1_kernel(const __
                           umma_smem_desc_sw128(ka + ks * 2048, 8192, 1024), id_q, ks != 0);
             umma_commit(&bars[2]);
         }
-        // bias gradient, overlapped with the MMAs: sum the dS tile along its diagonals (j - i = const); thread t owns diagonal t.
-        // At a fixed row the lanes of a warp read consecutive bf16 of that row (no bank conflicts).
+        // bias gradient, overlapped with the MMAs: diagonal sums (formed in pass 2, see diag_accumulate16) -> buckets
         if (has_bias && tid < 2 * TILE - 1) {
-            const int dd = tid;                               // j - i + 127
-            const int lo = max(0, TILE - 1 - dd), hi = min(min(TILE - 1, 2 * TILE - 2 - dd), (G > 1 ? TILE : Lq) - 1);
-            // four independent partial sums: the loads of a diagonal do not depend on one another, a single accumulator made
-            // this a chain of ~100 shared-memory latencies on the critical path behind the (much shorter) gradient MMAs
-            float acc4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            auto elem = [&](int il) -> float {
-                const int jl = il + dd - (TILE - 1);
-                return jl < lk_pad ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sdS + (jl >> 6) * T + sw128(il, jl & 63))) : 0.0f;
-            };
-            int il = lo;
-            for (; il + 3 <= hi; il += 4) {
-                acc4[0] += elem(il);
-                acc4[1] += elem(il + 1);
-                acc4[2] += elem(il + 2);
-                acc4[3] += elem(il + 3);
-            }
-            for (; il <= hi; ++il) acc4[0] += elem(il);
-            const float acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
-            const int rr = dd - (TILE - 1) + (Lq - 1);
-            if (rr >= 0 && rr < Lq + Lk - 1) atomicAdd(&bins[a.rel_bucket[rr - (Lq - 1) - a.q_offset + a.rel_zero]], acc);
+            const int rr = tid - (TILE - 1) + (Lq - 1);       // relative position j - i + (Lq - 1) of diagonal `tid`
+            const float acc = drel[tid];
+            if (rr >= 0 && rr < Lq + Lk - 1 && acc != 0.0f) atomicAdd(&bins[a.rel_bucket[rr - (Lq - 1) - a.q_offset + a.rel_zero]], acc);
         }
         mbar_wait(&bars[2], mma_phase);
         mma_phase ^= 1;
@@ -1074,6 +1076,7 @@ __global__ void __launch_bounds__(S2_THREADS, 2) t5_attn_bwd_tc2_kernel(const __
     float* brel = reinterpret_cast<float*>(smem + L.fl);         // [256] bias per relative position
     float* bins = brel + 256;                                    // [64]
     float* sred = bins + 64;                                     // [2][128] partial D_i
+    float* drel = sred + 2 * TILE;                               // [256] dS summed per diagonal (tile column - tile row + 127)
     uint64_t* bars = reinterpret_cast<uint64_t*>(sred + 4 * TILE);   // operands full, mma
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
     int* s_next = reinterpret_cast<int*>(tmem_ptr + 1);
@@ -1138,6 +1141,7 @@ __global__ void __launch_bounds__(S2_THREADS, 2) t5_attn_bwd_tc2_kernel(const __
             brel[tid] = a.bias_table[a.rel_bucket[rel + a.rel_zero] * a.H + h];
         }
         if (tid < 64) bins[tid] = 0.0f;
+        drel[tid] = 0.0f;                                     // (256 threads)
         const int sub = G > 1 ? r / Lq : 0;                   // row r = query i of sub-problem `sub`
         const int i = r - sub * Lq;
         const bool row_ok = G > 1 ? b + sub < a.B : i < Lq;
@@ -1245,6 +1249,7 @@ __global__ void __launch_bounds__(S2_THREADS, 2) t5_attn_bwd_tc2_kernel(const __
                     dsv[t] = ds;
                 }
                 if (r < lq_pad) st_tile16(sdS + (j0 >> 6) * L.tq, r, (j0 & 63) >> 4, dsv);
+                if (has_bias) diag_accumulate16(drel, dsv, j0 - (warp & 3) * 32 + (TILE - 1), lane);
             }
         }
         fence_proxy_async_smem();
@@ -1265,26 +1270,11 @@ __global__ void __launch_bounds__(S2_THREADS, 2) t5_attn_bwd_tc2_kernel(const __
                           umma_smem_desc_sw128(ka + ks * 2048, 8192, 1024), id_q, ks != 0);
             umma_commit(&bars[1]);
         }
-        // bias gradient, overlapped with the MMAs: sum the dS tile along its diagonals (j - i = const); thread t owns diagonal t
+        // bias gradient, overlapped with the MMAs: diagonal sums (formed in pass 2, see diag_accumulate16) -> buckets
         if (has_bias && tid < 2 * TILE - 1) {
-            const int dd = tid;                               // j - i + 127
-            const int lo = max(0, TILE - 1 - dd), hi = min(min(TILE - 1, 2 * TILE - 2 - dd), (G > 1 ? TILE : Lq) - 1);
-            float acc4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            auto elem = [&](int il) -> float {
-                const int jl = il + dd - (TILE - 1);
-                return jl < lk_pad ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sdS + (jl >> 6) * L.tq + sw128(il, jl & 63))) : 0.0f;
-            };
-            int il = lo;
-            for (; il + 3 <= hi; il += 4) {
-                acc4[0] += elem(il);
-                acc4[1] += elem(il + 1);
-                acc4[2] += elem(il + 2);
-                acc4[3] += elem(il + 3);
-            }
-            for (; il <= hi; ++il) acc4[0] += elem(il);
-            const float acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
-            const int rr = dd - (TILE - 1) + (Lq - 1);
-            if (rr >= 0 && rr < Lq + Lk - 1) atomicAdd(&bins[a.rel_bucket[rr - (Lq - 1) - a.q_offset + a.rel_zero]], acc);
+            const int rr = tid - (TILE - 1) + (Lq - 1);       // relative position j - i + (Lq - 1) of diagonal `tid`
+            const float acc = drel[tid];
+            if (rr >= 0 && rr < Lq + Lk - 1 && acc != 0.0f) atomicAdd(&bins[a.rel_bucket[rr - (Lq - 1) - a.q_offset + a.rel_zero]], acc);
         }
         mbar_wait(&bars[1], mma_phase);
         mma_phase ^= 1;
@@ -1501,7 +1491,7 @@ int t5_attention_bwd_tc(cudaStream_t st, int B, int H, int Lq, int Lk, const voi
     }
     const int nq = (Lq + TILE - 1) / TILE, nk = (Lk + TILE - 1) / TILE;
     const size_t smem = 1024 + static_cast<size_t>(2 * nq + 2 * nk + 4) * TILE * 128 + 2 * sizeof(float) * ((Lq + Lk + 3) & ~3) +
-                        sizeof(float) * ((num_buckets + 3) & ~3) + 64;
+                        sizeof(float) * (((num_buckets + 3) & ~3) + 512) + 64;
     KLAB_REQUIRE(smem <= 227 * 1024, "t5_attention_bwd_tc: %zu bytes of shared memory", smem);
     static size_t smem_set = 0;
     if (smem > smem_set) {

@@ -224,3 +224,28 @@ def test_true_resume_round_trip(tmp_path):
         assert torch.equal(opt_a.state[pa]["exp_avg"], opt_b.state[pb]["exp_avg"]) and opt_b.state[pb]["step"] == opt_a.state[pa]["step"]
     a.save("weights_only.pth")                                      # a weights-only file (the reference's writer) resumes with empty progress
     assert b.load_state("weights_only.pth") == {"epoch": None, "step": None}
+
+
+def test_optimizer_side_stream_registry():
+    """optim.allow_overlap / _overlap_ok: the fused Adam may leave the compute stream only when EVERY parameter of its step was
+    declared by its owner (MyModel declares the trainable transformer, whose weights forward() reads after wait_pending_updates());
+    a stale id of a freed parameter must not count."""
+    import gc
+
+    from klab_multimodalmodel_b200 import optim as KO
+    ps = [torch.nn.Parameter(torch.zeros(3)) for _ in range(3)]
+    assert not KO._overlap_ok(ps)
+    KO.allow_overlap(ps[:2])
+    assert KO._overlap_ok(ps[:2]) and not KO._overlap_ok(ps)
+    KO.allow_overlap(ps)
+    assert KO._overlap_ok(ps) and KO._overlap_ok(iter(ps))
+    stale = id(ps[2])
+    del ps[2]
+    gc.collect()
+    assert KO._OVERLAP_SAFE[stale]() is None                  # the weak reference died with the parameter
+    impostor = torch.nn.Parameter(torch.zeros(3))
+    KO._OVERLAP_SAFE[id(impostor)] = KO._OVERLAP_SAFE[stale]  # what an id reused by a new tensor would find
+    assert not KO._overlap_ok([impostor])
+    KO.wait_pending_updates(None)                              # nothing pending: a no-op without a GPU
+    for k in [id(p) for p in ps] + [stale, id(impostor)]:
+        KO._OVERLAP_SAFE.pop(k, None)

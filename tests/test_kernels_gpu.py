@@ -607,7 +607,8 @@ def test_fused_lmhead_cross_entropy(rows, V, d):
 # ------------------------------------------------------------------------------------------------ dynamic work distribution
 def test_dynamic_work_distribution_matches_static():
     """klab_set_dynamic_sched(1) (what the data-parallel reducer arms): the persistent GEMM and T5-attention kernels claim
-    work items from a per-launch counter.  Results must be bit-identical to the static stride, also when a launch has many
+    work items from a per-launch counter.  Results must be bit-identical to the static stride (the atomically reduced bias
+    gradient: to fp32 rounding), also when a launch has many
     more items than CTAs, uses split-K, is replayed from a CUDA graph (the last CTA re-arms the counter) and when far more
     launches than counter slots have been issued."""
     o, lib = ops(), L()
@@ -658,8 +659,11 @@ def test_dynamic_work_distribution_matches_static():
     lib.lib().klab_set_dynamic_sched(1)
     try:
         dyn = run_all()
-        for s_, d_ in zip(static, dyn):
+        for s_, d_ in zip(static[:-1], dyn[:-1]):
             assert torch.equal(s_, d_)
+        # the relative-position bias gradient is summed with shared-memory float atomics (diagonal sums of several warps meet in
+        # one slot; the order is not fixed), like the scatter-add of the reference's embedding backward: equal to fp32 rounding
+        assert (static[-1] - dyn[-1]).abs().max().item() <= 1e-5 * max(1.0, static[-1].abs().max().item())
         for rep in range(3):                               # counters re-armed by the last pair: repeated launches agree
             for s_, d_ in zip(static_pairs, run_pairs()):
                 assert torch.equal(s_, d_)
