@@ -252,12 +252,11 @@ __global__ void __launch_bounds__(128) t5_attn_bwd_tc_kernel(const __grid_consta
     float* brel = reinterpret_cast<float*>(sdS + 2 * T);                     // [Lq + Lk] bias per relative position
     float* drel = brel + ((a.Lq + a.Lk + 3) & ~3);                           // [Lq + Lk] dS summed per relative position
     float* bins = drel + ((a.Lq + a.Lk + 3) & ~3);                           // [num_buckets] per-bucket sums
-    float* dtile = bins + ((a.num_buckets + 3) & ~3);                        // [2][256] diagonal sums of the current dS tile (double buffered)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(dtile + 512);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bins + ((a.num_buckets + 3) & ~3));
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 4);
 
     const int h = blockIdx.x, b = blockIdx.y, bh = b * a.H + h;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
     const int Lq = a.Lq, Lk = a.Lk;
     constexpr int TM_S = 0, TM_DP = 128, TM_DV = 256, TM_DK = 320, TM_DQ = 384;   // + 64 per query tile
 
@@ -287,7 +286,6 @@ __global__ void __launch_bounds__(128) t5_attn_bwd_tc_kernel(const __grid_consta
             brel[r] = a.bias_table[a.rel_bucket[rel + a.rel_zero] * a.H + h];
             drel[r] = 0.0f;
         }
-    for (int r = tid; r < 512; r += blockDim.x) dtile[r] = 0.0f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -332,13 +330,8 @@ __global__ void __launch_bounds__(128) t5_attn_bwd_tc_kernel(const __grid_consta
     const uint32_t id_t = umma_idesc_bf16(TILE, DK, true, true);         // dV / dK: A MN-major (P^T), B MN-major, N = 64
     const uint32_t id_q = umma_idesc_bf16(TILE, DK, false, true);        // dQ     : A K-major (dS), B MN-major (K), N = 64
 
-    int tile_no = 0;
     for (int kb = 0; kb < nk; ++kb) {
-        for (int qt = 0; qt < nq; ++qt, ++tile_no) {
-            // Diagonal sums of this dS tile (bias gradient), formed from the registers of the softmax backward (diag_accumulate16).
-            // Two buffers: a thread clears its two slots of buffer n & 1 after the barrier that ends tile n's softmax phase, and
-            // the buffer is written again only after the same barrier of tile n + 1.
-            float* dt = dtile + (tile_no & 1) * 256;
+        for (int qt = 0; qt < nq; ++qt) {
             if (tid == 0) {
                 const uint32_t qa = smem_u32(sQ + qt * T), doa = smem_u32(sdO + qt * T);
                 const uint32_t ka = smem_u32(sK + kb * T), va = smem_u32(sV + kb * T);
@@ -384,13 +377,6 @@ __global__ void __launch_bounds__(128) t5_attn_bwd_tc_kernel(const __grid_consta
                     st_tile8(pb, tid, ((c0 & 63) >> 3) + g, pv + 8 * g);
                     st_tile8(db, tid, ((c0 & 63) >> 3) + g, dsv + 8 * g);
                 }
-                if (has_bias) {
-                    float lo16[16], hi16[16];
-#pragma unroll
-                    for (int t = 0; t < 16; ++t) { lo16[t] = dsv[t]; hi16[t] = dsv[16 + t]; }
-                    diag_accumulate16(dt, lo16, c0 - warp * 32 + (TILE - 1), lane);
-                    diag_accumulate16(dt, hi16, c0 + 16 - warp * 32 + (TILE - 1), lane);
-                }
             }
             fence_proxy_async_smem();
             tc_fence_before();
@@ -414,15 +400,28 @@ __global__ void __launch_bounds__(128) t5_attn_bwd_tc_kernel(const __grid_consta
                               umma_smem_desc_sw128(ka + ks * 2048, 8192, 1024), id_q, (kb | ks) != 0);
                 umma_commit(&bars[1]);
             }
-            // bias gradient, overlapped with the MMAs: thread t moves diagonals t and t + 128 of this tile (j_local - i_local + 127)
-            // to their relative position in the problem; it is the only writer of those drel[] slots
+            // bias gradient, overlapped with the MMAs: sum the dS tile along its diagonals (j - i = const).  Thread t owns
+            // diagonals t and t + 128 of this tile, so the adds into drel[] are race free; at a fixed row the 32 lanes of a
+            // warp read 32 consecutive bf16 of that row (no bank conflicts) -- replaces 128 shared atomics per thread.
             if (has_bias) {
-#pragma unroll
                 for (int half = 0; half < 2; ++half) {
-                    const int dd = tid + half * TILE;
+                    const int dd = tid + half * TILE;                 // j_local - i_local + 127
                     if (dd > 2 * TILE - 2) break;
-                    const float acc = dt[dd];
-                    dt[dd] = 0.0f;
+                    const int lo = max(0, TILE - 1 - dd), hi = min(TILE - 1, 2 * TILE - 2 - dd);
+                    float acc4[4] = {0.0f, 0.0f, 0.0f, 0.0f};            // independent partial sums: the loads overlap
+                    auto elem = [&](int il) -> float {
+                        const int jl = il + dd - (TILE - 1);
+                        return __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(sdS + (jl >> 6) * T + sw128(il, jl & 63)));
+                    };
+                    int il = lo;
+                    for (; il + 3 <= hi; il += 4) {
+                        acc4[0] += elem(il);
+                        acc4[1] += elem(il + 1);
+                        acc4[2] += elem(il + 2);
+                        acc4[3] += elem(il + 3);
+                    }
+                    for (; il <= hi; ++il) acc4[0] += elem(il);
+                    const float acc = (acc4[0] + acc4[1]) + (acc4[2] + acc4[3]);
                     const int r = dd - (TILE - 1) + (kb - qt) * TILE + (Lq - 1);
                     if (r >= 0 && r < Lq + Lk - 1) drel[r] += acc;
                 }
@@ -1491,7 +1490,7 @@ int t5_attention_bwd_tc(cudaStream_t st, int B, int H, int Lq, int Lk, const voi
     }
     const int nq = (Lq + TILE - 1) / TILE, nk = (Lk + TILE - 1) / TILE;
     const size_t smem = 1024 + static_cast<size_t>(2 * nq + 2 * nk + 4) * TILE * 128 + 2 * sizeof(float) * ((Lq + Lk + 3) & ~3) +
-                        sizeof(float) * (((num_buckets + 3) & ~3) + 512) + 64;
+                        sizeof(float) * ((num_buckets + 3) & ~3) + 64;
     KLAB_REQUIRE(smem <= 227 * 1024, "t5_attention_bwd_tc: %zu bytes of shared memory", smem);
     static size_t smem_set = 0;
     if (smem > smem_set) {
