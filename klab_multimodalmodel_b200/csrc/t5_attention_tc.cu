@@ -1019,8 +1019,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) t5_attn_bwd_tc1_kernel(const __
 //     UMMA A operands always span 128 rows: rows past the tile are whatever follows in shared memory (the layout keeps those
 //     reads inside the allocation); they only reach TMEM lanes that are never read (an MMA row depends on its own A row only);
 //   * 256 TMEM columns per CTA: dV | dK | dQ overwrite S | dP once every thread has consumed them.
-// Measured (B = 64, H = 16, us per launch, this kernel | 512-thread kernel): 96 x 96 self-attention 84.9 | 87.2, 32 x 96
-// cross-attention 52.2 | 65.7 (profiles/r02_t5_attn_2cta.txt).  The same scheme for the FORWARD kernel was built and measured at
+// Measured (B = 64, H = 16, us per launch, this kernel | 512-thread kernel): 96 x 96 self-attention 72.2 | 82.1, 32 x 96
+// cross-attention 52.8 | 66.2 (profiles/r02_t5_attn_2cta.txt).  The same scheme for the FORWARD kernel was built and measured at
 // parity or worse (45.4 | 45.3, 41.1 | 42.1, 128 x 128: 57.4 | 53.8) and removed: with the same number of resident warps each
 // thread's serial share of a problem doubles, which cancels the overlap.  Used when the footprint allows two CTAs per SM
 // (<= 113 KiB: not the packed 128-row tiles); KLAB_T5_ATTN_2CTA=0 switches it off.
